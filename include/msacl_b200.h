@@ -1,0 +1,193 @@
+/*
+ * msacl_b200 -- C ABI of the B200-native MSACL hot path (libmsacl_b200.so).
+ *
+ * The reference is pure Python and has no FFI; its "plugin API" is duck-typed Python
+ * (SURVEY.md section 8b).  Each entry point below therefore names the reference Python
+ * function whose arithmetic it replaces; the Python shims in the package
+ * (envs.py / sampler.py / buffer.py / targets.py) keep the reference's call signatures and
+ * forward to these symbols through ctypes.  INTEGRATION.md shows the binding.
+ *
+ * Conventions: all pointers are DEVICE pointers into caller-allocated, contiguous buffers
+ * (torch tensors) unless noted; nothing is allocated or synchronised inside; every call is
+ * stream-ordered on `stream` (a cudaStream_t passed as void*); return value 0 = success,
+ * negative = error (message via msacl_last_error()).  There is no CPU fallback.
+ */
+#ifndef MSACL_B200_H_
+#define MSACL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSACL_ABI_VERSION 1
+
+/* env ids: the fixed table of RL/env/make_env.py:19-32 */
+enum {
+  MSACL_ENV_VANDERPOL = 0,
+  MSACL_ENV_PENDULUM = 1,
+  MSACL_ENV_DUCTEDFAN = 2,
+  MSACL_ENV_TWOLINK = 3,
+  MSACL_ENV_SINGLETRACKCAR = 4,
+  MSACL_ENV_QUADTRACKING = 5,
+  MSACL_NUM_ENVS = 6
+};
+
+enum {
+  MSACL_OK = 0,
+  MSACL_ERR_BAD_ENV = -1,
+  MSACL_ERR_BAD_ARG = -2,
+  MSACL_ERR_CUDA = -3
+};
+
+/* Structure-of-arrays state of n env instances of one env type on one GPU.
+ * sf: float32 [sf_rows][stride]; sd: float64 [sd_rows][stride] (NULL when sd_rows == 0).
+ * Row counts / layout per env come from msacl_env_dims(). */
+typedef struct {
+  int32_t env_id;
+  int32_t max_step;      /* time limit (reference: 1000, e.g. RL/env/VanderPol.py:67) */
+  int64_t n;             /* env instances on this GPU */
+  int64_t stride;        /* row pitch in elements, >= n */
+  float* sf;
+  double* sd;
+  int32_t* step;         /* current_step per env */
+  int32_t* episode;      /* index of the current episode per env (keys the reset stream) */
+  float* ep_return;      /* running undiscounted return (RecordEpisodeStatistics) */
+  int32_t* ep_len;       /* running episode length */
+  int32_t* run;          /* n-step deque length, capped at n_step (sampler/base.py:95) */
+  uint64_t seed;         /* Philox key */
+  uint64_t env_base;     /* global id of local env 0 (multi-GPU sharding) */
+} msacl_env_state_t;
+
+/* dims[0]=obs_dim, [1]=act_dim, [2]=sf_rows, [3]=sd_rows, [4]=obs_offset (row of obs[0] in sf),
+ * [5]=control_step.  Host call.  Replaces the space probing of RL/utils/init_args.py:33-43. */
+int msacl_env_dims(int env_id, int32_t dims[6]);
+
+/* Host call: observation / action boxes, each float[obs_dim] / float[act_dim] HOST arrays
+ * (observation_space / action_space of the reference env classes). */
+int msacl_env_bounds(int env_id, float* obs_low, float* obs_high, float* act_low, float* act_high);
+
+/* env.reset() for every instance: episode[i] is used as the reset-stream index; step, run,
+ * ep_return, ep_len are zeroed.  Replaces <env>.reset (e.g. RL/env/VanderPol.py:69-86,
+ * RL/env/QuadTracking.py:152-202) with a Philox-keyed draw of the same distribution. */
+int msacl_env_reset(const msacl_env_state_t* st, void* stream);
+
+/* Recompute the QuadTracking hidden desired-frame state and observation from raw x,v,R,Omega
+ * already stored in sf (t := 0).  Used to inject initial states (tests, golden vectors). */
+int msacl_quad_init_from_raw(const msacl_env_state_t* st, void* stream);
+
+/* One vectorised env step with gymnasium-0.28.1 same-step autoreset.
+ * Replaces gymnasium.vector.SyncVectorEnv.step -> <env>.step (RL/env/ *.py::step) as called at
+ * RL/trainer/sampler/base.py:148.
+ *   action     [n][act_dim] (already clipped by the caller, as the reference does)
+ *   next_obs   [n][obs_dim] post-reset observation for done envs
+ *   reward     [n] raw env reward (float32)
+ *   terminated, truncated [n] (0/1)
+ *   final_obs  [n][obs_dim] pre-reset observation (info["final_observation"]) for every env */
+int msacl_env_step(const msacl_env_state_t* st, const float* action, float* next_obs, float* reward,
+                   uint8_t* terminated, uint8_t* truncated, float* final_obs, void* stream);
+
+/* Actor weights, StochaPolicy (RL/apprfunc/mlp.py:111-136) with hidden sizes [256,256]. */
+typedef struct {
+  const float* w1;   /* [256][obs_dim]  (torch nn.Linear weight layout) */
+  const float* b1;   /* [256] */
+  const float* w2t;  /* [256 in][256 out] = W2 transposed */
+  const float* b2;   /* [256] */
+  const float* w3;   /* [2*act_dim][256] */
+  const float* b3;   /* [2*act_dim] */
+  float min_log_std; /* -20 */
+  float max_log_std; /*   1 */
+} msacl_actor_t;
+
+/* Transition outputs of a K-step rollout, each [K][n][...] row-major.  Any pointer may be NULL
+ * to skip that field. */
+typedef struct {
+  float* obs;     /* [K][n][obs_dim]  observation the action was computed from */
+  float* act;     /* [K][n][act_dim]  clipped action */
+  float* rew;     /* [K][n]  reward * reward_scale */
+  float* cost;    /* [K][n]  sum(real_next_obs^2) * cost_scale */
+  float* obs2;    /* [K][n][obs_dim]  real_next_obs (pre-reset) */
+  uint8_t* done;  /* [K][n]  terminated | truncated */
+  float* logp;    /* [K][n]  log-prob of the sampled action */
+  uint8_t* emit;  /* [K][n]  1 iff the env's n-step deque is full after this transition */
+} msacl_transitions_t;
+
+/* Fused K-step rollout: actor forward + TanhGauss sample + clip + env step + reward/cost
+ * post-processing + autoreset + n-step run bookkeeping, state resident in registers.
+ * Replaces K iterations of BaseSampler._n_step (RL/trainer/sampler/base.py:118-163,220) incl.
+ * StochaPolicy.forward (mlp.py:132-136), TanhGaussDistribution.sample
+ * (act_distribution_cls.py:45-57) and rew_plus_cost (RL/utils/rew_plus_cost.py:18-21).
+ *   eps        optional [K][n][act_dim] explicit N(0,1) draws (tests); NULL -> Philox(seed,
+ *              env_base+i, step_base+k)
+ *   stats      optional double[8]: episodes, sum return, sum length, terminated, truncated,
+ *              sum scaled reward, sum cost, steps   (atomically accumulated)
+ *   deterministic != 0 -> action = mode() (act_distribution_cls.py:90-95; evaluator path) */
+int msacl_rollout_fused(const msacl_env_state_t* st, const msacl_actor_t* actor, int32_t K, uint32_t step_base,
+                        int32_t n_step, float reward_scale, float cost_scale, const float* eps,
+                        int32_t deterministic, const msacl_transitions_t* out, double* stats, void* stream);
+
+/* Fill out[n][act_dim] with the N(0,1) draws the rollout uses at global step `step`. */
+int msacl_action_noise(uint64_t seed, uint64_t env_base, int64_t n, int32_t act_dim, uint32_t step, float* out,
+                       void* stream);
+
+/* n-step replay ring, arrays [max_size][n_step][...] as RL/trainer/buffer/nstep_replay_buffer.py:52-67 */
+typedef struct {
+  int64_t max_size;
+  int32_t n_step, obs_dim, act_dim;
+  float* obs; float* act; float* rew; float* cost; float* obs2; float* done; float* logp;
+} msacl_ring_t;
+
+/* Assemble every emitted n-step window of a rollout chunk and store it in the ring in the
+ * reference's order (step-major, env-minor) starting at *ptr.  Replaces the deque logic of
+ * RL/trainer/sampler/base.py:178-217 plus NstepReplayBuffer.add_batch/store
+ * (nstep_replay_buffer.py:91-125).
+ *   tr        transitions of H + K steps: the first H = n_step-1 slices are the tail of the
+ *             previous chunk (history), the last K are new; emit flags of history are ignored
+ *   scratch   int64[2 + ceil(K*n/1024)] device scratch
+ *   ptr_size  device int64[2] = {ptr, size}, updated in place
+ *   count_out device int64[1]: number of windows stored by this call */
+int msacl_window_store(const msacl_transitions_t* tr, int32_t H, int32_t K, int64_t n, const msacl_ring_t* ring,
+                       int64_t* ptr_size, int64_t* count_out, int64_t* scratch, void* stream);
+
+/* batch[k] = ring[idx[k]] for all 7 fields ([B][n_step][...]); replaces
+ * NstepReplayBuffer.sample_batch's gather (nstep_replay_buffer.py:138-146). */
+int msacl_ring_gather(const msacl_ring_t* ring, const int64_t* idx, int64_t B, const msacl_ring_t* batch,
+                      void* stream);
+
+/* MSACL soft-TD backup (RL/algorithm/msacl.py:249-252), elementwise over B*n. */
+int msacl_q_backup(int64_t count, const float* rew, const float* done, const float* next_q1, const float* next_q2,
+                   const float* next_logp, float gamma, float alpha, float* backup, void* stream);
+
+/* Lyapunov risk forward + analytic backward (RL/algorithm/msacl.py:280-329).
+ *   obs, obs2 [B][n][D]; logp_new, logp_old, lya_obs, lya_obs2 [B][n]
+ *   coef_son / coef_diff / coef_sl: float[n] device (msacl.py:153-164)
+ *   loss_parts double[3] device, zeroed by the call: sum relu(a1|o|^2-V), sum relu(V-a2|o|^2),
+ *              sum_b sum_k lambda_k c_k relu(ESL (V(o2_k) - (1-eta)^(k+1) V(o_0)))
+ *   grad_lya_obs, grad_lya_obs2 [B][n]: d loss / d V  (loss = (p0+p1)/(B n) * pos_scale + p2/B * diff_scale)
+ *   is_clip, esl optional [B][n] outputs */
+int msacl_lyapunov_risk(int64_t B, int32_t n, int32_t D, const float* obs, const float* obs2, const float* logp_new,
+                        const float* logp_old, const float* lya_obs, const float* lya_obs2, const float* coef_son,
+                        const float* coef_diff, const float* coef_sl, float alpha1, float alpha2, float diff_scale,
+                        float pos_scale, double* loss_parts, float* grad_lya_obs, float* grad_lya_obs2,
+                        float* is_clip, float* esl, void* stream);
+
+/* Stability advantage (RL/algorithm/msacl.py:392-400): adv_raw[b] = sum_k lambda_k ((1-eta)^(k+1) V(o_0) - V(o2_k));
+ * moments double[2] device (zeroed by the call) receive sum and sum of squares for the batch
+ * normalisation, which msacl_advantage_normalize applies (unbiased std + 1e-8). */
+int msacl_stability_advantage(int64_t B, int32_t n, const float* lya_obs0, const float* lya_obs2,
+                              const float* coef_diff, const float* coef_sl, float* adv_raw, double* moments,
+                              void* stream);
+int msacl_advantage_normalize(int64_t B, const float* adv_raw, const double* moments, float* adv, void* stream);
+
+/* Device FP32 FFMA peak probe used by bench.py for the roofline denominator: runs
+ * `iters` dependent-free FFMA sweeps on every SM; returns FLOPs issued in *flops (host). */
+int msacl_ffma_probe(int32_t iters, float* sink, double* flops, void* stream);
+
+const char* msacl_last_error(void);
+int msacl_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSACL_B200_H_ */

@@ -1,0 +1,109 @@
+"""ctypes binding of csrc/libmsacl_b200.so (the C ABI declared in include/msacl_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc (build.py); if it
+cannot be built or loaded, importing the kernels raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_f32p = C.POINTER(C.c_float)
+c_f64p = C.POINTER(C.c_double)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+
+class EnvState(C.Structure):
+    _fields_ = [("env_id", C.c_int32), ("max_step", C.c_int32), ("n", C.c_int64), ("stride", C.c_int64),
+                ("sf", vp), ("sd", vp), ("step", vp), ("episode", vp), ("ep_return", vp), ("ep_len", vp),
+                ("run", vp), ("seed", C.c_uint64), ("env_base", C.c_uint64)]
+
+
+class Actor(C.Structure):
+    _fields_ = [("w1", vp), ("b1", vp), ("w2t", vp), ("b2", vp), ("w3", vp), ("b3", vp),
+                ("min_log_std", C.c_float), ("max_log_std", C.c_float)]
+
+
+class Transitions(C.Structure):
+    _fields_ = [("obs", vp), ("act", vp), ("rew", vp), ("cost", vp), ("obs2", vp), ("done", vp), ("logp", vp),
+                ("emit", vp)]
+
+
+class Ring(C.Structure):
+    _fields_ = [("max_size", C.c_int64), ("n_step", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32),
+                ("obs", vp), ("act", vp), ("rew", vp), ("cost", vp), ("obs2", vp), ("done", vp), ("logp", vp)]
+
+
+# name -> (restype, argtypes); must list every symbol of include/msacl_b200.h
+SIGNATURES = {
+    "msacl_last_error": (C.c_char_p, []),
+    "msacl_abi_version": (C.c_int, []),
+    "msacl_env_dims": (C.c_int, [C.c_int, c_i32p]),
+    "msacl_env_bounds": (C.c_int, [C.c_int, c_f32p, c_f32p, c_f32p, c_f32p]),
+    "msacl_env_reset": (C.c_int, [C.POINTER(EnvState), vp]),
+    "msacl_quad_init_from_raw": (C.c_int, [C.POINTER(EnvState), vp]),
+    "msacl_env_step": (C.c_int, [C.POINTER(EnvState), vp, vp, vp, vp, vp, vp, vp]),
+    "msacl_rollout_fused": (C.c_int, [C.POINTER(EnvState), C.POINTER(Actor), C.c_int32, C.c_uint32, C.c_int32,
+                                      C.c_float, C.c_float, vp, C.c_int32, C.POINTER(Transitions), vp, vp]),
+    "msacl_action_noise": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32, vp, vp]),
+    "msacl_window_store": (C.c_int, [C.POINTER(Transitions), C.c_int32, C.c_int32, C.c_int64, C.POINTER(Ring), vp, vp,
+                                     vp, vp]),
+    "msacl_ring_gather": (C.c_int, [C.POINTER(Ring), vp, C.c_int64, C.POINTER(Ring), vp]),
+    "msacl_q_backup": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp]),
+    "msacl_lyapunov_risk": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_float,
+                                      C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp]),
+    "msacl_stability_advantage": (C.c_int, [C.c_int64, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
+    "msacl_advantage_normalize": (C.c_int, [C.c_int64, vp, vp, vp, vp]),
+    "msacl_ffma_probe": (C.c_int, [C.c_int32, vp, c_f64p, vp]),
+}
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if needed) the CUDA library.  Raises on failure -- never falls back."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path):
+        _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.msacl_abi_version() != 1:
+        raise RuntimeError("libmsacl_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+class MsaclError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().msacl_last_error().decode("utf-8", "replace")
+        raise MsaclError(f"libmsacl_b200 error {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "libmsacl_b200 needs contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

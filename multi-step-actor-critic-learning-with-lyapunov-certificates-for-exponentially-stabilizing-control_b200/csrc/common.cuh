@@ -1,0 +1,73 @@
+// Shared host/device helpers for libmsacl_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/msacl_b200.h"
+#include "env_dynamics.cuh"
+
+namespace msacl {
+
+constexpr int kNumSMs = 148;  // B200
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define MSACL_DISPATCH_ENV(env_id, ...)                                        \
+  switch (env_id) {                                                            \
+    case kVanderPol: { constexpr int ID = kVanderPol; __VA_ARGS__; break; }    \
+    case kPendulum: { constexpr int ID = kPendulum; __VA_ARGS__; break; }      \
+    case kDuctedFan: { constexpr int ID = kDuctedFan; __VA_ARGS__; break; }    \
+    case kTwoLink: { constexpr int ID = kTwoLink; __VA_ARGS__; break; }        \
+    case kSingleTrackCar: { constexpr int ID = kSingleTrackCar; __VA_ARGS__; break; } \
+    case kQuadTracking: { constexpr int ID = kQuadTracking; __VA_ARGS__; break; }     \
+    default: set_error("unknown env id %d", (int)(env_id)); return MSACL_ERR_BAD_ENV; \
+  }
+
+// register-resident state of one env instance
+template <int ID>
+struct EnvRegs {
+  using E = Env<ID>;
+  float sf[E::SF];
+  double sd[E::SD > 0 ? E::SD : 1];
+  int32_t step, episode, ep_len, run;
+  float ep_return;
+
+  __device__ __forceinline__ void load(const msacl_env_state_t& st, int64_t i) {
+#pragma unroll
+    for (int r = 0; r < E::SF; ++r) sf[r] = st.sf[(int64_t)r * st.stride + i];
+#pragma unroll
+    for (int r = 0; r < E::SD; ++r) sd[r] = st.sd[(int64_t)r * st.stride + i];
+    step = st.step[i]; episode = st.episode[i]; ep_len = st.ep_len[i]; run = st.run[i];
+    ep_return = st.ep_return[i];
+  }
+  __device__ __forceinline__ void store(const msacl_env_state_t& st, int64_t i) const {
+#pragma unroll
+    for (int r = 0; r < E::SF; ++r) st.sf[(int64_t)r * st.stride + i] = sf[r];
+#pragma unroll
+    for (int r = 0; r < E::SD; ++r) st.sd[(int64_t)r * st.stride + i] = sd[r];
+    st.step[i] = step; st.episode[i] = episode; st.ep_len[i] = ep_len; st.run[i] = run;
+    st.ep_return[i] = ep_return;
+  }
+  __device__ __forceinline__ const float* obs() const { return sf + E::OBS_OFF; }
+
+  // strict out-of-box test on the float32-cast bounds (e.g. VanderPol.py:118-121);
+  // NaN compares false, i.e. never terminates, as in the reference
+  __device__ __forceinline__ bool out_of_bounds() const {
+    bool t = false;
+#pragma unroll
+    for (int j = 0; j < E::D; ++j) {
+      const float o = sf[E::OBS_OFF + j];
+      t = t || (o < E::obs_low(j)) || (o > E::obs_high(j));
+    }
+    return t;
+  }
+  __device__ __forceinline__ void reset(uint64_t seed, uint64_t env) {
+    E::reset(sf, sd, seed, env, (uint32_t)episode);
+    step = 0; ep_len = 0; ep_return = 0.f;
+  }
+};
+
+}  // namespace msacl

@@ -1,0 +1,348 @@
+// Fused K-step rollout kernel: actor MLP (obs -> 256 -> 256 -> 2A) + TanhGauss sample + clip +
+// env dynamics + reward/cost + same-step autoreset + n-step bookkeeping, for a tile of 64 env
+// instances per CTA.  Replaces K iterations of BaseSampler._n_step
+// (RL/trainer/sampler/base.py:118-163,220).
+//
+// Design (B200, sm_100a):
+//   * persistent grid of 2 CTAs per SM (148*2); each CTA owns tiles of TM=64 envs and keeps
+//     the env state in the registers of its first 64 threads for all K steps -- HBM sees the
+//     state once per launch and only the transition record per step.
+//   * the MLP is >99% of the FLOPs and is an FP32 contraction (parity with the
+//     reference's fp32 torch actor rules out bf16/tf32 single-pass tensor cores), so the
+//     binding roofline is the FP32 FFMA pipe.  Layer 2 (64x256x256 per tile-step) is a
+//     register-tiled SGEMM: 256 threads, 8x8 accumulators each; A = hidden-1 activations
+//     resident in shared memory K-major (warp-broadcast float4 reads), B = W2^T streamed from
+//     L2 in 8-row chunks through a cp.async double buffer (W2 is 256 KB and is shared by
+//     every CTA, so it lives in the 126 MB L2).
+//   * layer 3 (256 -> 2A) is applied to the register tile directly; partial sums are combined
+//     with a halving warp-shuffle reduction (62 shuffles for 64 values).
+//   * while one CTA runs its (latency-bound, 2-warp) env phase the co-resident CTA keeps the
+//     FFMA pipe busy with its GEMM phase.
+// Compiled with -fmad=false: only the explicit __fmaf_rn calls below contract.
+#include "common.cuh"
+
+namespace msacl {
+
+constexpr int TM = 64;          // envs per tile
+constexpr int HID = 256;        // hidden width (reference default, msacl_train.py policy_hidden_sizes)
+constexpr int NTHREADS = 256;
+constexpr int KC = 8;           // W2^T rows per cp.async chunk
+constexpr int NCHUNK = HID / KC;
+
+template <int D> struct PadD { static constexpr int value = (D <= 2) ? 2 : ((D + 3) / 4) * 4; };
+
+template <int ID>
+struct Smem {
+  using E = Env<ID>;
+  static constexpr int DP = PadD<E::D>::value;
+  static constexpr int A2 = 2 * E::A;
+  float h1[HID * TM];          // [k][m]
+  float wc[2][KC * HID];       // W2^T chunks [k][n]
+  float w1[HID * DP];          // [n][dp] rows padded to a vector width
+  float w3[A2 * HID];          // [j][k]
+  float b1[HID];
+  float b2[HID];
+  float b3[8];
+  float x[E::D * TM];          // obs tile [d][m]
+  float out[A2 * TM];          // logits [j][m]
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Halving butterfly: V values per lane summed over the 32 lanes; afterwards value
+// `orig` lives in v[0..V/32) of lane orig / (V/32) (V >= 32), or in v[0] of lanes
+// (orig * 32/V) .. (V < 32, replicated).
+template <int V>
+__device__ __forceinline__ void warp_multi_reduce(float (&v)[V], int lane) {
+  int c = V;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    if (c > 1) {
+      const bool upper = (lane & s) != 0;
+      const int half = c / 2;
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        if (i < half) {
+          const float keep = upper ? v[i + half] : v[i];
+          const float send = upper ? v[i] : v[i + half];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      c = half;
+    } else {
+      v[0] = v[0] + __shfl_xor_sync(0xffffffffu, v[0], s);
+    }
+  }
+}
+
+template <int ID>
+__global__ void __launch_bounds__(NTHREADS, 2)
+rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t step_base, int n_step,
+                     float reward_scale, float cost_scale, const float* __restrict__ eps, int deterministic,
+                     msacl_transitions_t out, double* stats) {
+  using E = Env<ID>;
+  using S = Smem<ID>;
+  constexpr int D = E::D, A = E::A, A2 = 2 * A, DP = S::DP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- stage the small weights once per CTA
+  for (int i = tid; i < HID * DP; i += NTHREADS) {
+    const int n = i / DP, d = i % DP;
+    sm.w1[i] = d < D ? actor.w1[n * D + d] : 0.f;
+  }
+  for (int i = tid; i < A2 * HID; i += NTHREADS) sm.w3[i] = actor.w3[i];
+  for (int i = tid; i < HID; i += NTHREADS) { sm.b1[i] = actor.b1[i]; sm.b2[i] = actor.b2[i]; }
+  if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
+
+  const int64_t num_tiles = (st.n + TM - 1) / TM;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t env0 = tile * TM;
+    const int64_t gi = env0 + tid;              // env owned by this thread (tid < TM)
+    const bool owner = tid < TM && gi < st.n;
+    EnvRegs<ID> r;
+    if (owner) {
+      r.load(st, gi);
+#pragma unroll
+      for (int d = 0; d < D; ++d) sm.x[d * TM + tid] = r.obs()[d];
+    } else if (tid < TM) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) sm.x[d * TM + tid] = 0.f;
+    }
+
+    for (int k = 0; k < K; ++k) {
+      // prefetch W2^T chunk 0 (overlaps layer 1)
+      {
+        const float4* src = reinterpret_cast<const float4*>(actor.w2t);
+        float4* dst = reinterpret_cast<float4*>(sm.wc[0]);
+        cp_async16(dst + tid, src + tid);
+        cp_async16(dst + tid + NTHREADS, src + tid + NTHREADS);
+        cp_async_commit();
+      }
+      __syncthreads();   // x tile (and, first time, weights) visible
+
+      // ---- layer 1: h1[n][m] = relu(b1[n] + sum_d W1[n][d] x[m][d]); thread = (m, 64 n's)
+      {
+        const int m = tid & (TM - 1), ng = tid >> 6;
+        float xv[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) xv[d] = d < D ? sm.x[d * TM + m] : 0.f;
+#pragma unroll 4
+        for (int nn = 0; nn < 64; ++nn) {
+          const int n = ng * 64 + nn;
+          float acc = sm.b1[n];
+          if constexpr (DP % 4 == 0) {
+#pragma unroll
+            for (int d4 = 0; d4 < DP / 4; ++d4) {
+              const float4 w = *reinterpret_cast<const float4*>(&sm.w1[n * DP + 4 * d4]);
+              acc = __fmaf_rn(w.x, xv[4 * d4 + 0], acc);
+              acc = __fmaf_rn(w.y, xv[4 * d4 + 1], acc);
+              acc = __fmaf_rn(w.z, xv[4 * d4 + 2], acc);
+              acc = __fmaf_rn(w.w, xv[4 * d4 + 3], acc);
+            }
+          } else {
+            const float2 w = *reinterpret_cast<const float2*>(&sm.w1[n * DP]);
+            acc = __fmaf_rn(w.x, xv[0], acc);
+            acc = __fmaf_rn(w.y, xv[1], acc);
+          }
+          sm.h1[n * TM + m] = fmaxf(acc, 0.f);
+        }
+      }
+
+      // ---- layer 2: register-tiled 64x256x256 SGEMM; thread tile = envs warp*8..+8 x
+      //      columns {lane*4..+4, 128+lane*4..+4}
+      float acc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        cp_async_wait<0>();
+        __syncthreads();   // chunk ch landed for everyone; everyone finished chunk ch-1 (and layer 1)
+        if (ch + 1 < NCHUNK) {
+          const float4* src = reinterpret_cast<const float4*>(actor.w2t + (size_t)(ch + 1) * KC * HID);
+          float4* dst = reinterpret_cast<float4*>(sm.wc[(ch + 1) & 1]);
+          cp_async16(dst + tid, src + tid);
+          cp_async16(dst + tid + NTHREADS, src + tid + NTHREADS);
+          cp_async_commit();
+        }
+        const float* wb = sm.wc[ch & 1];
+        const float* ha = sm.h1 + (size_t)ch * KC * TM + warp * 8;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+          const float4 a0 = *reinterpret_cast<const float4*>(ha + kk * TM);
+          const float4 a1 = *reinterpret_cast<const float4*>(ha + kk * TM + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(wb + kk * HID + lane * 4);
+          const float4 b1 = *reinterpret_cast<const float4*>(wb + kk * HID + 128 + lane * 4);
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][c] = __fmaf_rn(av[i], bv[c], acc[i][c]);
+        }
+      }
+
+      // ---- bias + ReLU, then layer 3 on the register tile
+      {
+        const float4 q0 = *reinterpret_cast<const float4*>(&sm.b2[lane * 4]);
+        const float4 q1 = *reinterpret_cast<const float4*>(&sm.b2[128 + lane * 4]);
+        const float bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[i][c] = fmaxf(acc[i][c] + bb[c], 0.f);
+      }
+      float part[8 * A2];   // index i*A2 + j
+#pragma unroll
+      for (int j = 0; j < A2; ++j) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&sm.w3[j * HID + lane * 4]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sm.w3[j * HID + 128 + lane * 4]);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float p = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) p = __fmaf_rn(acc[i][c], wv[c], p);
+          part[i * A2 + j] = p;
+        }
+      }
+      warp_multi_reduce<8 * A2>(part, lane);
+      {
+        constexpr int V = 8 * A2;
+        if constexpr (V >= 32) {
+          constexpr int per = V / 32;
+#pragma unroll
+          for (int q = 0; q < per; ++q) {
+            const int orig = lane * per + q;
+            const int i = orig / A2, j = orig % A2;
+            sm.out[j * TM + warp * 8 + i] = part[q] + sm.b3[j];
+          }
+        } else {
+          constexpr int rep = 32 / V;
+          if (lane % rep == 0) {
+            const int orig = lane / rep;
+            const int i = orig / A2, j = orig % A2;
+            sm.out[j * TM + warp * 8 + i] = part[0] + sm.b3[j];
+          }
+        }
+      }
+      __syncthreads();   // logits visible; all reads of x / h1 for this step are done
+
+      // ---- env phase: one thread per env
+      if (owner) {
+        const int64_t row = (int64_t)k * st.n + gi;
+        if (out.obs) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) out.obs[row * D + d] = r.obs()[d];
+        }
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!deterministic) {
+          if (eps) {
+#pragma unroll
+            for (int j = 0; j < A; ++j) z[j] = eps[row * A + j];
+          } else {
+            action_noise4(st.seed, st.env_base + (uint64_t)gi, step_base + (uint32_t)k, z);
+          }
+        }
+        float act[A];
+        float lp_gauss = 0.f, lp_tanh = 0.f, lp_scale = 0.f;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+          const float mean = sm.out[j * TM + tid];
+          const float ls = sm.out[(A + j) * TM + tid];
+          const float sd = expf(fminf(fmaxf(ls, actor.min_log_std), actor.max_log_std));
+          const float half = (E::act_high(j) - E::act_low(j)) / 2.0f;
+          const float mid = (E::act_high(j) + E::act_low(j)) / 2.0f;
+          float u = deterministic ? mean : (sd * z[j] + mean);      // torch.normal: z*std, then +mean
+          const float th = tanhf(u);
+          const float a_lim = half * th + mid;
+          // Normal.log_prob(u) = -((u-mean)^2)/(2 var) - log(std) - log(sqrt(2 pi))
+          const float diff = u - mean;
+          const float g = ((-(diff * diff)) / (2.0f * (sd * sd)) - logf(sd)) - 0.91893853320467267f;
+          const float t = logf(1.000001f - th * th);
+          const float sc = logf(half);
+          lp_gauss = (j == 0) ? g : lp_gauss + g;
+          lp_tanh = (j == 0) ? t : lp_tanh + t;
+          lp_scale = (j == 0) ? sc : lp_scale + sc;
+          act[j] = fminf(fmaxf(a_lim, E::act_low(j)), E::act_high(j));   // base.py:141-143
+        }
+        const float logp = (lp_gauss - lp_tanh) - lp_scale;
+
+        const float rew = E::step(r.sf, r.sd, act);
+        const bool term = r.out_of_bounds();
+        r.step += 1;
+        const bool trunc = r.step >= st.max_step;
+        const bool done = term || trunc;
+        r.ep_return += rew;
+        r.ep_len += 1;
+        const float rew_s = rew * reward_scale;                                  // rew_plus_cost.py:18
+        const float cost = np_rowsum_sq<D>(r.obs()) * cost_scale;                // :20-21
+        r.run = min(r.run + 1, n_step);
+        const bool emit = r.run >= n_step;
+        if (out.act) {
+#pragma unroll
+          for (int j = 0; j < A; ++j) out.act[row * A + j] = act[j];
+        }
+        if (out.obs2) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) out.obs2[row * D + d] = r.obs()[d];        // real_next_obs (pre-reset)
+        }
+        if (out.rew) out.rew[row] = rew_s;
+        if (out.cost) out.cost[row] = cost;
+        if (out.done) out.done[row] = done ? 1 : 0;
+        if (out.logp) out.logp[row] = logp;
+        if (out.emit) out.emit[row] = emit ? 1 : 0;
+        if (stats) {
+          if (done) {
+            atomicAdd(&stats[0], 1.0);
+            atomicAdd(&stats[1], (double)r.ep_return);
+            atomicAdd(&stats[2], (double)r.ep_len);
+            atomicAdd(&stats[term ? 3 : 4], 1.0);
+          }
+        }
+        if (done) {
+          r.episode += 1;
+          r.run = 0;
+          r.reset(st.seed, st.env_base + (uint64_t)gi);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) sm.x[d * TM + tid] = r.obs()[d];
+      }
+      // next iteration's first __syncthreads orders the x writes before layer 1
+    }
+    if (owner) r.store(st, gi);
+    __syncthreads();   // protect sm.x before the next tile's owners overwrite it
+  }
+}
+
+}  // namespace msacl
+
+using namespace msacl;
+
+extern "C" int msacl_rollout_fused(const msacl_env_state_t* st, const msacl_actor_t* actor, int32_t K,
+                                   uint32_t step_base, int32_t n_step, float reward_scale, float cost_scale,
+                                   const float* eps, int32_t deterministic, const msacl_transitions_t* out,
+                                   double* stats, void* stream) {
+  if (!st || !actor || !out || st->n <= 0 || K <= 0 || n_step <= 0) { set_error("rollout_fused: bad argument"); return MSACL_ERR_BAD_ARG; }
+  if (!actor->w1 || !actor->b1 || !actor->w2t || !actor->b2 || !actor->w3 || !actor->b3) { set_error("rollout_fused: null actor weights"); return MSACL_ERR_BAD_ARG; }
+  if ((reinterpret_cast<uintptr_t>(actor->w2t) & 15) != 0) { set_error("rollout_fused: w2t must be 16-byte aligned"); return MSACL_ERR_BAD_ARG; }
+  const int64_t tiles = (st->n + TM - 1) / TM;
+  const unsigned grid = (unsigned)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+  MSACL_DISPATCH_ENV(st->env_id, {
+    const size_t smem = sizeof(Smem<ID>);
+    auto kern = rollout_fused_kernel<ID>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("rollout_fused: smem attr: %s", cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
+    kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(*st, *actor, K, step_base, n_step, reward_scale, cost_scale,
+                                                        eps, deterministic, *out, stats);
+  });
+  return check_launch("rollout_fused");
+}

@@ -1,0 +1,208 @@
+// MSACL learner targets over [B, n] replay windows, given the network outputs.
+// Replaces the ~40 small elementwise/reduction torch ops of RL/algorithm/msacl.py:
+//   soft-TD backup :249-252, Lyapunov risk :280-329 (+ analytic backward), stability
+//   advantage :392-400.  One warp per window: lane k owns step k (n <= 32), the clipped
+//   importance-ratio cumprod is a warp scan and the lambda-weighted sums are warp reductions.
+// HBM-bound: algorithmic bytes per window = 4*n*(2D + 4) read + 4*n*2 written (risk).
+#include "common.cuh"
+
+namespace msacl {
+
+__global__ void __launch_bounds__(256)
+q_backup_kernel(int64_t count, const float* __restrict__ rew, const float* __restrict__ done,
+                const float* __restrict__ q1, const float* __restrict__ q2, const float* __restrict__ logp, float gamma,
+                float alpha, float* __restrict__ backup) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float nq = fminf(q1[i], q2[i]);
+    backup[i] = rew[i] + ((1.0f - done[i]) * gamma) * (nq - alpha * logp[i]);   // msacl.py:250-252
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32)
+lyapunov_risk_kernel(int64_t B, int n, int D, const float* __restrict__ obs, const float* __restrict__ obs2,
+                     const float* __restrict__ logp_new, const float* __restrict__ logp_old,
+                     const float* __restrict__ lya_obs, const float* __restrict__ lya_obs2,
+                     const float* __restrict__ coef_son, const float* __restrict__ coef_diff,
+                     const float* __restrict__ coef_sl, float alpha1, float alpha2, float diff_scale, float pos_scale,
+                     double* __restrict__ loss_parts, float* __restrict__ g_obs, float* __restrict__ g_obs2,
+                     float* __restrict__ is_clip_out, float* __restrict__ esl_out) {
+  __shared__ float s_part[3][WPB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool act = lane < n;
+  const float son = act ? coef_son[lane] : 0.f, dif = act ? coef_diff[lane] : 0.f, sl = act ? coef_sl[lane] : 0.f;
+  const float inv_bn = pos_scale / (float)((double)B * n);
+  const float w_scale = diff_scale / (float)B;
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+  for (int64_t b = (int64_t)blockIdx.x * WPB + warp; b < B; b += (int64_t)gridDim.x * WPB) {
+    const int64_t e = b * n + lane;
+    float ratio = 1.f, v1 = 0.f, v2 = 0.f, op = 0.f, op2 = 0.f;
+    if (act) {
+      ratio = fminf(fmaxf(expf(logp_new[e] - logp_old[e]), 0.f), 1.f);   // clamp(ratio, 0, 1) :284-285
+      v1 = lya_obs[e]; v2 = lya_obs2[e];
+      const float* o = obs + e * D;
+      const float* q = obs2 + e * D;
+      for (int d = 0; d < D; ++d) { op = __fmaf_rn(o[d], o[d], op); op2 = __fmaf_rn(q[d], q[d], op2); }
+    }
+    // inclusive cumprod over the window (:286)
+    float c = ratio;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float y = __shfl_up_sync(0xffffffffu, c, o);
+      if (lane >= o) c *= y;
+    }
+    const float lo = alpha1 * op - v1, up = v1 - alpha2 * op;           // boundedness hinge :291-301
+    const float start_norm = sqrtf(__shfl_sync(0xffffffffu, op, 0));    // ||o_0|| :306-307
+    const float start_lya = __shfl_sync(0xffffffffu, v1, 0);
+    const float esl = (start_norm * son - sqrtf(op2)) >= 0.f ? 1.f : -1.f;   // :308-312
+    const float inner = esl * (v2 - start_lya * sl);                    // :318-323
+    const float term = c * fmaxf(inner, 0.f);
+    const float w = (act && inner > 0.f) ? dif * c * esl * w_scale : 0.f;
+    const float back0 = warp_sum(w * sl);
+    if (act) {
+      p0 += fmaxf(lo, 0.f);
+      p1 += fmaxf(up, 0.f);
+      p2 += dif * term;
+      float g1 = ((lo > 0.f) ? -inv_bn : 0.f) + ((up > 0.f) ? inv_bn : 0.f);
+      if (lane == 0) g1 -= back0;
+      g_obs[e] = g1;
+      g_obs2[e] = w;
+      if (is_clip_out) is_clip_out[e] = c;
+      if (esl_out) esl_out[e] = esl;
+    }
+  }
+  p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
+  if (lane == 0) { s_part[0][warp] = p0; s_part[1][warp] = p1; s_part[2][warp] = p2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int w = 0; w < WPB; ++w) s += (double)s_part[threadIdx.x][w];
+    atomicAdd(&loss_parts[threadIdx.x], s);
+  }
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32)
+stability_adv_kernel(int64_t B, int n, const float* __restrict__ lya_obs0, const float* __restrict__ lya_obs2,
+                     const float* __restrict__ coef_diff, const float* __restrict__ coef_sl, float* __restrict__ adv_raw,
+                     double* __restrict__ moments) {
+  __shared__ double s_m[2][WPB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool act = lane < n;
+  const float dif = act ? coef_diff[lane] : 0.f, sl = act ? coef_sl[lane] : 0.f;
+  double m1 = 0.0, m2 = 0.0;
+  for (int64_t b = (int64_t)blockIdx.x * WPB + warp; b < B; b += (int64_t)gridDim.x * WPB) {
+    const float v0 = lya_obs0[b];
+    const float v2 = act ? lya_obs2[b * n + lane] : 0.f;
+    const float a = warp_sum(dif * (v0 * sl - v2));       // msacl.py:395-399
+    if (lane == 0) { adv_raw[b] = a; m1 += (double)a; m2 += (double)a * (double)a; }
+  }
+  if (lane == 0) { s_m[0][warp] = m1; s_m[1][warp] = m2; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int w = 0; w < WPB; ++w) s += s_m[threadIdx.x][w];
+    atomicAdd(&moments[threadIdx.x], s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adv_normalize_kernel(int64_t B, const float* __restrict__ adv_raw, const double* __restrict__ moments, float* __restrict__ adv) {
+  const double mean = moments[0] / (double)B;
+  const double var = (moments[1] - moments[0] * mean) / (double)(B - 1);     // unbiased, torch.std default
+  const float fmean = (float)mean;
+  const float denom = (float)sqrt(var > 0.0 ? var : 0.0) + 1e-8f;            // msacl.py:400
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) adv[i] = (adv_raw[i] - fmean) / denom;
+}
+
+// FP32 FFMA peak probe: 8 independent accumulator chains per thread, 2 CTAs x 256 threads per SM
+__global__ void __launch_bounds__(256) ffma_probe_kernel(int iters, float* sink) {
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = (float)(threadIdx.x + j) * 1e-3f;
+  const float x = 1.0000001f, y = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = __fmaf_rn(a[j], x, y);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == 123.456f) sink[0] = s;
+}
+
+}  // namespace msacl
+
+using namespace msacl;
+
+static inline unsigned grid_for(int64_t work_items, int per_block) {
+  const int64_t want = (work_items + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+extern "C" int msacl_q_backup(int64_t count, const float* rew, const float* done, const float* next_q1,
+                              const float* next_q2, const float* next_logp, float gamma, float alpha, float* backup,
+                              void* stream) {
+  if (count <= 0 || !rew || !done || !next_q1 || !next_q2 || !next_logp || !backup) { set_error("q_backup: bad argument"); return MSACL_ERR_BAD_ARG; }
+  q_backup_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(count, rew, done, next_q1, next_q2, next_logp, gamma, alpha, backup);
+  return check_launch("q_backup");
+}
+
+extern "C" int msacl_lyapunov_risk(int64_t B, int32_t n, int32_t D, const float* obs, const float* obs2,
+                                   const float* logp_new, const float* logp_old, const float* lya_obs,
+                                   const float* lya_obs2, const float* coef_son, const float* coef_diff,
+                                   const float* coef_sl, float alpha1, float alpha2, float diff_scale, float pos_scale,
+                                   double* loss_parts, float* grad_lya_obs, float* grad_lya_obs2, float* is_clip,
+                                   float* esl, void* stream) {
+  if (B <= 0 || n <= 0 || n > 32 || D <= 0 || !obs || !obs2 || !logp_new || !logp_old || !lya_obs || !lya_obs2 ||
+      !coef_son || !coef_diff || !coef_sl || !loss_parts || !grad_lya_obs || !grad_lya_obs2) {
+    set_error("lyapunov_risk: bad argument (n_step must be <= 32)");
+    return MSACL_ERR_BAD_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(loss_parts, 0, 3 * sizeof(double), s);
+  constexpr int WPB = 8;
+  lyapunov_risk_kernel<WPB><<<grid_for(B, WPB), WPB * 32, 0, s>>>(B, n, D, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2,
+                                                               coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale,
+                                                               pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);
+  return check_launch("lyapunov_risk");
+}
+
+extern "C" int msacl_stability_advantage(int64_t B, int32_t n, const float* lya_obs0, const float* lya_obs2,
+                                         const float* coef_diff, const float* coef_sl, float* adv_raw, double* moments,
+                                         void* stream) {
+  if (B <= 0 || n <= 0 || n > 32 || !lya_obs0 || !lya_obs2 || !coef_diff || !coef_sl || !adv_raw || !moments) {
+    set_error("stability_advantage: bad argument");
+    return MSACL_ERR_BAD_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(moments, 0, 2 * sizeof(double), s);
+  constexpr int WPB = 8;
+  stability_adv_kernel<WPB><<<grid_for(B, WPB), WPB * 32, 0, s>>>(B, n, lya_obs0, lya_obs2, coef_diff, coef_sl, adv_raw, moments);
+  return check_launch("stability_advantage");
+}
+
+extern "C" int msacl_advantage_normalize(int64_t B, const float* adv_raw, const double* moments, float* adv, void* stream) {
+  if (B <= 1 || !adv_raw || !moments || !adv) { set_error("advantage_normalize: bad argument"); return MSACL_ERR_BAD_ARG; }
+  adv_normalize_kernel<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, adv_raw, moments, adv);
+  return check_launch("advantage_normalize");
+}
+
+extern "C" int msacl_ffma_probe(int32_t iters, float* sink, double* flops, void* stream) {
+  if (iters <= 0 || !sink) { set_error("ffma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
+  const unsigned grid = 2 * kNumSMs * 4;
+  ffma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+  if (flops) *flops = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)grid;
+  return check_launch("ffma_probe");
+}

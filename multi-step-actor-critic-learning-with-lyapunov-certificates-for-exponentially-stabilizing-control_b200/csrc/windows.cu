@@ -1,0 +1,192 @@
+// n-step window assembly + device replay ring.
+// Replaces the per-env deque logic of RL/trainer/sampler/base.py:178-217 and
+// NstepReplayBuffer.store/add_batch/sample_batch (RL/trainer/buffer/nstep_replay_buffer.py:91-150).
+//
+// The rollout kernel already recorded, per transition, whether the env's deque is full
+// (`emit`).  The reference appends emitted windows in step-major / env-minor order and stores
+// them at consecutive ring slots, so slot(t,i) = (ptr + exclusive_scan(emit)[t*n+i]) % max_size.
+// Three small kernels: per-block counts, single-block scan of the counts, scatter.
+// Integer bookkeeping is bit-exact; payload is copied verbatim.  HBM-bound:
+// bytes per stored window = 2 * 4 * n_step * (2D + A + 4)  (read transitions + write ring).
+#include "common.cuh"
+
+namespace msacl {
+
+constexpr int WB = 256;   // flags per block
+
+__global__ void __launch_bounds__(WB) window_count_kernel(const uint8_t* __restrict__ emit_new, int64_t total,
+                                                          int64_t* __restrict__ block_counts) {
+  const int64_t f = (int64_t)blockIdx.x * WB + threadIdx.x;
+  const int flag = (f < total && emit_new[f]) ? 1 : 0;
+  const int c = __syncthreads_count(flag);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+// exclusive scan of block_counts[0..nb) in place (single block); header[0]=old ptr, header[1]=total
+__global__ void __launch_bounds__(1024) window_scan_kernel(int64_t* __restrict__ block_counts, int64_t nb,
+                                                           int64_t* __restrict__ header, int64_t* __restrict__ ptr_size,
+                                                           int64_t* __restrict__ count_out, int64_t max_size) {
+  __shared__ int64_t warp_sums[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < nb; base += 1024) {
+    const int64_t idx = base + threadIdx.x;
+    const int64_t v = idx < nb ? block_counts[idx] : 0;
+    int64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_sums[lane] = w;   // inclusive
+    }
+    __syncthreads();
+    const int64_t warp_off = warp > 0 ? warp_sums[warp - 1] : 0;
+    const int64_t incl = carry + warp_off + x;
+    if (idx < nb) block_counts[idx] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int64_t total = carry;
+    header[0] = ptr_size[0];
+    header[1] = total;
+    ptr_size[0] = (ptr_size[0] + total) % max_size;
+    const int64_t s = ptr_size[1] + total;
+    ptr_size[1] = s < max_size ? s : max_size;
+    if (count_out) count_out[0] = total;
+  }
+}
+
+__global__ void __launch_bounds__(WB)
+window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_flags, msacl_ring_t ring,
+                      const int64_t* __restrict__ block_offsets, const int64_t* __restrict__ header) {
+  __shared__ int warp_counts[WB / 32];
+  __shared__ int64_t s_slot[WB];
+  __shared__ int64_t s_src[WB];   // flat (t, i) index of the newest transition of the window
+  __shared__ int s_num;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t f = (int64_t)blockIdx.x * WB + tid;
+  const uint8_t* emit_new = tr.emit + (int64_t)H * n;
+  const int flag = (f < total_flags && emit_new[f]) ? 1 : 0;
+  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) warp_counts[warp] = __popc(ballot);
+  __syncthreads();
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += warp_counts[w];
+  const int local = before + __popc(ballot & ((1u << lane) - 1u));
+  if (tid == 0) {
+    int s = 0;
+    for (int w = 0; w < WB / 32; ++w) s += warp_counts[w];
+    s_num = s;
+  }
+  const int64_t old_ptr = header[0], total = header[1];
+  if (flag) {
+    const int64_t order = block_offsets[blockIdx.x] + local;   // position in the reference's append order
+    // windows that a later window of the same call would overwrite are skipped (sequential
+    // store semantics: the last writer wins)
+    const bool live = (total - order) <= ring.max_size;
+    s_slot[local] = live ? (old_ptr + order) % ring.max_size : -1;
+    s_src[local] = f + (int64_t)H * n;
+  }
+  __syncthreads();
+  const int num = s_num;
+  const int ns = ring.n_step, D = ring.obs_dim, A = ring.act_dim;
+  for (int w = warp; w < num; w += WB / 32) {
+    const int64_t slot = s_slot[w];
+    if (slot < 0) continue;
+    const int64_t newest = s_src[w];
+    const int64_t t_new = newest / n, i = newest % n;
+    const int64_t t0 = t_new - (ns - 1);
+    for (int e = lane; e < ns * D; e += 32) {
+      const int r = e / D, d = e % D;
+      const int64_t src = ((t0 + r) * n + i) * D + d;
+      ring.obs[(slot * ns + r) * D + d] = tr.obs[src];
+      ring.obs2[(slot * ns + r) * D + d] = tr.obs2[src];
+    }
+    for (int e = lane; e < ns * A; e += 32) {
+      const int r = e / A, d = e % A;
+      ring.act[(slot * ns + r) * A + d] = tr.act[((t0 + r) * n + i) * A + d];
+    }
+    for (int r = lane; r < ns; r += 32) {
+      const int64_t src = (t0 + r) * n + i;
+      ring.rew[slot * ns + r] = tr.rew[src];
+      ring.cost[slot * ns + r] = tr.cost[src];
+      ring.done[slot * ns + r] = tr.done[src] ? 1.0f : 0.0f;
+      ring.logp[slot * ns + r] = tr.logp[src];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ring_gather_kernel(msacl_ring_t ring, const int64_t* __restrict__ idx, int64_t B, msacl_ring_t batch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int64_t s = idx[b];
+  const int ns = ring.n_step, D = ring.obs_dim, A = ring.act_dim;
+  for (int e = lane; e < ns * D; e += 32) {
+    batch.obs[b * ns * D + e] = ring.obs[s * ns * D + e];
+    batch.obs2[b * ns * D + e] = ring.obs2[s * ns * D + e];
+  }
+  for (int e = lane; e < ns * A; e += 32) batch.act[b * ns * A + e] = ring.act[s * ns * A + e];
+  for (int e = lane; e < ns; e += 32) {
+    batch.rew[b * ns + e] = ring.rew[s * ns + e];
+    batch.cost[b * ns + e] = ring.cost[s * ns + e];
+    batch.done[b * ns + e] = ring.done[s * ns + e];
+    batch.logp[b * ns + e] = ring.logp[s * ns + e];
+  }
+}
+
+}  // namespace msacl
+
+using namespace msacl;
+
+static int validate_ring(const msacl_ring_t* r) {
+  if (!r || r->max_size <= 0 || r->n_step <= 0 || r->obs_dim <= 0 || r->act_dim <= 0 || !r->obs || !r->act ||
+      !r->rew || !r->cost || !r->obs2 || !r->done || !r->logp) {
+    set_error("invalid ring descriptor");
+    return MSACL_ERR_BAD_ARG;
+  }
+  return MSACL_OK;
+}
+
+extern "C" int msacl_window_store(const msacl_transitions_t* tr, int32_t H, int32_t K, int64_t n,
+                                  const msacl_ring_t* ring, int64_t* ptr_size, int64_t* count_out, int64_t* scratch,
+                                  void* stream) {
+  if (int rc = validate_ring(ring)) return rc;
+  if (!tr || !tr->obs || !tr->act || !tr->rew || !tr->cost || !tr->obs2 || !tr->done || !tr->logp || !tr->emit ||
+      !ptr_size || !scratch || K <= 0 || n <= 0 || H < ring->n_step - 1) {
+    set_error("window_store: bad argument (need all transition fields and H >= n_step-1)");
+    return MSACL_ERR_BAD_ARG;
+  }
+  const int64_t total = (int64_t)K * n;
+  const int64_t nb = (total + WB - 1) / WB;
+  cudaStream_t s = (cudaStream_t)stream;
+  window_count_kernel<<<(unsigned)nb, WB, 0, s>>>(tr->emit + (int64_t)H * n, total, scratch + 2);
+  window_scan_kernel<<<1, 1024, 0, s>>>(scratch + 2, nb, scratch, ptr_size, count_out, ring->max_size);
+  window_scatter_kernel<<<(unsigned)nb, WB, 0, s>>>(*tr, H, n, total, *ring, scratch + 2, scratch);
+  return check_launch("window_store");
+}
+
+extern "C" int msacl_ring_gather(const msacl_ring_t* ring, const int64_t* idx, int64_t B, const msacl_ring_t* batch,
+                                 void* stream) {
+  if (int rc = validate_ring(ring)) return rc;
+  if (int rc = validate_ring(batch)) return rc;
+  if (!idx || B <= 0) { set_error("ring_gather: bad argument"); return MSACL_ERR_BAD_ARG; }
+  const int wpb = 8;
+  ring_gather_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(*ring, idx, B, *batch);
+  return check_launch("ring_gather");
+}

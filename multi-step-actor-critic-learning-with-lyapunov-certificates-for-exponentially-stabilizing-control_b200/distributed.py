@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing: env instances shard across ranks with NO collective on the step path
+(every env is independent; RNG is keyed by the global env id, so results do not depend on the
+number of GPUs).  Collectives (NCCL on GPUs, gloo in the CPU tests) are used only for the
+per-chunk episode statistics and for assembling a global replay batch from per-rank
+sub-batches.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_env_range(total_envs, rank, world):
+    """Contiguous env-id range [lo, hi) owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(int(total_envs), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_reduce_stats(stats):
+    """Sum the [8] float64 rollout statistics vector (episodes, sum return, sum length,
+    terminated, truncated, ...) over ranks."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        stats = stats.clone()
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+def all_gather_replay_batch(sub_batch):
+    """Concatenate per-rank replay sub-batches {field: [B/G, n, ...]} along the batch axis in
+    rank order -> {field: [B, n, ...]} on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return sub_batch
+    world = dist.get_world_size()
+    out = {}
+    for k in sorted(sub_batch):
+        t = sub_batch[k].contiguous()
+        full = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(full, t)
+        out[k] = full
+    return out
+
+
+def episode_summary(stats):
+    """Host dict from a (reduced) statistics vector."""
+    s = stats.detach().cpu().tolist()
+    ep = max(s[0], 1.0)
+    return {"episodes": int(s[0]), "mean_return": s[1] / ep, "mean_length": s[2] / ep, "terminated": int(s[3]),
+            "truncated": int(s[4])}

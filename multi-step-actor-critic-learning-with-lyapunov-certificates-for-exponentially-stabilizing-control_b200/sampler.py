@@ -1,0 +1,205 @@
+"""Fused GPU rollout sampler -- drop-in for `NstepOffSampler`
+(RL/trainer/sampler/nstep_off_sampler.py:8-29 on top of RL/trainer/sampler/base.py:48-323).
+
+`sample()` runs `horizon = sample_batch_size` vector steps in ONE kernel launch
+(msacl_rollout_fused): actor forward, TanhGauss sampling, clipping, env dynamics, reward/cost
+scaling, same-step autoreset and the n-step deque bookkeeping all happen on the device with
+the env state resident in registers.  The emitted n-step windows stay on the device
+(`DeviceWindowBatch`) and are appended to `B200NstepReplayBuffer` by a device scatter.
+"""
+import ctypes as C
+import time
+from typing import NamedTuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .envs import EnvStateBuffers, B200VectorEnv
+from .specs import get_spec
+
+SAMPLER_TIME_TAG = "Time/Sampler time [ms]-RL iter"      # RL/utils/tensorboard_setup.py:38
+
+
+class nStepExperience(NamedTuple):
+    """Same fields as RL/trainer/sampler/base.py:33-45."""
+    n_step_obs: np.ndarray
+    n_step_act: np.ndarray
+    n_step_rew: np.ndarray
+    n_step_cost: np.ndarray
+    n_step_obs2: np.ndarray
+    n_step_done: np.ndarray
+    n_step_log_prob: np.ndarray
+
+
+class ActorWeights:
+    """Device copy of a StochaPolicy MLP (obs -> 256 -> 256 -> 2*act), packed for the kernel."""
+
+    HIDDEN = 256
+
+    def __init__(self, layers, device="cuda", min_log_std=-20.0, max_log_std=1.0):
+        (w1, b1), (w2, b2), (w3, b3) = layers
+        dev = torch.device(device)
+        t = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a.detach(), dtype=torch.float32).to(dev).contiguous()
+        self.w1, self.b1, self.b2, self.w3, self.b3 = t(w1), t(b1), t(b2), t(w3), t(b3)
+        self.w2t = t(w2).t().contiguous()
+        if self.w1.shape[0] != self.HIDDEN or tuple(self.w2t.shape) != (self.HIDDEN, self.HIDDEN) or self.w3.shape[1] != self.HIDDEN:
+            raise ValueError("the fused rollout kernel is specialised for policy_hidden_sizes=[256, 256]")
+        self.obs_dim = self.w1.shape[1]
+        self.act_dim = self.w3.shape[0] // 2
+        self.desc = _lib.Actor(w1=self.w1.data_ptr(), b1=self.b1.data_ptr(), w2t=self.w2t.data_ptr(), b2=self.b2.data_ptr(),
+                               w3=self.w3.data_ptr(), b3=self.b3.data_ptr(), min_log_std=float(min_log_std),
+                               max_log_std=float(max_log_std))
+
+    @classmethod
+    def from_policy(cls, policy, device="cuda"):
+        """policy: a reference-style StochaPolicy (RL/apprfunc/mlp.py:111-136): `.policy` is an
+        nn.Sequential of Linear/activation pairs, `.min_log_std`, `.max_log_std`."""
+        seq = policy.policy if hasattr(policy, "policy") else policy
+        lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
+        if len(lin) != 3:
+            raise ValueError("expected a 2-hidden-layer policy MLP")
+        return cls([(l.weight, l.bias) for l in lin], device=device,
+                   min_log_std=getattr(policy, "min_log_std", -20.0), max_log_std=getattr(policy, "max_log_std", 1.0))
+
+
+class TransitionBuffers:
+    """[(H + K), n, .] transition store: H = n_step - 1 history slices + K new slices."""
+
+    def __init__(self, spec, n, K, n_step, device):
+        self.H, self.K, self.n = n_step - 1, K, n
+        T = self.H + K
+        f = lambda *s: torch.zeros(T, n, *s, dtype=torch.float32, device=device)
+        b = lambda: torch.zeros(T, n, dtype=torch.uint8, device=device)
+        self.obs, self.act, self.rew, self.cost = f(spec.obs_dim), f(spec.act_dim), f(), f()
+        self.obs2, self.done, self.logp, self.emit = f(spec.obs_dim), b(), f(), b()
+
+    def fields(self):
+        return dict(obs=self.obs, act=self.act, rew=self.rew, cost=self.cost, obs2=self.obs2, done=self.done,
+                    logp=self.logp, emit=self.emit)
+
+    def desc(self, t0=0):
+        return _lib.Transitions(**{k: v[t0:].data_ptr() for k, v in self.fields().items()})
+
+    def roll_history(self):
+        if self.H == 0:
+            return
+        for v in self.fields().values():
+            v[:self.H].copy_(v[self.K:self.K + self.H].clone() if self.K < self.H else v[self.K:self.K + self.H])
+
+
+class DeviceWindowBatch:
+    """Result of one `sample()`: the chunk's transitions + emit flags, still on the device."""
+
+    def __init__(self, tr: TransitionBuffers, n_step):
+        self.tr, self.n_step = tr, n_step
+
+    def count(self):
+        return int(self.tr.emit[self.tr.H:].sum().item())
+
+    def __len__(self):
+        return self.count()
+
+    def materialize(self):
+        """Host list of nStepExperience in the reference's order (step-major, env-minor)."""
+        tr, ns = self.tr, self.n_step
+        emit = self.tr.emit[tr.H:].cpu().numpy().astype(bool)
+        f = {k: v.cpu().numpy() for k, v in tr.fields().items()}
+        out = []
+        for t, i in zip(*np.nonzero(emit)):
+            sl = slice(t + tr.H - ns + 1, t + tr.H + 1)
+            out.append(nStepExperience(f["obs"][sl, i], f["act"][sl, i], f["rew"][sl, i], f["cost"][sl, i], f["obs2"][sl, i],
+                                       f["done"][sl, i].astype(np.float32), f["logp"][sl, i]))
+        return out
+
+    def __iter__(self):
+        return iter(self.materialize())
+
+
+class FusedRollout:
+    """Owns env state + transition buffers and launches msacl_rollout_fused."""
+
+    def __init__(self, env_name, num_envs, horizon, n_step=20, reward_scale=100.0, cost_scale=100.0, seed=0, env_base=0,
+                 device="cuda", max_step=None, state=None):
+        self.spec = get_spec(env_name)
+        self.state = state or EnvStateBuffers(env_name, num_envs, seed=seed, env_base=env_base, device=device, max_step=max_step)
+        self.n, self.K, self.n_step = self.state.n, int(horizon), int(n_step)
+        self.reward_scale, self.cost_scale = float(reward_scale), float(cost_scale)
+        self.tr = TransitionBuffers(self.spec, self.n, self.K, self.n_step, self.state.device)
+        self.stats = torch.zeros(8, dtype=torch.float64, device=self.state.device)
+        self.global_step = 0
+
+    def run(self, actor: ActorWeights, eps=None, deterministic=False, write=True):
+        """One K-step chunk.  eps: optional CUDA float32 [K, n, act_dim] explicit N(0,1) draws."""
+        if actor.obs_dim != self.spec.obs_dim or actor.act_dim != self.spec.act_dim:
+            raise ValueError("actor dimensions do not match the environment")
+        tr = self.tr
+        tr.roll_history()
+        out = tr.desc(tr.H) if write else _lib.Transitions()
+        if eps is not None:
+            eps = eps.contiguous()
+            assert tuple(eps.shape) == (self.K, self.n, self.spec.act_dim) and eps.is_cuda
+        _lib.check(_lib.load().msacl_rollout_fused(
+            C.byref(self.state.desc), C.byref(actor.desc), self.K, self.global_step & 0xFFFFFFFF, self.n_step,
+            self.reward_scale, self.cost_scale, None if eps is None else eps.data_ptr(), 1 if deterministic else 0,
+            C.byref(out), self.stats.data_ptr(), _lib.current_stream()))
+        self.global_step += self.K
+        return DeviceWindowBatch(tr, self.n_step)
+
+
+class B200NstepOffSampler:
+    """Reference-compatible constructor: B200NstepOffSampler(**kwargs) with the kwargs of
+    RL/trainer/sampler/base.py:55-95 (env_name, env_num, sample_batch_size, reward_scale,
+    cost_scale, noise_params, n_step, ...).  `.networks` may be assigned by the trainer
+    (RL/trainer/nstep_off_serial_trainer.py:34) and is re-read on every `sample()`."""
+
+    def __init__(self, **kwargs):
+        self.env_id = kwargs["env_name"]
+        self.num_envs = int(kwargs["env_num"])
+        if kwargs.get("noise_params") is not None:
+            raise RuntimeError("additive exploration noise is not part of the fused rollout (reference default: None)")
+        if kwargs.get("action_type", "continu") != "continu":
+            raise RuntimeError("Only continuous action space is supported!")
+        self.horizon = int(kwargs["sample_batch_size"])
+        self.sample_batch_size = self.horizon * self.num_envs
+        self.n_step = int(kwargs.get("n_step", 1))
+        self.reward_scale, self.cost_scale = kwargs["reward_scale"], kwargs["cost_scale"]
+        self.device = torch.device(kwargs.get("device", "cuda"))
+        self.envs = B200VectorEnv(self.env_id, self.num_envs, env_seed=kwargs.get("env_seed") or 0,
+                                  env_base=kwargs.get("env_base", 0), device=self.device)
+        self.obs_dim = self.envs.single_observation_space.shape
+        self.act_dim = self.envs.single_action_space.shape
+        self.networks = kwargs.get("networks")
+        self.total_sample_number = 0
+        self.rollout = FusedRollout(self.env_id, self.num_envs, self.horizon, self.n_step, self.reward_scale, self.cost_scale,
+                                    device=self.device, state=self.envs.state)
+        self.envs.state.reset()        # base.py:98  envs.reset(seed=None)
+        self._actor = None
+
+    @property
+    def obs(self):
+        return self.envs.state.obs
+
+    def get_total_sample_num(self):
+        return self.total_sample_number
+
+    get_total_sample_number = get_total_sample_num
+
+    def load_state_dict(self, state_dict):
+        self.networks.load_state_dict(state_dict)
+
+    def set_actor(self, actor: ActorWeights):
+        self._actor = actor
+
+    def _sample(self):
+        actor = self._actor if self.networks is None else ActorWeights.from_policy(self.networks.policy, device=self.device)
+        if actor is None:
+            raise RuntimeError("sampler has no policy: assign `.networks` or call set_actor()")
+        return self.rollout.run(actor)
+
+    def sample(self):
+        self.total_sample_number += self.sample_batch_size
+        start = time.perf_counter()
+        data = self._sample()
+        torch.cuda.current_stream().synchronize()
+        return data, {SAMPLER_TIME_TAG: (time.perf_counter() - start) * 1000}

@@ -1,0 +1,62 @@
+"""CPU-only checks of the C-ABI boundary: the library builds/loads, exports every symbol the
+header declares, and the product path refuses to run without a GPU (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+import msacl_b200
+from msacl_b200 import _lib, specs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "msacl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(msacl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = msacl_b200.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/msacl_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES and the header disagree"
+    assert lib.msacl_abi_version() == 1
+
+
+def test_env_dims_match_spec_table():
+    import ctypes as C
+    lib = msacl_b200.load_library()
+    for name in specs.ENV_NAMES:
+        s = specs.get_spec(name)
+        dims = (C.c_int32 * 6)()
+        assert lib.msacl_env_dims(s.env_id, dims) == 0
+        assert list(dims) == [s.obs_dim, s.act_dim, s.sf_rows, s.sd_rows, s.obs_off, s.control_step]
+    dims = (C.c_int32 * 6)()
+    assert lib.msacl_env_dims(17, dims) == -1
+    assert b"unknown env id" in lib.msacl_last_error()
+
+
+def test_unknown_env_raises_like_reference():
+    with pytest.raises(ValueError, match="Unknown custom env"):
+        specs.get_spec("CartPole")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.dirname(_lib.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(Exception):
+        msacl_b200.create_envs(env_name="VanderPol", env_num=4, env_seed=0)

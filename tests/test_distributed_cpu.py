@@ -1,0 +1,50 @@
+"""world_size-2 gloo tests of the multi-GPU host logic (no GPU needed)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import msacl_b200  # noqa: F401
+from msacl_b200 import distributed as mdist
+
+
+def test_shard_ranges_cover_and_balance():
+    for total, world in [(16, 2), (17, 4), (1 << 24, 8), (5, 8)]:
+        spans = [mdist.shard_env_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    stats = torch.tensor([1.0 + rank, 10.0 * (rank + 1), 5.0, float(rank), 1.0, 0, 0, 0], dtype=torch.float64)
+    red = mdist.all_reduce_stats(stats)
+    sub = {"obs": torch.full((3, 4, 2), float(rank)), "rew": torch.full((3, 4), float(rank) + 0.5)}
+    full = mdist.all_gather_replay_batch(sub)
+    q.put((rank, red.tolist(), {k: v.tolist() for k, v in full.items()}, mdist.episode_summary(red)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_stats_and_replay_gather():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    for rank, red, full, summ in res:
+        assert red[:5] == [3.0, 30.0, 10.0, 1.0, 2.0]
+        assert torch.tensor(full["obs"]).shape == (6, 4, 2)
+        assert torch.tensor(full["obs"])[:3].eq(0).all() and torch.tensor(full["obs"])[3:].eq(1).all()
+        assert torch.tensor(full["rew"])[:, 0].tolist() == [0.5] * 3 + [1.5] * 3
+        assert summ["episodes"] == 3 and summ["mean_return"] == 10.0

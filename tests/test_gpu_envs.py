@@ -1,0 +1,185 @@
+"""GPU parity of the unfused env kernels (through the C ABI) against (a) golden vectors from
+the reference and (b) the NumPy oracle on seeded inputs.
+
+Stated tolerances (float32): VanderPol is bit-exact (same IEEE op order, no transcendental);
+envs with sin/cos differ by the ulp-level error of CUDA's sinf/cosf vs NumPy's SIMD kernels,
+amplified by at most 5 Euler sub-steps: |d obs| <= 2e-6 + 2e-6*|obs|; QuadTracking
+(closed-form Newton polar vs LAPACK sgesdd, 4 sub-steps): 5e-6 abs on obs, R, Omega.
+Done flags are compared exactly on all cases whose pre-bound margin exceeds the tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, quad_state
+from oracle import envs as oenv
+from oracle import philox as ophx
+from oracle import rollout as oroll
+
+pytestmark = pytest.mark.gpu
+
+BOX = oenv.ENV_NAMES[:5]
+TOL = {"VanderPol": (0.0, 0.0), "Pendulum": (2e-6, 2e-6), "DuctedFan": (2e-6, 2e-6), "TwoLink": (4e-6, 2e-6),
+       "SingleTrackCar": (2e-6, 2e-6), "QuadTracking": (5e-6, 2e-6)}
+
+
+def _vec(name, n, **kw):
+    from msacl_b200.envs import B200VectorEnv
+    return B200VectorEnv(name, n, **kw)
+
+
+def _safe_flags(name, obs, margin):
+    spec = oenv.SPECS[name]
+    near = (np.abs(obs - spec.obs_low) < margin) | (np.abs(obs - spec.obs_high) < margin)
+    return ~near.any(axis=1)
+
+
+def test_device_bounds_match_spec_table():
+    import ctypes as C
+    import msacl_b200
+    from msacl_b200 import specs
+    lib = msacl_b200.load_library()
+    for name in specs.ENV_NAMES:
+        s = specs.get_spec(name)
+        ol, oh = (C.c_float * s.obs_dim)(), (C.c_float * s.obs_dim)()
+        al, ah = (C.c_float * s.act_dim)(), (C.c_float * s.act_dim)()
+        assert lib.msacl_env_bounds(s.env_id, ol, oh, al, ah) == 0
+        assert np.array_equal(np.array(ol, np.float32), s.obs_low) and np.array_equal(np.array(oh, np.float32), s.obs_high)
+        assert np.array_equal(np.array(al, np.float32), s.act_low) and np.array_equal(np.array(ah, np.float32), s.act_high)
+        o = oenv.SPECS[name]
+        assert np.array_equal(o.obs_low, s.obs_low) and np.array_equal(o.act_high, s.act_high)
+
+
+@pytest.mark.parametrize("name", BOX)
+def test_box_env_step_vs_reference_golden(name):
+    g = load_golden(f"env_step_{name}.npz")
+    n = g["obs_in"].shape[0]
+    v = _vec(name, n)
+    v.state.set_box_state(g["obs_in"], g["step_in"])
+    nxt, rew, te, tr, fin = v.step_device(torch.as_tensor(g["act"]).cuda())
+    fin, rew, te, tr = fin.cpu().numpy(), rew.cpu().numpy(), te.cpu().numpy().astype(bool), tr.cpu().numpy().astype(bool)
+    atol, rtol = TOL[name]
+    if atol == 0.0:
+        assert np.array_equal(fin, g["obs_out"]) and np.array_equal(rew, g["reward"])
+    else:
+        np.testing.assert_allclose(fin, g["obs_out"], rtol=rtol, atol=atol)
+        np.testing.assert_allclose(rew, g["reward"], rtol=1e-5, atol=1e-5)
+    assert np.array_equal(tr, g["trunc"])
+    safe = _safe_flags(name, g["obs_out"], 1e-4)
+    assert np.array_equal(te[safe], g["term"][safe]) and te.any()
+    # autoreset: done envs restart at step 0 with a fresh in-box observation, others continue
+    done = te | tr
+    step_after = v.state.step.cpu().numpy()
+    assert np.array_equal(step_after[done], np.zeros(done.sum(), np.int32))
+    assert np.array_equal(step_after[~done], g["step_in"][~done] + 1)
+    nxt = nxt.cpu().numpy()
+    assert np.array_equal(nxt[~done], fin[~done])
+    spec = oenv.SPECS[name]
+    assert np.all((nxt[done] >= spec.reset_low) & (nxt[done] <= spec.reset_high))
+
+
+def test_quad_env_step_vs_reference_golden():
+    g = load_golden("env_step_QuadTracking.npz")
+    n = g["act"].shape[0]
+    v = _vec("QuadTracking", n)
+    s = quad_state(g, "in")
+    v.state.set_quad_state(s["x"], s["v"], s["R"], s["Om"], t=s["t"], Rd_last=s["Rd_last"], obs=s["obs"], step=s["step"])
+    nxt, rew, te, tr, fin = v.step_device(torch.as_tensor(g["act"]).cuda())
+    done = (te | tr).bool().cpu().numpy()
+    out = v.state.get_quad_state()
+    atol, rtol = TOL["QuadTracking"]
+    keep = ~done      # done envs were reset on the device
+    for k in ("x", "v", "R", "Om"):
+        np.testing.assert_allclose(out[k][keep], g[f"{k}_out"][keep], rtol=rtol, atol=atol, err_msg=k)
+    np.testing.assert_allclose(out["Rd_last"][keep], g["Rd_last_out"][keep], rtol=0, atol=1e-9)
+    assert np.array_equal(out["t"][keep], g["t_out"][keep])
+    # e_Omega carries (Rd - Rd_last)/0.04 -> error of Rd (float32 x,v inputs) is amplified 25x
+    np.testing.assert_allclose(fin.cpu().numpy(), g["obs_out"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(rew.cpu().numpy(), g["reward"], rtol=2e-5, atol=2e-4)
+    assert np.array_equal(te.bool().cpu().numpy(), g["term"]) and np.array_equal(tr.bool().cpu().numpy(), g["trunc"])
+
+
+def test_quad_init_from_raw_matches_reference_reset():
+    g = load_golden("env_step_QuadTracking.npz")
+    n = g["x_reset"].shape[0]
+    v = _vec("QuadTracking", n)
+    v.state.set_quad_state(g["x_reset"], g["v_reset"], g["R_reset"], g["Om_reset"])
+    out = v.state.get_quad_state()
+    np.testing.assert_allclose(out["obs"], g["obs_reset"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(out["Rd_last"], g["Rd_last_reset"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", oenv.ENV_NAMES)
+def test_philox_reset_matches_oracle(name):
+    n, seed, base = 777, 1234567890123, 10_000_000_000
+    v = _vec(name, n, env_seed=seed, env_base=base)
+    v.state.episode.copy_(torch.arange(n, dtype=torch.int32) % 5)
+    v.state.reset()
+    ids = base + np.arange(n, dtype=np.uint64)
+    want = oroll.philox_reset(name, seed, ids, np.arange(n) % 5)
+    got = v.state.obs.cpu().numpy()
+    if name == "QuadTracking":
+        np.testing.assert_allclose(got, want["obs"], rtol=1e-5, atol=2e-6)
+        st = v.state.get_quad_state()
+        np.testing.assert_allclose(st["R"], want["R"], rtol=0, atol=2e-7)
+        assert np.array_equal(st["x"], want["x"]) and np.array_equal(st["Om"], want["Om"])
+    else:
+        assert np.array_equal(got, want["obs"])      # integer Philox + one mul/add: bit-exact
+
+
+def test_action_noise_bits_and_moments():
+    import ctypes as C
+    import msacl_b200
+    from msacl_b200 import _lib
+    lib = msacl_b200.load_library()
+    n, A, seed, base, step = 1 << 16, 4, 42, 123, 77
+    out = torch.empty(n, A, device="cuda")
+    _lib.check(lib.msacl_action_noise(seed, base, n, A, step, out.data_ptr(), _lib.current_stream()))
+    got = out.cpu().numpy()
+    want = ophx.action_noise(seed, base + np.arange(n, dtype=np.uint64), step, A)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+    assert abs(got.mean()) < 0.01 and abs(got.std() - 1.0) < 0.01
+
+
+@pytest.mark.parametrize("name", oenv.ENV_NAMES)
+def test_env_step_vs_oracle_seeded_multistep(name):
+    """64 teacher-forced steps from Philox resets with random in-box actions at N=4096 incl.
+    autoresets (max_step shortened) -- state re-synchronised to the oracle every step."""
+    n, T, seed = 4096, 24, 99
+    spec = oenv.SPECS[name]
+    v = _vec(name, n, env_seed=seed, max_step=9)
+    v.state.reset()
+    object.__setattr__(spec, "max_step", 9)
+    try:
+        ids = np.arange(n, dtype=np.uint64)
+        ost = oroll.philox_reset(name, seed, ids, np.zeros(n, np.int64))
+        venv = oroll.VectorEnv(name, ost, seed=seed, env_ids=ids)
+        rng = np.random.default_rng(5)
+        atol, rtol = TOL[name]
+        n_done = 0
+        for t in range(T):
+            act = rng.uniform(spec.act_low, spec.act_high, size=(n, spec.act_dim)).astype(np.float32)
+            if name == "QuadTracking":
+                act[:, 0] = 42.5 + rng.normal(0, 3, n)
+                act[:, 1:] *= 0.05
+            nxt, rew, te, tr, fin = v.step_device(torch.as_tensor(act).cuda())
+            o_next, o_rew, o_te, o_tr, o_fin, _ = venv.step(act)
+            fin_h = fin.cpu().numpy()
+            scale = 10.0 if name == "QuadTracking" else 1.0
+            np.testing.assert_allclose(fin_h, o_fin, rtol=rtol * scale, atol=max(atol, 1e-12) * scale)
+            safe = _safe_flags(name, o_fin, 1e-4)
+            assert np.array_equal(te.bool().cpu().numpy()[safe], o_te[safe])
+            assert np.array_equal(tr.bool().cpu().numpy(), o_tr)
+            agree = te.bool().cpu().numpy() == o_te
+            np.testing.assert_allclose(nxt.cpu().numpy()[agree], o_next[agree], rtol=rtol * scale, atol=max(atol, 1e-12) * scale)
+            n_done += int((o_te | o_tr).sum())
+            # re-synchronise the device to the oracle state (teacher forcing)
+            if name == "QuadTracking":
+                s = venv.state
+                v.state.set_quad_state(s["x"], s["v"], s["R"], s["Om"], t=s["t"], Rd_last=s["Rd_last"], obs=s["obs"], step=s["step"])
+            else:
+                v.state.set_box_state(venv.state["obs"], venv.state["step"])
+            v.state.episode.copy_(torch.as_tensor(venv.episode.astype(np.int32)).cuda())
+        assert n_done > 0
+    finally:
+        object.__setattr__(spec, "max_step", 1000)

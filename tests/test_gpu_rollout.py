@@ -1,0 +1,162 @@
+"""GPU parity of the fused rollout kernel (actor + sample + clip + env + reward/cost + autoreset
++ n-step bookkeeping) against the NumPy oracle and the reference's golden sampler run.
+
+Tolerances (float32): the actor is an FP32 FFMA contraction whose summation order differs from
+BLAS, so pre-tanh logits agree to ~1e-5 relative; actions: 2e-5*|range|; log-prob: 2e-4 abs
+(it contains log(1+1e-6-tanh^2), ill-conditioned near saturation); env outputs as in
+test_gpu_envs.py after the action difference is propagated (5e-4 abs over one step).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import actor as oactor
+from oracle import envs as oenv
+from oracle import philox as ophx
+from oracle import rollout as oroll
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(name, n, K, n_step=5, seed=3, max_step=None, weights=None):
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    spec = oenv.SPECS[name]
+    w = weights or oactor.init_policy_weights(spec.obs_dim, spec.act_dim, seed=1)
+    ro = FusedRollout(name, n, K, n_step=n_step, seed=seed, max_step=max_step)
+    return ro, ActorWeights(w), w
+
+
+def _sync_state(ro, name, st):
+    if name == "QuadTracking":
+        ro.state.set_quad_state(st["x"], st["v"], st["R"], st["Om"], t=st["t"], Rd_last=st["Rd_last"], obs=st["obs"], step=st["step"])
+    else:
+        ro.state.set_box_state(st["obs"], st["step"])
+
+
+@pytest.mark.parametrize("name", oenv.ENV_NAMES)
+def test_fused_step_vs_oracle_teacher_forced(name):
+    n, T, seed = 1000, 12, 3            # n not a multiple of the 64-env tile on purpose
+    spec = oenv.SPECS[name]
+    ro, aw, w = _mk(name, n, 1, n_step=4, seed=seed, max_step=7)
+    ro.state.reset()
+    object.__setattr__(spec, "max_step", 7)
+    try:
+        ids = np.arange(n, dtype=np.uint64)
+        venv = oroll.VectorEnv(name, oroll.philox_reset(name, seed, ids, np.zeros(n, np.int64)), seed=seed, env_ids=ids)
+        emitter = oroll.WindowEmitter(n, 4)
+        rng = np.random.default_rng(0)
+        rngspan = (spec.act_high - spec.act_low)
+        for t in range(T):
+            eps = rng.standard_normal((n, spec.act_dim)).astype(np.float32)
+            tr = oroll.sampler_step(venv, w, eps)
+            emit, _ = emitter.push(tr)
+            ro.run(aw, eps=torch.as_tensor(eps[None]).cuda())
+            g = {k: v[ro.tr.H].cpu().numpy() for k, v in ro.tr.fields().items()}
+            assert np.array_equal(g["obs"], tr["obs"])                      # same (re-synced) input state
+            np.testing.assert_allclose(g["act"], tr["act"], rtol=0, atol=2e-5 * rngspan.max())
+            np.testing.assert_allclose(g["logp"], tr["logp"], rtol=1e-4, atol=3e-4)
+            tol = 2e-3 if name == "QuadTracking" else 5e-4
+            np.testing.assert_allclose(g["obs2"], tr["obs2"], rtol=1e-4, atol=tol)
+            np.testing.assert_allclose(g["rew"], tr["rew"], rtol=2e-3, atol=0.5)
+            np.testing.assert_allclose(g["cost"], tr["cost"], rtol=2e-3, atol=0.5)
+            near = (np.abs(tr["obs2"] - spec.obs_low) < 5e-3).any(1) | (np.abs(tr["obs2"] - spec.obs_high) < 5e-3).any(1)
+            assert np.array_equal(g["done"].astype(bool)[~near], tr["done"][~near])
+            assert np.array_equal(g["emit"].astype(bool), emit)
+            _sync_state(ro, name, venv.state)
+            ro.state.episode.copy_(torch.as_tensor(venv.episode.astype(np.int32)).cuda())
+            # keep run counters aligned if a near-boundary env disagreed on done
+            ro.state.run.copy_(torch.as_tensor(emitter.run.astype(np.int32)).cuda())
+        assert venv.episode.sum() > 0
+    finally:
+        object.__setattr__(spec, "max_step", 1000)
+
+
+@pytest.mark.parametrize("name", ["VanderPol", "TwoLink", "QuadTracking"])
+def test_internal_philox_equals_explicit_noise(name):
+    import msacl_b200
+    from msacl_b200 import _lib
+    n, K, seed = 640, 6, 11
+    spec = oenv.SPECS[name]
+    ro1, aw, _ = _mk(name, n, K, seed=seed)
+    ro2, _, _ = _mk(name, n, K, seed=seed)
+    ro1.state.reset(); ro2.state.reset()
+    ro1.global_step = ro2.global_step = 40
+    eps = torch.empty(K, n, spec.act_dim, device="cuda")
+    lib = msacl_b200.load_library()
+    for k in range(K):
+        _lib.check(lib.msacl_action_noise(seed, 0, n, spec.act_dim, 40 + k, eps[k].data_ptr(), _lib.current_stream()))
+    ro1.run(aw)
+    ro2.run(aw, eps=eps)
+    for k, v in ro1.tr.fields().items():
+        assert torch.equal(v, ro2.tr.fields()[k]), k
+    assert torch.equal(ro1.state.sf, ro2.state.sf)
+    # and the noise itself matches the oracle's Philox restatement
+    want = ophx.action_noise(seed, np.arange(n, dtype=np.uint64), 42, spec.act_dim)
+    np.testing.assert_allclose(eps[2].cpu().numpy(), want, rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["Pendulum", "DuctedFan"])
+def test_free_running_rollout_tracks_oracle(name):
+    """K=16 steps in one launch without re-sync: tolerance grows with the horizon."""
+    n, K, seed = 512, 16, 5
+    spec = oenv.SPECS[name]
+    ro, aw, w = _mk(name, n, K, n_step=4, seed=seed)
+    ro.state.reset()
+    ids = np.arange(n, dtype=np.uint64)
+    venv = oroll.VectorEnv(name, oroll.philox_reset(name, seed, ids, np.zeros(n, np.int64)), seed=seed, env_ids=ids)
+    rng = np.random.default_rng(1)
+    eps = rng.standard_normal((K, n, spec.act_dim)).astype(np.float32)
+    ro.run(aw, eps=torch.as_tensor(eps).cuda())
+    g = {k: v[ro.tr.H:].cpu().numpy() for k, v in ro.tr.fields().items()}
+    alive = np.ones(n, bool)
+    for k in range(K):
+        tr = oroll.sampler_step(venv, w, eps[k])
+        alive &= g["done"][k].astype(bool) == tr["done"]
+        np.testing.assert_allclose(g["obs2"][k][alive], tr["obs2"][alive], rtol=1e-3, atol=2e-3)
+        np.testing.assert_allclose(g["act"][k][alive], tr["act"][alive], rtol=0, atol=5e-3)
+    assert alive.mean() > 0.98
+
+
+def test_golden_sampler_actions_and_logp_from_reference():
+    """The reference sampler's own recorded step (weights, obs, eps -> action, log-prob) replayed
+    through the fused kernel for every env."""
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    for name in oenv.ENV_NAMES:
+        g = load_golden(f"sampler_{name}.npz")
+        spec = oenv.SPECS[name]
+        T, N = g["step_eps"].shape[:2]
+        aw = ActorWeights([(g[f"W{i}"], g[f"b{i}"]) for i in range(3)])
+        ro = FusedRollout(name, N, 1, n_step=int(g["n_step"]), max_step=int(g["max_step"]))
+        post = {k[5:]: g[k] for k in g if k.startswith("post_")}
+        prev = {k[5:]: g[k] for k in g if k.startswith("init_")}
+        for t in range(T):
+            if name == "QuadTracking":
+                ro.state.set_quad_state(prev["x"], prev["v"], prev["R"], prev["Om"], t=prev["t"], Rd_last=prev["Rd_last"],
+                                        obs=prev["obs"], step=prev["step"])
+            else:
+                ro.state.set_box_state(prev["obs"], prev["step"])
+            ro.run(aw, eps=torch.as_tensor(g["step_eps"][t][None]).cuda())
+            out = {k: v[ro.tr.H].cpu().numpy() for k, v in ro.tr.fields().items()}
+            span = float((spec.act_high - spec.act_low).max())
+            np.testing.assert_allclose(out["act"], g["step_act"][t], rtol=0, atol=2e-5 * span)
+            v = g["step_valid"][t]
+            np.testing.assert_allclose(out["logp"][v], g["step_logp"][t][v], rtol=1e-4, atol=3e-4)
+            tol = 2e-3 if name == "QuadTracking" else 5e-4
+            np.testing.assert_allclose(out["obs2"], g["step_obs2"][t], rtol=1e-4, atol=tol)
+            assert np.array_equal(out["done"].astype(bool), g["step_done"][t] > 0)
+            np.testing.assert_allclose(out["rew"][v], g["step_rew"][t][v], rtol=2e-3, atol=0.5)
+            np.testing.assert_allclose(out["cost"][v], g["step_cost"][t][v], rtol=2e-3, atol=0.5)
+            prev = {k: post[k][t] for k in post}
+
+
+def test_deterministic_mode_is_tanh_mean():
+    name, n = "TwoLink", 256
+    spec = oenv.SPECS[name]
+    ro, aw, w = _mk(name, n, 1)
+    ro.state.reset()
+    obs = ro.state.obs.cpu().numpy()
+    ro.run(aw, deterministic=True)
+    mean, _ = oactor.policy_forward(w, obs)
+    want = np.clip(oactor.tanh_gauss_mode(mean, spec.act_low, spec.act_high), spec.act_low, spec.act_high)
+    np.testing.assert_allclose(ro.tr.act[ro.tr.H].cpu().numpy(), want, rtol=0, atol=1e-3)

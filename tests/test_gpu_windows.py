@@ -1,0 +1,99 @@
+"""Bit-exact checks of the n-step window scatter + replay ring (integer bookkeeping and payload)
+against the oracle's restatement of base.py:178-217 + nstep_replay_buffer.py, and against the
+reference's own recorded ring (golden)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import actor as oactor
+from oracle import envs as oenv
+from oracle import rollout as oroll
+
+pytestmark = pytest.mark.gpu
+FIELDS = ("obs", "act", "rew", "cost", "obs2", "done", "logp")
+
+
+@pytest.mark.parametrize("name,ring_size", [("VanderPol", 997), ("TwoLink", 100000), ("QuadTracking", 5003)])
+def test_window_store_matches_oracle_ring(name, ring_size):
+    from msacl_b200.buffer import B200NstepReplayBuffer
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    n, K, chunks, n_step = 300, 7, 6, 5
+    spec = oenv.SPECS[name]
+    ro = FusedRollout(name, n, K, n_step=n_step, seed=8, max_step=11)
+    ro.state.reset()
+    aw = ActorWeights(oactor.init_policy_weights(spec.obs_dim, spec.act_dim, seed=2))
+    buf = B200NstepReplayBuffer(obs_dim=spec.obs_dim, act_dim=spec.act_dim, buffer_max_size=ring_size, n_step=n_step)
+    emitter = oroll.WindowEmitter(n, n_step)
+    ring = oroll.ReplayRing(ring_size, n_step, spec.obs_dim, spec.act_dim)
+    total = 0
+    for c in range(chunks):
+        batch = ro.run(aw)
+        cnt = buf.add_batch(batch)
+        f = {k: v[ro.tr.H:].cpu().numpy() for k, v in ro.tr.fields().items()}
+        host_windows = batch.materialize()
+        wins_all = []
+        for k in range(K):
+            tr = {fld: f[fld][k] for fld in FIELDS}
+            tr["done"] = tr["done"].astype(bool)
+            emit, wins = emitter.push(tr)
+            assert np.array_equal(emit, f["emit"][k].astype(bool))
+            wins_all += wins
+        ring.add_batch(wins_all)
+        total += len(wins_all)
+        assert int(cnt.item()) == len(wins_all) == len(host_windows)
+        for hw, ow in zip(host_windows[:50], wins_all[:50]):
+            assert np.array_equal(hw.n_step_obs, ow["obs"]) and np.array_equal(hw.n_step_log_prob, ow["logp"])
+        assert buf.ptr == ring.ptr and buf.size == ring.size
+    assert total > ring_size or ring_size > 5000     # the small rings must have wrapped
+    for k in FIELDS:
+        assert np.array_equal(buf.n_step_buf[k].cpu().numpy(), ring.buf[k]), k
+    # gather = fancy indexing
+    idx = np.random.default_rng(0).integers(0, ring.size, size=257)
+    got = buf.gather(idx)
+    want = ring.gather(idx)
+    for k in FIELDS:
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    b = buf.sample_batch(64)
+    assert set(b) == set(FIELDS) and b["obs"].shape == (64, n_step, spec.obs_dim) and b["rew"].shape == (64, n_step)
+
+
+def test_ring_from_reference_golden_transitions():
+    """Feed the reference sampler's recorded per-step transitions through the device scatter and
+    compare the ring with the reference NstepReplayBuffer's arrays bit for bit."""
+    from msacl_b200 import _lib
+    from msacl_b200.buffer import B200NstepReplayBuffer
+    from msacl_b200.sampler import DeviceWindowBatch, TransitionBuffers
+    from msacl_b200.specs import get_spec
+    for name in oenv.ENV_NAMES:
+        g = load_golden(f"sampler_{name}.npz")
+        spec = get_spec(name)
+        T, N = g["step_eps"].shape[:2]
+        n_step = int(g["n_step"])
+        buf = B200NstepReplayBuffer(obs_dim=spec.obs_dim, act_dim=spec.act_dim, buffer_max_size=int(g["ring"]), n_step=n_step)
+        K = 8
+        tr = TransitionBuffers(spec, N, K, n_step, torch.device("cuda"))
+        for c in range(T // K):
+            tr.roll_history()
+            sl = slice(c * K, (c + 1) * K)
+            put = lambda dst, a: dst[tr.H:].copy_(torch.as_tensor(np.nan_to_num(a[sl])).to(dst.dtype).cuda())
+            put(tr.obs, g["step_obs"]); put(tr.act, g["step_act"]); put(tr.rew, g["step_rew"]); put(tr.cost, g["step_cost"])
+            put(tr.obs2, g["step_obs2"]); put(tr.logp, g["step_logp"])
+            tr.done[tr.H:].copy_(torch.as_tensor((g["step_done"][sl] > 0).astype(np.uint8)).cuda())
+            tr.emit[tr.H:].copy_(torch.as_tensor(g["step_emit"][sl].astype(np.uint8)).cuda())
+            buf.add_batch(DeviceWindowBatch(tr, n_step))
+            assert buf.ptr == g["ptr_after"][(c + 1) * K - 1] and buf.size == g["size_after"][(c + 1) * K - 1]
+        for k in FIELDS:
+            assert np.array_equal(buf.n_step_buf[k].cpu().numpy(), g["ring_" + k]), (name, k)
+
+
+def test_host_store_path_and_ram():
+    from msacl_b200.buffer import B200NstepReplayBuffer
+    buf = B200NstepReplayBuffer(obs_dim=2, act_dim=1, buffer_max_size=3, n_step=4)
+    assert buf.__get_RAM__() == 0.0 and len(buf) == 0
+    for i in range(5):
+        buf.store(np.full((4, 2), i, np.float32), np.full((4, 1), i, np.float32), np.full(4, i), np.full(4, i),
+                  np.full((4, 2), i, np.float32), np.zeros(4), np.full(4, -i))
+    assert buf.ptr == 2 and buf.size == 3
+    assert buf.n_step_buf["rew"][:, 0].cpu().tolist() == [3.0, 4.0, 2.0]
+    assert buf.__get_RAM__() == round(3 * 4 * (2 + 1 + 1 + 1 + 2 + 1 + 1) * 4 / 2 ** 20, 2)
