@@ -91,7 +91,9 @@ def test_quad_env_step_vs_reference_golden():
     keep = ~done      # done envs were reset on the device
     for k in ("x", "v", "R", "Om"):
         np.testing.assert_allclose(out[k][keep], g[f"{k}_out"][keep], rtol=rtol, atol=atol, err_msg=k)
-    np.testing.assert_allclose(out["Rd_last"][keep], g["Rd_last_out"][keep], rtol=0, atol=1e-9)
+    # Rd is a function of the float32 x, v (gain kx = 69.44 on e_x): ulp-level differences in v
+    # (through R[:,2] from the polar step) show up at ~3e-7 in the desired frame
+    np.testing.assert_allclose(out["Rd_last"][keep], g["Rd_last_out"][keep], rtol=0, atol=2e-6)
     assert np.array_equal(out["t"][keep], g["t_out"][keep])
     # e_Omega carries (Rd - Rd_last)/0.04 -> error of Rd (float32 x,v inputs) is amplified 25x
     np.testing.assert_allclose(fin.cpu().numpy(), g["obs_out"], rtol=1e-5, atol=2e-5)
