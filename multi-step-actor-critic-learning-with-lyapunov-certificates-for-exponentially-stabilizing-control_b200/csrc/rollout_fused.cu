@@ -1,23 +1,26 @@
 // Fused K-step rollout kernel: actor MLP (obs -> 256 -> 256 -> 2A) + TanhGauss sample + clip +
-// env dynamics + reward/cost + same-step autoreset + n-step bookkeeping, for a tile of 64 env
-// instances per CTA.  Replaces K iterations of BaseSampler._n_step
-// (RL/trainer/sampler/base.py:118-163,220).
+// env dynamics + reward/cost + same-step autoreset + n-step bookkeeping.  Replaces K iterations
+// of BaseSampler._n_step (RL/trainer/sampler/base.py:118-163,220).
 //
-// Design (B200, sm_100a):
-//   * persistent grid of 2 CTAs per SM (148*2); each CTA owns tiles of TM=64 envs and keeps
-//     the env state in the registers of its first 64 threads for all K steps -- HBM sees the
-//     state once per launch and only the transition record per step.
+// Design (B200, sm_100a), v2 -- warp specialised, one persistent CTA of 12 warps per SM:
+//   * warps 0-7 ("GEMM warps") run the MLP for two 64-env tiles A/B alternately; warps 8-9 own
+//     the env instances of tile A, warps 10-11 those of tile B ("env warps": state in registers
+//     for all K steps, so HBM sees the state once per launch and one transition record per step).
+//     While the env warps of tile A sample the action and integrate the ODE, the GEMM warps are
+//     already multiplying tile B: the latency-bound env phase is off the FFMA critical path.
+//     Hand-offs use named barriers (bar.arrive / bar.sync): X_READY[T] (env -> GEMM, obs tile in
+//     smem) and LOGITS[T] (GEMM -> env).
 //   * the MLP is >99% of the FLOPs and is an FP32 contraction (parity with the
-//     reference's fp32 torch actor rules out bf16/tf32 single-pass tensor cores), so the
+//     reference's fp32 torch actor rules out single-pass bf16/tf32 tensor-core MMA), so the
 //     binding roofline is the FP32 FFMA pipe.  Layer 2 (64x256x256 per tile-step) is a
-//     register-tiled SGEMM: 256 threads, 8x8 accumulators each; A = hidden-1 activations
-//     resident in shared memory K-major (warp-broadcast float4 reads), B = W2^T streamed from
-//     L2 in 8-row chunks through a cp.async double buffer (W2 is 256 KB and is shared by
-//     every CTA, so it lives in the 126 MB L2).
-//   * layer 3 (256 -> 2A) is applied to the register tile directly; partial sums are combined
-//     with a halving warp-shuffle reduction (62 shuffles for 64 values).
-//   * while one CTA runs its (latency-bound, 2-warp) env phase the co-resident CTA keeps the
-//     FFMA pipe busy with its GEMM phase.
+//     register-tiled SGEMM: 8x8 accumulators per thread; A = hidden-1 activations resident in
+//     shared memory K-major (warp-broadcast float4 reads), B = W2^T streamed from L2 in 32-row
+//     chunks through a cp.async double buffer that never drains (the chunk sequence is the same
+//     for every tile, so the prefetch runs across tile boundaries).  W2 (256 KB) is shared by
+//     all CTAs and lives in the 126 MB L2.
+//   * layer 1 (D -> 256) is register-tiled too (2 envs x 32 units per thread, conflict-free
+//     float2 stores of the K-major activations); layer 3 (256 -> 2A) is applied to the layer-2
+//     register tile and combined with a halving warp-shuffle reduction (62 shuffles / 64 values).
 // Compiled with -fmad=false: only the explicit __fmaf_rn calls below contract.
 #include "common.cuh"
 
@@ -25,27 +28,32 @@ namespace msacl {
 
 constexpr int TM = 64;          // envs per tile
 constexpr int HID = 256;        // hidden width (reference default, msacl_train.py policy_hidden_sizes)
-constexpr int NTHREADS = 256;
-constexpr int KC = 8;           // W2^T rows per cp.async chunk
+constexpr int NGEMM = 256;      // GEMM threads (warps 0-7)
+constexpr int NTILE = 2;        // tiles in flight per CTA
+constexpr int NTHREADS = NGEMM + NTILE * TM;   // 384
+constexpr int KC = 32;          // W2^T rows per cp.async chunk
 constexpr int NCHUNK = HID / KC;
+static_assert(NCHUNK % 2 == 0, "buffer parity must be tile-invariant");
 
-template <int D> struct PadD { static constexpr int value = (D <= 2) ? 2 : ((D + 3) / 4) * 4; };
+enum : int { BAR_GEMM = 1, BAR_LOGITS = 2, BAR_XREADY = 4 };
 
 template <int ID>
 struct Smem {
   using E = Env<ID>;
-  static constexpr int DP = PadD<E::D>::value;
   static constexpr int A2 = 2 * E::A;
-  float h1[HID * TM];          // [k][m]
-  float wc[2][KC * HID];       // W2^T chunks [k][n]
-  float w1[HID * DP];          // [n][dp] rows padded to a vector width
-  float w3[A2 * HID];          // [j][k]
+  float h1[HID * TM];            // [k][m]  hidden-1 activations of the tile in the GEMM
+  float wc[2][KC * HID];         // W2^T chunks [k][n]
+  float w1t[E::D * HID];         // W1^T [d][n]
+  float w3[A2 * HID];            // [j][k]
   float b1[HID];
   float b2[HID];
   float b3[8];
-  float x[E::D * TM];          // obs tile [d][m]
-  float out[A2 * TM];          // logits [j][m]
+  float x[NTILE][E::D * TM];     // obs tiles [d][m]
+  float out[NTILE][A2 * TM];     // logits [j][m]
 };
+
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -81,245 +89,263 @@ __device__ __forceinline__ void warp_multi_reduce(float (&v)[V], int lane) {
 }
 
 template <int ID>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, 1)
 rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t step_base, int n_step,
                      float reward_scale, float cost_scale, const float* __restrict__ eps, int deterministic,
                      msacl_transitions_t out, double* stats) {
   using E = Env<ID>;
   using S = Smem<ID>;
-  constexpr int D = E::D, A = E::A, A2 = 2 * A, DP = S::DP;
+  constexpr int D = E::D, A = E::A, A2 = 2 * A;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // ---- stage the small weights once per CTA
-  for (int i = tid; i < HID * DP; i += NTHREADS) {
-    const int n = i / DP, d = i % DP;
-    sm.w1[i] = d < D ? actor.w1[n * D + d] : 0.f;
+  for (int i = tid; i < D * HID; i += NTHREADS) {
+    const int d = i / HID, n = i % HID;
+    sm.w1t[i] = actor.w1[n * D + d];
   }
   for (int i = tid; i < A2 * HID; i += NTHREADS) sm.w3[i] = actor.w3[i];
   for (int i = tid; i < HID; i += NTHREADS) { sm.b1[i] = actor.b1[i]; sm.b2[i] = actor.b2[i]; }
   if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
+  __syncthreads();
 
   const int64_t num_tiles = (st.n + TM - 1) / TM;
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t env0 = tile * TM;
-    const int64_t gi = env0 + tid;              // env owned by this thread (tid < TM)
-    const bool owner = tid < TM && gi < st.n;
-    EnvRegs<ID> r;
-    if (owner) {
-      r.load(st, gi);
-#pragma unroll
-      for (int d = 0; d < D; ++d) sm.x[d * TM + tid] = r.obs()[d];
-    } else if (tid < TM) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) sm.x[d * TM + tid] = 0.f;
-    }
+  const int64_t num_pairs = (num_tiles + NTILE - 1) / NTILE;
 
-    for (int k = 0; k < K; ++k) {
-      // prefetch W2^T chunk 0 (overlaps layer 1)
-      {
-        const float4* src = reinterpret_cast<const float4*>(actor.w2t);
-        float4* dst = reinterpret_cast<float4*>(sm.wc[0]);
-        cp_async16(dst + tid, src + tid);
-        cp_async16(dst + tid + NTHREADS, src + tid + NTHREADS);
-        cp_async_commit();
-      }
-      __syncthreads();   // x tile (and, first time, weights) visible
-
-      // ---- layer 1: h1[n][m] = relu(b1[n] + sum_d W1[n][d] x[m][d]); thread = (m, 64 n's)
-      {
-        const int m = tid & (TM - 1), ng = tid >> 6;
-        float xv[DP];
+  if (tid < NGEMM) {
+    // =========================== GEMM warps ===========================
+    auto prefetch_chunk = [&](int ch) {
+      const float4* src = reinterpret_cast<const float4*>(actor.w2t + (size_t)ch * KC * HID);
+      float4* dst = reinterpret_cast<float4*>(sm.wc[ch & 1]);
 #pragma unroll
-        for (int d = 0; d < DP; ++d) xv[d] = d < D ? sm.x[d * TM + m] : 0.f;
-#pragma unroll 4
-        for (int nn = 0; nn < 64; ++nn) {
-          const int n = ng * 64 + nn;
-          float acc = sm.b1[n];
-          if constexpr (DP % 4 == 0) {
+      for (int q = 0; q < KC * HID / 4 / NGEMM; ++q) cp_async16(dst + tid + q * NGEMM, src + tid + q * NGEMM);
+      cp_async_commit();
+    };
+    prefetch_chunk(0);
+    for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+      const int nt = (int)((num_tiles - NTILE * pair) < NTILE ? (num_tiles - NTILE * pair) : NTILE);
+      for (int k = 0; k < K; ++k) {
+        for (int T = 0; T < nt; ++T) {
+          bar_sync(BAR_XREADY + T, NGEMM + TM);   // obs tile T in smem; all GEMM warps done with h1
+          float acc[8][8];
+          // ---- layer 1: thread tile = envs {2*lane, 2*lane+1} x units warp*32..+32
+          {
 #pragma unroll
-            for (int d4 = 0; d4 < DP / 4; ++d4) {
-              const float4 w = *reinterpret_cast<const float4*>(&sm.w1[n * DP + 4 * d4]);
-              acc = __fmaf_rn(w.x, xv[4 * d4 + 0], acc);
-              acc = __fmaf_rn(w.y, xv[4 * d4 + 1], acc);
-              acc = __fmaf_rn(w.z, xv[4 * d4 + 2], acc);
-              acc = __fmaf_rn(w.w, xv[4 * d4 + 3], acc);
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = *reinterpret_cast<const float4*>(&sm.b1[warp * 32 + 4 * q]);
+              acc[0][q] = b.x; acc[1][q] = b.y; acc[2][q] = b.z; acc[3][q] = b.w;     // env 2*lane
+              acc[4][q] = b.x; acc[5][q] = b.y; acc[6][q] = b.z; acc[7][q] = b.w;     // env 2*lane+1
             }
-          } else {
-            const float2 w = *reinterpret_cast<const float2*>(&sm.w1[n * DP]);
-            acc = __fmaf_rn(w.x, xv[0], acc);
-            acc = __fmaf_rn(w.y, xv[1], acc);
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              const float2 xv = *reinterpret_cast<const float2*>(&sm.x[T][d * TM + 2 * lane]);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(&sm.w1t[d * HID + warp * 32 + 4 * q]);
+                acc[0][q] = __fmaf_rn(w.x, xv.x, acc[0][q]); acc[1][q] = __fmaf_rn(w.y, xv.x, acc[1][q]);
+                acc[2][q] = __fmaf_rn(w.z, xv.x, acc[2][q]); acc[3][q] = __fmaf_rn(w.w, xv.x, acc[3][q]);
+                acc[4][q] = __fmaf_rn(w.x, xv.y, acc[4][q]); acc[5][q] = __fmaf_rn(w.y, xv.y, acc[5][q]);
+                acc[6][q] = __fmaf_rn(w.z, xv.y, acc[6][q]); acc[7][q] = __fmaf_rn(w.w, xv.y, acc[7][q]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int n = warp * 32 + 4 * q + c;
+                *reinterpret_cast<float2*>(&sm.h1[n * TM + 2 * lane]) =
+                    make_float2(fmaxf(acc[c][q], 0.f), fmaxf(acc[4 + c][q], 0.f));
+              }
           }
-          sm.h1[n * TM + m] = fmaxf(acc, 0.f);
-        }
-      }
 
-      // ---- layer 2: register-tiled 64x256x256 SGEMM; thread tile = envs warp*8..+8 x
-      //      columns {lane*4..+4, 128+lane*4..+4}
-      float acc[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
-
-      for (int ch = 0; ch < NCHUNK; ++ch) {
-        cp_async_wait<0>();
-        __syncthreads();   // chunk ch landed for everyone; everyone finished chunk ch-1 (and layer 1)
-        if (ch + 1 < NCHUNK) {
-          const float4* src = reinterpret_cast<const float4*>(actor.w2t + (size_t)(ch + 1) * KC * HID);
-          float4* dst = reinterpret_cast<float4*>(sm.wc[(ch + 1) & 1]);
-          cp_async16(dst + tid, src + tid);
-          cp_async16(dst + tid + NTHREADS, src + tid + NTHREADS);
-          cp_async_commit();
-        }
-        const float* wb = sm.wc[ch & 1];
-        const float* ha = sm.h1 + (size_t)ch * KC * TM + warp * 8;
-#pragma unroll
-        for (int kk = 0; kk < KC; ++kk) {
-          const float4 a0 = *reinterpret_cast<const float4*>(ha + kk * TM);
-          const float4 a1 = *reinterpret_cast<const float4*>(ha + kk * TM + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(wb + kk * HID + lane * 4);
-          const float4 b1 = *reinterpret_cast<const float4*>(wb + kk * HID + 128 + lane * 4);
-          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          // ---- layer 2: register-tiled 64x256x256 SGEMM; thread tile = envs warp*8..+8 x
+          //      columns {lane*4..+4, 128+lane*4..+4}
 #pragma unroll
           for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[i][c] = __fmaf_rn(av[i], bv[c], acc[i][c]);
-        }
-      }
+            for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
 
-      // ---- bias + ReLU, then layer 3 on the register tile
-      {
-        const float4 q0 = *reinterpret_cast<const float4*>(&sm.b2[lane * 4]);
-        const float4 q1 = *reinterpret_cast<const float4*>(&sm.b2[128 + lane * 4]);
-        const float bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+          for (int ch = 0; ch < NCHUNK; ++ch) {
+            cp_async_wait<0>();
+            bar_sync(BAR_GEMM, NGEMM);        // chunk ch landed for all; chunk ch-1 (and layer 1) finished by all
+            prefetch_chunk((ch + 1) % NCHUNK); // runs across tile boundaries: the pipe never drains
+            const float* wb = sm.wc[ch & 1];
+            const float* ha = sm.h1 + (size_t)ch * KC * TM + warp * 8;
+#pragma unroll 1
+            for (int k8 = 0; k8 < KC; k8 += 8) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+              for (int kk = 0; kk < 8; ++kk) {
+                const float4 a0 = *reinterpret_cast<const float4*>(ha + (k8 + kk) * TM);
+                const float4 a1 = *reinterpret_cast<const float4*>(ha + (k8 + kk) * TM + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(wb + (k8 + kk) * HID + lane * 4);
+                const float4 b1 = *reinterpret_cast<const float4*>(wb + (k8 + kk) * HID + 128 + lane * 4);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[i][c] = fmaxf(acc[i][c] + bb[c], 0.f);
-      }
-      float part[8 * A2];   // index i*A2 + j
+                for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < A2; ++j) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&sm.w3[j * HID + lane * 4]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&sm.w3[j * HID + 128 + lane * 4]);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float p = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) p = __fmaf_rn(acc[i][c], wv[c], p);
-          part[i * A2 + j] = p;
-        }
-      }
-      warp_multi_reduce<8 * A2>(part, lane);
-      {
-        constexpr int V = 8 * A2;
-        if constexpr (V >= 32) {
-          constexpr int per = V / 32;
-#pragma unroll
-          for (int q = 0; q < per; ++q) {
-            const int orig = lane * per + q;
-            const int i = orig / A2, j = orig % A2;
-            sm.out[j * TM + warp * 8 + i] = part[q] + sm.b3[j];
+                  for (int c = 0; c < 8; ++c) acc[i][c] = __fmaf_rn(av[i], bv[c], acc[i][c]);
+              }
+            }
           }
-        } else {
-          constexpr int rep = 32 / V;
-          if (lane % rep == 0) {
-            const int orig = lane / rep;
-            const int i = orig / A2, j = orig % A2;
-            sm.out[j * TM + warp * 8 + i] = part[0] + sm.b3[j];
-          }
-        }
-      }
-      __syncthreads();   // logits visible; all reads of x / h1 for this step are done
 
-      // ---- env phase: one thread per env
+          // ---- bias + ReLU, then layer 3 on the register tile
+          {
+            const float4 q0 = *reinterpret_cast<const float4*>(&sm.b2[lane * 4]);
+            const float4 q1 = *reinterpret_cast<const float4*>(&sm.b2[128 + lane * 4]);
+            const float bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[i][c] = fmaxf(acc[i][c] + bb[c], 0.f);
+          }
+          float part[8 * A2];   // index i*A2 + j
+#pragma unroll
+          for (int j = 0; j < A2; ++j) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&sm.w3[j * HID + lane * 4]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&sm.w3[j * HID + 128 + lane * 4]);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float p = 0.f;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) p = __fmaf_rn(acc[i][c], wv[c], p);
+              part[i * A2 + j] = p;
+            }
+          }
+          warp_multi_reduce<8 * A2>(part, lane);
+          {
+            constexpr int V = 8 * A2;
+            if constexpr (V >= 32) {
+              constexpr int per = V / 32;
+#pragma unroll
+              for (int q = 0; q < per; ++q) {
+                const int orig = lane * per + q;
+                const int i = orig / A2, j = orig % A2;
+                sm.out[T][j * TM + warp * 8 + i] = part[q] + sm.b3[j];
+              }
+            } else {
+              constexpr int rep = 32 / V;
+              if (lane % rep == 0) {
+                const int orig = lane / rep;
+                const int i = orig / A2, j = orig % A2;
+                sm.out[T][j * TM + warp * 8 + i] = part[0] + sm.b3[j];
+              }
+            }
+          }
+          __threadfence_block();
+          bar_arrive(BAR_LOGITS + T, NGEMM + TM);   // logits of tile T are in smem
+        }
+      }
+    }
+    cp_async_wait<0>();
+  } else {
+    // =========================== env warps ===========================
+    const int T = (tid - NGEMM) >> 6;        // tile slot owned by this warp pair
+    const int et = (tid - NGEMM) & (TM - 1); // env within the tile
+    for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+      const int64_t tile = NTILE * pair + T;
+      if (tile >= num_tiles) break;          // CTA-uniform per warp pair; GEMM warps skip this slot too
+      const int64_t gi = tile * TM + et;
+      const bool owner = gi < st.n;
+      EnvRegs<ID> r;
       if (owner) {
-        const int64_t row = (int64_t)k * st.n + gi;
-        if (out.obs) {
+        r.load(st, gi);
 #pragma unroll
-          for (int d = 0; d < D; ++d) out.obs[row * D + d] = r.obs()[d];
-        }
-        float z[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!deterministic) {
-          if (eps) {
+        for (int d = 0; d < D; ++d) sm.x[T][d * TM + et] = r.obs()[d];
+      } else {
 #pragma unroll
-            for (int j = 0; j < A; ++j) z[j] = eps[row * A + j];
-          } else {
-            action_noise4(st.seed, st.env_base + (uint64_t)gi, step_base + (uint32_t)k, z);
+        for (int d = 0; d < D; ++d) sm.x[T][d * TM + et] = 0.f;
+      }
+      __threadfence_block();
+      bar_arrive(BAR_XREADY + T, NGEMM + TM);
+      for (int k = 0; k < K; ++k) {
+        bar_sync(BAR_LOGITS + T, NGEMM + TM);
+        if (owner) {
+          const int64_t row = (int64_t)k * st.n + gi;
+          if (out.obs) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) out.obs[row * D + d] = r.obs()[d];
           }
-        }
-        float act[A];
-        float lp_gauss = 0.f, lp_tanh = 0.f, lp_scale = 0.f;
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
+          if (!deterministic) {
+            if (eps) {
 #pragma unroll
-        for (int j = 0; j < A; ++j) {
-          const float mean = sm.out[j * TM + tid];
-          const float ls = sm.out[(A + j) * TM + tid];
-          const float sd = expf(fminf(fmaxf(ls, actor.min_log_std), actor.max_log_std));
-          const float half = (E::act_high(j) - E::act_low(j)) / 2.0f;
-          const float mid = (E::act_high(j) + E::act_low(j)) / 2.0f;
-          float u = deterministic ? mean : (sd * z[j] + mean);      // torch.normal: z*std, then +mean
-          const float th = tanhf(u);
-          const float a_lim = half * th + mid;
-          // Normal.log_prob(u) = -((u-mean)^2)/(2 var) - log(std) - log(sqrt(2 pi))
-          const float diff = u - mean;
-          const float g = ((-(diff * diff)) / (2.0f * (sd * sd)) - logf(sd)) - 0.91893853320467267f;
-          const float t = logf(1.000001f - th * th);
-          const float sc = logf(half);
-          lp_gauss = (j == 0) ? g : lp_gauss + g;
-          lp_tanh = (j == 0) ? t : lp_tanh + t;
-          lp_scale = (j == 0) ? sc : lp_scale + sc;
-          act[j] = fminf(fmaxf(a_lim, E::act_low(j)), E::act_high(j));   // base.py:141-143
-        }
-        const float logp = (lp_gauss - lp_tanh) - lp_scale;
+              for (int j = 0; j < A; ++j) z[j] = eps[row * A + j];
+            } else {
+              action_noise4(st.seed, st.env_base + (uint64_t)gi, step_base + (uint32_t)k, z);
+            }
+          }
+          float act[A];
+          float lp_gauss = 0.f, lp_tanh = 0.f, lp_scale = 0.f;
+#pragma unroll
+          for (int j = 0; j < A; ++j) {
+            const float mean = sm.out[T][j * TM + et];
+            const float ls = sm.out[T][(A + j) * TM + et];
+            const float sd = expf(fminf(fmaxf(ls, actor.min_log_std), actor.max_log_std));
+            const float half = (E::act_high(j) - E::act_low(j)) / 2.0f;
+            const float mid = (E::act_high(j) + E::act_low(j)) / 2.0f;
+            const float u = deterministic ? mean : (sd * z[j] + mean);      // torch.normal: z*std, then +mean
+            const float th = tanhf(u);
+            const float a_lim = half * th + mid;
+            // Normal.log_prob(u) = -((u-mean)^2)/(2 var) - log(std) - log(sqrt(2 pi))
+            const float diff = u - mean;
+            const float g = ((-(diff * diff)) / (2.0f * (sd * sd)) - logf(sd)) - 0.91893853320467267f;
+            const float t = logf(1.000001f - th * th);
+            const float sc = logf(half);
+            lp_gauss = (j == 0) ? g : lp_gauss + g;
+            lp_tanh = (j == 0) ? t : lp_tanh + t;
+            lp_scale = (j == 0) ? sc : lp_scale + sc;
+            act[j] = fminf(fmaxf(a_lim, E::act_low(j)), E::act_high(j));   // base.py:141-143
+          }
+          const float logp = (lp_gauss - lp_tanh) - lp_scale;
 
-        const float rew = E::step(r.sf, r.sd, act);
-        const bool term = r.out_of_bounds();
-        r.step += 1;
-        const bool trunc = r.step >= st.max_step;
-        const bool done = term || trunc;
-        r.ep_return += rew;
-        r.ep_len += 1;
-        const float rew_s = rew * reward_scale;                                  // rew_plus_cost.py:18
-        const float cost = np_rowsum_sq<D>(r.obs()) * cost_scale;                // :20-21
-        r.run = min(r.run + 1, n_step);
-        const bool emit = r.run >= n_step;
-        if (out.act) {
+          const float rew = E::step(r.sf, r.sd, act);
+          const bool term = r.out_of_bounds();
+          r.step += 1;
+          const bool trunc = r.step >= st.max_step;
+          const bool done = term || trunc;
+          r.ep_return += rew;
+          r.ep_len += 1;
+          const float rew_s = rew * reward_scale;                                  // rew_plus_cost.py:18
+          const float cost = np_rowsum_sq<D>(r.obs()) * cost_scale;                // :20-21
+          r.run = min(r.run + 1, n_step);
+          const bool emit = r.run >= n_step;
+          if (out.act) {
 #pragma unroll
-          for (int j = 0; j < A; ++j) out.act[row * A + j] = act[j];
-        }
-        if (out.obs2) {
+            for (int j = 0; j < A; ++j) out.act[row * A + j] = act[j];
+          }
+          if (out.obs2) {
 #pragma unroll
-          for (int d = 0; d < D; ++d) out.obs2[row * D + d] = r.obs()[d];        // real_next_obs (pre-reset)
-        }
-        if (out.rew) out.rew[row] = rew_s;
-        if (out.cost) out.cost[row] = cost;
-        if (out.done) out.done[row] = done ? 1 : 0;
-        if (out.logp) out.logp[row] = logp;
-        if (out.emit) out.emit[row] = emit ? 1 : 0;
-        if (stats) {
-          if (done) {
+            for (int d = 0; d < D; ++d) out.obs2[row * D + d] = r.obs()[d];        // real_next_obs (pre-reset)
+          }
+          if (out.rew) out.rew[row] = rew_s;
+          if (out.cost) out.cost[row] = cost;
+          if (out.done) out.done[row] = done ? 1 : 0;
+          if (out.logp) out.logp[row] = logp;
+          if (out.emit) out.emit[row] = emit ? 1 : 0;
+          if (stats && done) {
             atomicAdd(&stats[0], 1.0);
             atomicAdd(&stats[1], (double)r.ep_return);
             atomicAdd(&stats[2], (double)r.ep_len);
             atomicAdd(&stats[term ? 3 : 4], 1.0);
           }
-        }
-        if (done) {
-          r.episode += 1;
-          r.run = 0;
-          r.reset(st.seed, st.env_base + (uint64_t)gi);
-        }
+          if (done) {
+            r.episode += 1;
+            r.run = 0;
+            r.reset(st.seed, st.env_base + (uint64_t)gi);
+          }
 #pragma unroll
-        for (int d = 0; d < D; ++d) sm.x[d * TM + tid] = r.obs()[d];
+          for (int d = 0; d < D; ++d) sm.x[T][d * TM + et] = r.obs()[d];
+        }
+        if (k + 1 < K) {
+          __threadfence_block();
+          bar_arrive(BAR_XREADY + T, NGEMM + TM);
+        }
       }
-      // next iteration's first __syncthreads orders the x writes before layer 1
+      if (owner) r.store(st, gi);
     }
-    if (owner) r.store(st, gi);
-    __syncthreads();   // protect sm.x before the next tile's owners overwrite it
   }
 }
 
@@ -334,8 +360,8 @@ extern "C" int msacl_rollout_fused(const msacl_env_state_t* st, const msacl_acto
   if (!st || !actor || !out || st->n <= 0 || K <= 0 || n_step <= 0) { set_error("rollout_fused: bad argument"); return MSACL_ERR_BAD_ARG; }
   if (!actor->w1 || !actor->b1 || !actor->w2t || !actor->b2 || !actor->w3 || !actor->b3) { set_error("rollout_fused: null actor weights"); return MSACL_ERR_BAD_ARG; }
   if ((reinterpret_cast<uintptr_t>(actor->w2t) & 15) != 0) { set_error("rollout_fused: w2t must be 16-byte aligned"); return MSACL_ERR_BAD_ARG; }
-  const int64_t tiles = (st->n + TM - 1) / TM;
-  const unsigned grid = (unsigned)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+  const int64_t pairs = ((st->n + TM - 1) / TM + NTILE - 1) / NTILE;
+  const unsigned grid = (unsigned)(pairs < kNumSMs ? pairs : kNumSMs);
   MSACL_DISPATCH_ENV(st->env_id, {
     const size_t smem = sizeof(Smem<ID>);
     auto kern = rollout_fused_kernel<ID>;
