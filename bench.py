@@ -256,18 +256,23 @@ def main():
     # ---------------- roofline of the dominant kernel (rollout_fused_kernel): FP32 FFMA pipe
     flops_per_step = actor_flops(D, A) + DYN_FLOPS[args.env]
     achieved_tflops = flops_per_step * n * K / (kern_ms * 1e-3) / 1e12
-    sink = torch.zeros(1, device=dev)
+    sink = torch.rand(128, device=dev)
     import ctypes as C
-    fl = C.c_double(0.0)
     lib = _lib.load()
-    for _ in range(2):
-        _lib.check(lib.msacl_ffma_probe(20000, sink.data_ptr(), C.byref(fl), _lib.current_stream()))
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record(stream)
-    _lib.check(lib.msacl_ffma_probe(20000, sink.data_ptr(), C.byref(fl), _lib.current_stream()))
-    p1.record(stream)
-    torch.cuda.synchronize()
-    ffma_peak = fl.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+    def probe(mode, iters):
+        fl = C.c_double(0.0)
+        for _ in range(2):
+            _lib.check(lib.msacl_ffma_probe(mode, iters, sink.data_ptr(), C.byref(fl), _lib.current_stream()))
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        _lib.check(lib.msacl_ffma_probe(mode, iters, sink.data_ptr(), C.byref(fl), _lib.current_stream()))
+        p1.record(stream)
+        torch.cuda.synchronize()
+        return fl.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+    ffma_peak = probe(0, 20000)
+    ffma_outer = probe(1, 20000)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -281,6 +286,7 @@ def main():
                 "frac": achieved_tflops / ffma_peak, "traffic": None,
                 "peak_source": "measured in this run: msacl_ffma_probe (8 independent FFMA chains/thread, 2x256 threads/SM); "
                                "MEASURED_PEAKS.json has no FP32 figure (theoretical 148*128*2*1.965 GHz = 74.4)",
+                "register_tiled_sgemm_ceiling_tflops": ffma_outer,
                 "kernel": f"rollout_fused_kernel<{args.env}>", "kernel_ms": kern_ms,
                 "algorithmic_flops_per_env_step": flops_per_step,
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,

@@ -180,9 +180,13 @@ int msacl_stability_advantage(int64_t B, int32_t n, const float* lya_obs0, const
                               void* stream);
 int msacl_advantage_normalize(int64_t B, const float* adv_raw, const double* moments, float* adv, void* stream);
 
-/* Device FP32 FFMA peak probe used by bench.py for the roofline denominator: runs
- * `iters` dependent-free FFMA sweeps on every SM; returns FLOPs issued in *flops (host). */
-int msacl_ffma_probe(int32_t iters, float* sink, double* flops, void* stream);
+/* Device FP32 FFMA peak probes used by bench.py for the roofline denominator.
+ * mode 0: independent FFMA chains with immediate operands (pipe peak);
+ * mode 1: register-resident 8x8 outer-product accumulation, i.e. a register-tiled SGEMM inner
+ *         loop with no memory traffic (three-register FFMA ceiling).
+ * sink: device float[128] (sink[64..128) is read as operand source in mode 1).
+ * Returns the FLOPs issued in *flops (host). */
+int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, void* stream);
 
 const char* msacl_last_error(void);
 int msacl_abi_version(void);

@@ -2,7 +2,7 @@
 // env dynamics + reward/cost + same-step autoreset + n-step bookkeeping.  Replaces K iterations
 // of BaseSampler._n_step (RL/trainer/sampler/base.py:118-163,220).
 //
-// Design (B200, sm_100a), v2 -- warp specialised, one persistent CTA of 12 warps per SM:
+// Design (B200, sm_100a), v3 -- warp specialised, one persistent CTA of 12 warps per SM:
 //   * warps 0-7 ("GEMM warps") run the MLP for two 64-env tiles A/B alternately; warps 8-9 own
 //     the env instances of tile A, warps 10-11 those of tile B ("env warps": state in registers
 //     for all K steps, so HBM sees the state once per launch and one transition record per step).
@@ -12,15 +12,18 @@
 //     smem) and LOGITS[T] (GEMM -> env).
 //   * the MLP is >99% of the FLOPs and is an FP32 contraction (parity with the
 //     reference's fp32 torch actor rules out single-pass bf16/tf32 tensor-core MMA), so the
-//     binding roofline is the FP32 FFMA pipe.  Layer 2 (64x256x256 per tile-step) is a
-//     register-tiled SGEMM: 8x8 accumulators per thread; A = hidden-1 activations resident in
-//     shared memory K-major (warp-broadcast float4 reads), B = W2^T streamed from L2 in 32-row
-//     chunks through a cp.async double buffer that never drains (the chunk sequence is the same
-//     for every tile, so the prefetch runs across tile boundaries).  W2 (256 KB) is shared by
-//     all CTAs and lives in the 126 MB L2.
-//   * layer 1 (D -> 256) is register-tiled too (2 envs x 32 units per thread, conflict-free
-//     float2 stores of the K-major activations); layer 3 (256 -> 2A) is applied to the layer-2
-//     register tile and combined with a halving warp-shuffle reduction (62 shuffles / 64 values).
+//     binding roofline is the FP32 FFMA pipe.  Every GEMM warp owns 8 envs of the tile for the
+//     whole MLP (8x8 register tile per thread: envs warp*8..+8 x units {lane*4..+4,
+//     128+lane*4..+4}), so layers 1-3 need no block-wide barrier at all: the hidden-1
+//     activations a warp writes (K-major layout, warp-broadcast float4 reads in the inner loop)
+//     are only ever read by the same warp.
+//   * W2^T (256 KB, shared by all CTAs, resident in the 126 MB L2) is streamed in 16-row chunks
+//     by TMA bulk copies (cp.async.bulk -> UBLKCP) into a 4-stage shared-memory ring guarded by
+//     full/empty mbarriers: one elected thread issues, consumers wait per warp and release per
+//     warp, so warps drift freely and the FFMA pipe is not gated by block barriers.  The chunk
+//     sequence is identical for every tile, so the ring never drains across tile boundaries.
+//   * layer 3 (256 -> 2A) is applied to the layer-2 register tile and combined with a halving
+//     warp-shuffle reduction (62 shuffles / 64 values).
 // Compiled with -fmad=false: only the explicit __fmaf_rn calls below contract.
 #include "common.cuh"
 
@@ -31,18 +34,21 @@ constexpr int HID = 256;        // hidden width (reference default, msacl_train.
 constexpr int NGEMM = 256;      // GEMM threads (warps 0-7)
 constexpr int NTILE = 2;        // tiles in flight per CTA
 constexpr int NTHREADS = NGEMM + NTILE * TM;   // 384
-constexpr int KC = 32;          // W2^T rows per cp.async chunk
+constexpr int KC = 16;          // W2^T rows per TMA chunk
 constexpr int NCHUNK = HID / KC;
-static_assert(NCHUNK % 2 == 0, "buffer parity must be tile-invariant");
+constexpr int NSTAGE = 4;       // ring depth
+constexpr int PREFETCH = NSTAGE - 2;   // chunks in flight ahead of the consumer
+constexpr uint32_t CHUNK_BYTES = KC * HID * 4;
+static_assert(NCHUNK % NSTAGE == 0, "stage index must be tile-invariant");
 
-enum : int { BAR_GEMM = 1, BAR_LOGITS = 2, BAR_XREADY = 4 };
+enum : int { BAR_LOGITS = 2, BAR_XREADY = 4 };
 
 template <int ID>
 struct Smem {
   using E = Env<ID>;
   static constexpr int A2 = 2 * E::A;
   float h1[HID * TM];            // [k][m]  hidden-1 activations of the tile in the GEMM
-  float wc[2][KC * HID];         // W2^T chunks [k][n]
+  float wc[NSTAGE][KC * HID];    // W2^T chunk ring [k][n]
   float w1t[E::D * HID];         // W1^T [d][n]
   float w3[A2 * HID];            // [j][k]
   float b1[HID];
@@ -50,17 +56,40 @@ struct Smem {
   float b3[8];
   float x[NTILE][E::D * TM];     // obs tiles [d][m]
   float out[NTILE][A2 * TM];     // logits [j][m]
+  unsigned long long full_bar[NSTAGE];
+  unsigned long long empty_bar[NSTAGE];
 };
+
+// ---- mbarrier / TMA bulk-copy primitives (PTX ISA 8.x, sm_90+)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // Halving butterfly: V values per lane summed over the 32 lanes; afterwards value
 // `orig` lives in v[0..V/32) of lane orig / (V/32) (V >= 32), or in v[0] of lanes
@@ -108,6 +137,12 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
   for (int i = tid; i < A2 * HID; i += NTHREADS) sm.w3[i] = actor.w3[i];
   for (int i = tid; i < HID; i += NTHREADS) { sm.b1[i] = actor.b1[i]; sm.b2[i] = actor.b2[i]; }
   if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], NGEMM / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncthreads();
 
   const int64_t num_tiles = (st.n + TM - 1) / TM;
@@ -115,71 +150,89 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
 
   if (tid < NGEMM) {
     // =========================== GEMM warps ===========================
-    auto prefetch_chunk = [&](int ch) {
-      const float4* src = reinterpret_cast<const float4*>(actor.w2t + (size_t)ch * KC * HID);
-      float4* dst = reinterpret_cast<float4*>(sm.wc[ch & 1]);
-#pragma unroll
-      for (int q = 0; q < KC * HID / 4 / NGEMM; ++q) cp_async16(dst + tid + q * NGEMM, src + tid + q * NGEMM);
-      cp_async_commit();
+    // number of W2 chunks this CTA will consume (producer must not run past it)
+    int64_t my_tile_steps = 0;
+    for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x)
+      my_tile_steps += ((num_tiles - NTILE * pair) < NTILE ? (num_tiles - NTILE * pair) : NTILE) * (int64_t)K;
+    const int64_t total_chunks = my_tile_steps * NCHUNK;
+    const bool producer = (tid == 0);
+    auto produce = [&](int64_t gi) {          // issue chunk gi (global index) into stage gi % NSTAGE
+      if (gi >= total_chunks) return;
+      const int stg = (int)(gi % NSTAGE);
+      if (gi >= NSTAGE) mbar_wait(&sm.empty_bar[stg], (uint32_t)(((gi / NSTAGE) & 1) ^ 1));
+      mbar_expect_tx(&sm.full_bar[stg], CHUNK_BYTES);
+      tma_bulk_g2s(sm.wc[stg], actor.w2t + (size_t)(gi % NCHUNK) * KC * HID, CHUNK_BYTES, &sm.full_bar[stg]);
     };
-    prefetch_chunk(0);
+    if (producer) {
+#pragma unroll
+      for (int i = 0; i < PREFETCH; ++i) produce(i);
+    }
+    int64_t g = 0;                            // global chunk counter (identical in all GEMM threads)
+    const int m0 = warp * 8;                  // this warp's envs within the tile
     for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
       const int nt = (int)((num_tiles - NTILE * pair) < NTILE ? (num_tiles - NTILE * pair) : NTILE);
       for (int k = 0; k < K; ++k) {
         for (int T = 0; T < nt; ++T) {
-          bar_sync(BAR_XREADY + T, NGEMM + TM);   // obs tile T in smem; all GEMM warps done with h1
+          bar_sync(BAR_XREADY + T, NGEMM + TM);   // obs tile T is in smem
           float acc[8][8];
-          // ---- layer 1: thread tile = envs {2*lane, 2*lane+1} x units warp*32..+32
+          // ---- layer 1 on the same thread tile as layer 2 (envs m0..m0+8 x 8 units)
           {
+            const float4 q0 = *reinterpret_cast<const float4*>(&sm.b1[lane * 4]);
+            const float4 q1 = *reinterpret_cast<const float4*>(&sm.b1[128 + lane * 4]);
+            const float bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b = *reinterpret_cast<const float4*>(&sm.b1[warp * 32 + 4 * q]);
-              acc[0][q] = b.x; acc[1][q] = b.y; acc[2][q] = b.z; acc[3][q] = b.w;     // env 2*lane
-              acc[4][q] = b.x; acc[5][q] = b.y; acc[6][q] = b.z; acc[7][q] = b.w;     // env 2*lane+1
-            }
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[i][c] = bb[c];
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-              const float2 xv = *reinterpret_cast<const float2*>(&sm.x[T][d * TM + 2 * lane]);
+              const float4 a0 = *reinterpret_cast<const float4*>(&sm.x[T][d * TM + m0]);
+              const float4 a1 = *reinterpret_cast<const float4*>(&sm.x[T][d * TM + m0 + 4]);
+              const float4 b0 = *reinterpret_cast<const float4*>(&sm.w1t[d * HID + lane * 4]);
+              const float4 b1 = *reinterpret_cast<const float4*>(&sm.w1t[d * HID + 128 + lane * 4]);
+              const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w = *reinterpret_cast<const float4*>(&sm.w1t[d * HID + warp * 32 + 4 * q]);
-                acc[0][q] = __fmaf_rn(w.x, xv.x, acc[0][q]); acc[1][q] = __fmaf_rn(w.y, xv.x, acc[1][q]);
-                acc[2][q] = __fmaf_rn(w.z, xv.x, acc[2][q]); acc[3][q] = __fmaf_rn(w.w, xv.x, acc[3][q]);
-                acc[4][q] = __fmaf_rn(w.x, xv.y, acc[4][q]); acc[5][q] = __fmaf_rn(w.y, xv.y, acc[5][q]);
-                acc[6][q] = __fmaf_rn(w.z, xv.y, acc[6][q]); acc[7][q] = __fmaf_rn(w.w, xv.y, acc[7][q]);
-              }
+              for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[i][c] = __fmaf_rn(av[i], bv[c], acc[i][c]);
             }
+            // h1[n][m0..m0+8): two float4 stores per unit.  Lanes stride by whole rows (256 B), so
+            // these 16 stores per tile-step are bank-conflicted (32-way); at 16 of ~1100 shared-memory
+            // instructions per tile-step that is <1% of the step and cheaper than swizzling the
+            // 1024 warp-broadcast reads of the inner loop.
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int n = warp * 32 + 4 * q + c;
-                *reinterpret_cast<float2*>(&sm.h1[n * TM + 2 * lane]) =
-                    make_float2(fmaxf(acc[c][q], 0.f), fmaxf(acc[4 + c][q], 0.f));
-              }
+            for (int c = 0; c < 8; ++c) {
+              const int n = (c < 4) ? (lane * 4 + c) : (128 + lane * 4 + (c - 4));
+              float* row = &sm.h1[n * TM + m0];
+              *reinterpret_cast<float4*>(row) =
+                  make_float4(fmaxf(acc[0][c], 0.f), fmaxf(acc[1][c], 0.f), fmaxf(acc[2][c], 0.f), fmaxf(acc[3][c], 0.f));
+              *reinterpret_cast<float4*>(row + 4) =
+                  make_float4(fmaxf(acc[4][c], 0.f), fmaxf(acc[5][c], 0.f), fmaxf(acc[6][c], 0.f), fmaxf(acc[7][c], 0.f));
+            }
+            __syncwarp();     // the activations are consumed by this warp only
           }
 
-          // ---- layer 2: register-tiled 64x256x256 SGEMM; thread tile = envs warp*8..+8 x
-          //      columns {lane*4..+4, 128+lane*4..+4}
+          // ---- layer 2: register-tiled SGEMM over K = 256, W2^T chunks from the TMA ring
 #pragma unroll
           for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
 
-          for (int ch = 0; ch < NCHUNK; ++ch) {
-            cp_async_wait<0>();
-            bar_sync(BAR_GEMM, NGEMM);        // chunk ch landed for all; chunk ch-1 (and layer 1) finished by all
-            prefetch_chunk((ch + 1) % NCHUNK); // runs across tile boundaries: the pipe never drains
-            const float* wb = sm.wc[ch & 1];
-            const float* ha = sm.h1 + (size_t)ch * KC * TM + warp * 8;
+          for (int ch = 0; ch < NCHUNK; ++ch, ++g) {
+            if (producer) produce(g + PREFETCH);
+            const int stg = (int)(g % NSTAGE);
+            mbar_wait(&sm.full_bar[stg], (uint32_t)((g / NSTAGE) & 1));
+            const float* wb = sm.wc[stg] + lane * 4;
+            const float* ha = sm.h1 + (size_t)ch * KC * TM + m0;
 #pragma unroll 1
-            for (int k8 = 0; k8 < KC; k8 += 8) {
+            for (int k8 = 0; k8 < KC; k8 += 8) {     // 8 k's = 512 FFMA per body keeps the loop inside the I-cache
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk) {
                 const float4 a0 = *reinterpret_cast<const float4*>(ha + (k8 + kk) * TM);
                 const float4 a1 = *reinterpret_cast<const float4*>(ha + (k8 + kk) * TM + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(wb + (k8 + kk) * HID + lane * 4);
-                const float4 b1 = *reinterpret_cast<const float4*>(wb + (k8 + kk) * HID + 128 + lane * 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(wb + (k8 + kk) * HID);
+                const float4 b1 = *reinterpret_cast<const float4*>(wb + (k8 + kk) * HID + 128);
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -188,6 +241,8 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
                   for (int c = 0; c < 8; ++c) acc[i][c] = __fmaf_rn(av[i], bv[c], acc[i][c]);
               }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty_bar[stg]);   // this warp is done with the stage
           }
 
           // ---- bias + ReLU, then layer 3 on the register tile
@@ -239,7 +294,6 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
         }
       }
     }
-    cp_async_wait<0>();
   } else {
     // =========================== env warps ===========================
     const int T = (tid - NGEMM) >> 6;        // tile slot owned by this warp pair

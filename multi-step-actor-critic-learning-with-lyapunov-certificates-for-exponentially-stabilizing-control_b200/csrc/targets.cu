@@ -123,7 +123,12 @@ adv_normalize_kernel(int64_t B, const float* __restrict__ adv_raw, const double*
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) adv[i] = (adv_raw[i] - fmean) / denom;
 }
 
-// FP32 FFMA peak probe: 8 independent accumulator chains per thread, 2 CTAs x 256 threads per SM
+// FP32 FFMA peak probes (roofline denominators for the fused rollout kernel).
+//  mode 0: 8 independent accumulator chains per thread, multiplier/addend are compile-time
+//          constants (ptxas emits the immediate form) -- the best case the FMA pipe can do.
+//  mode 1: the register-tiled SGEMM inner product itself, without any memory traffic: 8x8
+//          accumulators, acc[i][c] += a[i] * b[c] with all operands in registers (three-register
+//          FFMA, operand-collector bound) -- the ceiling for any register-blocked FP32 GEMM.
 __global__ void __launch_bounds__(256) ffma_probe_kernel(int iters, float* sink) {
   float a[8];
 #pragma unroll
@@ -138,6 +143,30 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(int iters, float* sink)
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == 123.456f) sink[0] = s;
+}
+
+__global__ void __launch_bounds__(256) ffma_probe_outer_kernel(int iters, const float* __restrict__ src, float* sink) {
+  float a[8], b[8], acc[8][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = src[(threadIdx.x + j) & 63]; b[j] = src[(threadIdx.x * 3 + j) & 63]; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = __fmaf_rn(a[i], b[c], acc[i][c]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s += acc[i][c];
   if (s == 123.456f) sink[0] = s;
 }
 
@@ -199,10 +228,15 @@ extern "C" int msacl_advantage_normalize(int64_t B, const float* adv_raw, const 
   return check_launch("advantage_normalize");
 }
 
-extern "C" int msacl_ffma_probe(int32_t iters, float* sink, double* flops, void* stream) {
-  if (iters <= 0 || !sink) { set_error("ffma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
+extern "C" int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, void* stream) {
+  if (iters <= 0 || !sink || mode < 0 || mode > 1) { set_error("ffma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
   const unsigned grid = 2 * kNumSMs * 4;
-  ffma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
-  if (flops) *flops = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)grid;
+  if (mode == 0) {
+    ffma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (flops) *flops = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)grid;
+  } else {
+    ffma_probe_outer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink + 64, sink);   // sink[64..128) = operand source
+    if (flops) *flops = 2.0 * 128.0 * (double)iters * 256.0 * (double)grid;
+  }
   return check_launch("ffma_probe");
 }

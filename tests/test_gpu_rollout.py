@@ -47,6 +47,7 @@ def test_fused_step_vs_oracle_teacher_forced(name):
         emitter = oroll.WindowEmitter(n, 4)
         rng = np.random.default_rng(0)
         rngspan = (spec.act_high - spec.act_low)
+        _sync_state(ro, name, venv.state)     # device reset == oracle reset only to float32 round-off (Quad trig)
         for t in range(T):
             eps = rng.standard_normal((n, spec.act_dim)).astype(np.float32)
             tr = oroll.sampler_step(venv, w, eps)
