@@ -15,8 +15,8 @@
 //     binding roofline is the FP32 FFMA pipe.  Every GEMM warp owns 8 envs of the tile for the
 //     whole MLP (8x8 register tile per thread: envs warp*8..+8 x units {lane*4..+4,
 //     128+lane*4..+4}), so layers 1-3 need no block-wide barrier at all: the hidden-1
-//     activations a warp writes (K-major layout, warp-broadcast float4 reads in the inner loop)
-//     are only ever read by the same warp.
+//     activations a warp writes (K-major layout with an XOR granule swizzle: conflict-free float4
+//     stores, warp-broadcast float4 reads) are only ever read by the same warp.
 //   * W2^T (256 KB, shared by all CTAs, resident in the 126 MB L2) is streamed in 16-row chunks
 //     by TMA bulk copies (cp.async.bulk -> UBLKCP) into a 4-stage shared-memory ring guarded by
 //     full/empty mbarriers: one elected thread issues, consumers wait per warp and release per
@@ -197,17 +197,19 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[i][c] = __fmaf_rn(av[i], bv[c], acc[i][c]);
             }
-            // h1[n][m0..m0+8): two float4 stores per unit.  Lanes stride by whole rows (256 B), so
-            // these 16 stores per tile-step are bank-conflicted (32-way); at 16 of ~1100 shared-memory
-            // instructions per tile-step that is <1% of the step and cheaper than swizzling the
-            // 1024 warp-broadcast reads of the inner loop.
+            // h1 row n holds 16 granules of 4 envs; granule g is stored at g ^ ((n>>2)&7).  For unit
+            // n = 4*lane+c (or 128+4*lane+c) the key is lane&7, so a warp-wide float4 store touches
+            // every bank exactly four times (conflict-free), and a warp's two granules {2w, 2w+1}
+            // stay inside one aligned 32-byte pair, so the inner loop still reads them with two
+            // warp-broadcast float4 loads at compile-time-known offsets.
+            const int key = lane & 7;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const int n = (c < 4) ? (lane * 4 + c) : (128 + lane * 4 + (c - 4));
-              float* row = &sm.h1[n * TM + m0];
-              *reinterpret_cast<float4*>(row) =
+              float* row = &sm.h1[n * TM];
+              *reinterpret_cast<float4*>(row + ((2 * warp) ^ key) * 4) =
                   make_float4(fmaxf(acc[0][c], 0.f), fmaxf(acc[1][c], 0.f), fmaxf(acc[2][c], 0.f), fmaxf(acc[3][c], 0.f));
-              *reinterpret_cast<float4*>(row + 4) =
+              *reinterpret_cast<float4*>(row + ((2 * warp + 1) ^ key) * 4) =
                   make_float4(fmaxf(acc[4][c], 0.f), fmaxf(acc[5][c], 0.f), fmaxf(acc[6][c], 0.f), fmaxf(acc[7][c], 0.f));
             }
             __syncwarp();     // the activations are consumed by this warp only
@@ -224,15 +226,20 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
             const int stg = (int)(g % NSTAGE);
             mbar_wait(&sm.full_bar[stg], (uint32_t)((g / NSTAGE) & 1));
             const float* wb = sm.wc[stg] + lane * 4;
-            const float* ha = sm.h1 + (size_t)ch * KC * TM + m0;
+            // swizzle key of hidden unit kg = ch*16 + kk is (kg>>2)&7 = ((ch&1)<<2) | (kk>>2):
+            // pair index = warp ^ (key>>1) (runtime, per 8 k's), order inside the pair = key&1 (compile time)
 #pragma unroll 1
-            for (int k8 = 0; k8 < KC; k8 += 8) {     // 8 k's = 512 FFMA per body keeps the loop inside the I-cache
+            for (int half = 0; half < 2; ++half) {
+              const float* ha = sm.h1 + (size_t)(ch * KC + half * 8) * TM + ((warp ^ (((ch & 1) << 1) | half)) << 3);
+              const float* wh = wb + half * 8 * HID;
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk) {
-                const float4 a0 = *reinterpret_cast<const float4*>(ha + (k8 + kk) * TM);
-                const float4 a1 = *reinterpret_cast<const float4*>(ha + (k8 + kk) * TM + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(wb + (k8 + kk) * HID);
-                const float4 b1 = *reinterpret_cast<const float4*>(wb + (k8 + kk) * HID + 128);
+                const float4 lo = *reinterpret_cast<const float4*>(ha + kk * TM);
+                const float4 hi = *reinterpret_cast<const float4*>(ha + kk * TM + 4);
+                const float4 a0 = ((kk >> 2) & 1) ? hi : lo;     // envs m0..m0+3
+                const float4 a1 = ((kk >> 2) & 1) ? lo : hi;     // envs m0+4..m0+7
+                const float4 b0 = *reinterpret_cast<const float4*>(wh + kk * HID);
+                const float4 b1 = *reinterpret_cast<const float4*>(wh + kk * HID + 128);
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
