@@ -273,6 +273,7 @@ def main():
 
     ffma_peak = probe(0, 20000)
     ffma_outer = probe(1, 20000)
+    ffma2_outer = probe(2, 20000)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -286,7 +287,7 @@ def main():
                 "frac": achieved_tflops / ffma_peak, "traffic": None,
                 "peak_source": "measured in this run: msacl_ffma_probe (8 independent FFMA chains/thread, 2x256 threads/SM); "
                                "MEASURED_PEAKS.json has no FP32 figure (theoretical 148*128*2*1.965 GHz = 74.4)",
-                "register_tiled_sgemm_ceiling_tflops": ffma_outer,
+                "register_tiled_sgemm_ceiling_tflops": ffma_outer, "register_tiled_ffma2_ceiling_tflops": ffma2_outer,
                 "kernel": f"rollout_fused_kernel<{args.env}>", "kernel_ms": kern_ms,
                 "algorithmic_flops_per_env_step": flops_per_step,
                 "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,

@@ -183,7 +183,8 @@ int msacl_advantage_normalize(int64_t B, const float* adv_raw, const double* mom
 /* Device FP32 FFMA peak probes used by bench.py for the roofline denominator.
  * mode 0: independent FFMA chains with immediate operands (pipe peak);
  * mode 1: register-resident 8x8 outer-product accumulation, i.e. a register-tiled SGEMM inner
- *         loop with no memory traffic (three-register FFMA ceiling).
+ *         loop with no memory traffic (three-register FFMA ceiling);
+ * mode 2: the same outer product with packed FFMA2 (fma.rn.f32x2).
  * sink: device float[128] (sink[64..128) is read as operand source in mode 1).
  * Returns the FLOPs issued in *flops (host). */
 int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, void* stream);

@@ -170,6 +170,45 @@ __global__ void __launch_bounds__(256) ffma_probe_outer_kernel(int iters, const 
   if (s == 123.456f) sink[0] = s;
 }
 
+// mode 2: the same outer product with packed FFMA2 (fma.rn.f32x2, scalar-broadcast A operand)
+__global__ void __launch_bounds__(256) ffma2_probe_outer_kernel(int iters, const float* __restrict__ src, float* sink) {
+  typedef unsigned long long u64;
+  float a[8];
+  u64 b[4], acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = src[(threadIdx.x + j) & 63];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float lo = src[(threadIdx.x * 3 + 2 * j) & 63], hi = src[(threadIdx.x * 3 + 2 * j + 1) & 63];
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b[j]) : "f"(lo), "f"(hi));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0ull;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        u64 aa;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[i]));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i][c]) : "l"(aa), "l"(b[c]));
+      }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i][c]));
+      s += lo + hi;
+    }
+  if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace msacl
 
 using namespace msacl;
@@ -229,13 +268,16 @@ extern "C" int msacl_advantage_normalize(int64_t B, const float* adv_raw, const 
 }
 
 extern "C" int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, void* stream) {
-  if (iters <= 0 || !sink || mode < 0 || mode > 1) { set_error("ffma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
+  if (iters <= 0 || !sink || mode < 0 || mode > 2) { set_error("ffma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
   const unsigned grid = 2 * kNumSMs * 4;
   if (mode == 0) {
     ffma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
     if (flops) *flops = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)grid;
-  } else {
+  } else if (mode == 1) {
     ffma_probe_outer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink + 64, sink);   // sink[64..128) = operand source
+    if (flops) *flops = 2.0 * 128.0 * (double)iters * 256.0 * (double)grid;
+  } else {
+    ffma2_probe_outer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink + 64, sink);
     if (flops) *flops = 2.0 * 128.0 * (double)iters * 256.0 * (double)grid;
   }
   return check_launch("ffma_probe");
