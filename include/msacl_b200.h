@@ -189,6 +189,11 @@ int msacl_advantage_normalize(int64_t B, const float* adv_raw, const double* mom
  * Returns the FLOPs issued in *flops (host). */
 int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, void* stream);
 
+/* Diagnostic: D[128][256] = A[128][256] * W[256][256]^T on the tcgen05 tensor cores with the
+ * split-bf16 scheme (splits = 1: plain bf16; 3: a1*b1 + a1*b2 + a2*b1), FP32 accumulation in TMEM.
+ * Exercises the descriptor / TMEM plumbing of the tensor-core rollout path. */
+int msacl_selftest_tc_gemm(const float* A, const float* W, float* D, int32_t splits, void* stream);
+
 const char* msacl_last_error(void);
 int msacl_abi_version(void);
 

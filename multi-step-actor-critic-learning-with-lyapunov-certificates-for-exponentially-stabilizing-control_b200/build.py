@@ -15,8 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libmsacl_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["env_step.cu", "rollout_fused.cu", "windows.cu", "targets.cu"]
-HEADERS = ["common.cuh", "env_dynamics.cuh", "philox.cuh", os.path.join(ROOT, "include", "msacl_b200.h")]
+SOURCES = ["env_step.cu", "rollout_fused.cu", "windows.cu", "targets.cu", "tc_selftest.cu"]
+HEADERS = ["common.cuh", "env_dynamics.cuh", "philox.cuh", "tcgen05.cuh", os.path.join(ROOT, "include", "msacl_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

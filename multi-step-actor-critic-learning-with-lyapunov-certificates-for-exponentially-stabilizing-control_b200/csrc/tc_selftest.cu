@@ -1,0 +1,97 @@
+// Self-test of the tcgen05 building blocks: D[128][256] = A[128][256] * W[256][256]^T with the
+// split-bf16 scheme (1 product = plain bf16, 3 products = a1b1 + a1b2 + a2b1) accumulated in TMEM.
+// Validates the shared-memory descriptor / instruction descriptor / TMEM addressing used by the
+// tensor-core rollout kernel against a float64 matmul (tests/test_gpu_tc.py).
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace msacl {
+
+constexpr int ST_M = 128, ST_N = 256, ST_K = 256, ST_KC = 64;
+
+__global__ void __launch_bounds__(128, 1)
+tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ D, int splits) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* a1 = smem;                       // 4 chunks x 16 KB
+  unsigned char* a2 = smem + 65536;
+  unsigned char* b1 = smem + 131072;              // one 64-wide K chunk: 8 blocks x 4 KB
+  unsigned char* b2 = smem + 131072 + 32768;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + 196608);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 196608 + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // A: thread = row
+  for (int kb = 0; kb < ST_K / 8; ++kb) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tc::split_bf16(A[tid * ST_K + kb * 8 + j], hi[j], lo[j]);
+    const int c = kb / 8, kl = kb % 8;
+    const uint4 vh = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), hi[4] | (hi[5] << 16), hi[6] | (hi[7] << 16));
+    const uint4 vl = make_uint4(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16), lo[4] | (lo[5] << 16), lo[6] | (lo[7] << 16));
+    *reinterpret_cast<uint4*>(a1 + c * 16384 + kl * 2048 + tid * 16) = vh;
+    *reinterpret_cast<uint4*>(a2 + c * 16384 + kl * 2048 + tid * 16) = vl;
+  }
+  const uint32_t idesc = tc::make_idesc_bf16(ST_M, ST_N);
+  for (int c = 0; c < ST_K / ST_KC; ++c) {
+    for (int idx = tid; idx < ST_N * 8; idx += 128) {
+      const int n = idx % ST_N, kl = idx / ST_N;
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tc::split_bf16(W[n * ST_K + c * ST_KC + kl * 8 + j], hi[j], lo[j]);
+      *reinterpret_cast<uint4*>(b1 + kl * 4096 + n * 16) =
+          make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16), hi[4] | (hi[5] << 16), hi[6] | (hi[7] << 16));
+      *reinterpret_cast<uint4*>(b2 + kl * 4096 + n * 16) =
+          make_uint4(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16), lo[4] | (lo[5] << 16), lo[6] | (lo[7] << 16));
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      for (int j = 0; j < ST_KC / 16; ++j) {
+        const uint64_t da1 = tc::make_smem_desc(tc::smem_u32(a1 + c * 16384 + j * 2 * 2048), 2048, 128);
+        const uint64_t da2 = tc::make_smem_desc(tc::smem_u32(a2 + c * 16384 + j * 2 * 2048), 2048, 128);
+        const uint64_t db1 = tc::make_smem_desc(tc::smem_u32(b1 + j * 2 * 4096), 4096, 128);
+        const uint64_t db2 = tc::make_smem_desc(tc::smem_u32(b2 + j * 2 * 4096), 4096, 128);
+        tc::umma_bf16(tmem, da1, db1, idesc, (c > 0 || j > 0) ? 1u : 0u);
+        if (splits == 3) {
+          tc::umma_bf16(tmem, da1, db2, idesc, 1u);
+          tc::umma_bf16(tmem, da2, db1, idesc, 1u);
+        }
+      }
+      tc::umma_commit(bar);
+    }
+    tc::mbar_wait(bar, (uint32_t)(c & 1));
+    tc::tc_fence_after();
+  }
+  // epilogue: warp w reads TMEM lanes 32w..32w+31 (= rows), 32 columns at a time
+  for (int cb = 0; cb < ST_N / 32; ++cb) {
+    uint32_t r[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * ST_N + cb * 32 + j] = __uint_as_float(r[j]);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace msacl
+
+using namespace msacl;
+
+extern "C" int msacl_selftest_tc_gemm(const float* A, const float* W, float* D, int32_t splits, void* stream) {
+  if (!A || !W || !D || (splits != 1 && splits != 3)) { set_error("selftest_tc_gemm: bad argument"); return MSACL_ERR_BAD_ARG; }
+  const int smem = 196608 + 128;
+  cudaError_t e = cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("selftest_tc_gemm: %s", cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
+  tc_gemm_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, W, D, splits);
+  return check_launch("selftest_tc_gemm");
+}
