@@ -127,6 +127,18 @@ int msacl_rollout_fused(const msacl_env_state_t* st, const msacl_actor_t* actor,
                         int32_t n_step, float reward_scale, float cost_scale, const float* eps,
                         int32_t deterministic, const msacl_transitions_t* out, double* stats, void* stream);
 
+/* Tensor-core variant of msacl_rollout_fused (same contract, same outputs): the two dense actor layers
+ * run on tcgen05 UMMA with a split-bf16 ("bf16x3": x1*w1 + x1*w2 + x2*w1) scheme and FP32 accumulation
+ * in TMEM; layer 3, sampling and the dynamics stay FP32.  Logits agree with the FP32 path to ~3e-5
+ * relative (tolerances in tests/test_gpu_tc.py).  w1p / w2p are the operand images produced by
+ * msacl_tc_pack_actor (sizes from msacl_tc_pack_bytes); repack after every weight update. */
+int msacl_tc_pack_bytes(int64_t* w1p_bytes, int64_t* w2p_bytes);
+int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, void* w1p, void* w2p, void* stream);
+int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_actor_t* actor, const void* w1p, const void* w2p,
+                           int32_t K, uint32_t step_base, int32_t n_step, float reward_scale, float cost_scale,
+                           const float* eps, int32_t deterministic, const msacl_transitions_t* out, double* stats,
+                           void* stream);
+
 /* Fill out[n][act_dim] with the N(0,1) draws the rollout uses at global step `step`. */
 int msacl_action_noise(uint64_t seed, uint64_t env_base, int64_t n, int32_t act_dim, uint32_t step, float* out,
                        void* stream);

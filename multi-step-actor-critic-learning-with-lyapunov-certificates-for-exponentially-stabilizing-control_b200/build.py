@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libmsacl_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["env_step.cu", "rollout_fused.cu", "windows.cu", "targets.cu", "tc_selftest.cu"]
+SOURCES = ["env_step.cu", "rollout_fused.cu", "windows.cu", "targets.cu", "tc_selftest.cu", "rollout_tc.cu"]
 HEADERS = ["common.cuh", "env_dynamics.cuh", "philox.cuh", "tcgen05.cuh", os.path.join(ROOT, "include", "msacl_b200.h")]
 
 NVCC_FLAGS = [

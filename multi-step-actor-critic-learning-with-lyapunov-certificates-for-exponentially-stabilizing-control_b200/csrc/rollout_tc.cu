@@ -1,0 +1,439 @@
+// Tensor-core fused rollout (tcgen05 / TMEM / TMA), sm_100a.
+//
+// Same contract as rollout_fused.cu (K iterations of BaseSampler._n_step,
+// RL/trainer/sampler/base.py:118-163,220) but the two dense actor layers run on the 5th-gen tensor
+// cores with a split-bf16 ("bf16x3") scheme that keeps FP32-class accuracy:
+//     x = x1 + x2 (+ O(2^-17 |x|)),  w = w1 + w2   (all four bf16, round-to-nearest-even)
+//     x.w ~= x1.w1 + x1.w2 + x2.w1                 (three UMMAs, FP32 accumulation in TMEM)
+// Relative error of a product ~1e-5 (vs 4e-3 for single-pass bf16); tolerances in tests/test_gpu_tc.py.
+//
+// One persistent CTA per SM, 18 warps, two 128-env tiles (slots) in flight:
+//   warps 0-7   env warps: thread = env instance (slot = warp/4), state in registers for all K steps;
+//               sample action, integrate the ODE, reward/cost/autoreset, write the transition, and write
+//               the next observation as the layer-1 A operand (16-wide K block: obs, 1.0 for the bias, 0).
+//   warp 16     MMA issuer (one elected thread): layer 1 = 3 UMMAs (K=16, bias folded in as a K column),
+//               layer 2 = 8 K-chunks x 2 k-steps x 3 UMMAs of 128x256x16, accumulators in TMEM
+//               (H1: columns 0-255, H2: columns 256-511); tcgen05.commit signals mbarriers.
+//   warps 8-11  epilogue 1: TMEM(H1) -> ReLU -> split to bf16 hi/lo -> shared-memory A stages (UMMA
+//               canonical K-major layout, thread = row, 16-byte conflict-free stores).
+//   warp 17     TMA producer: pre-split W2 chunk images (32 KB) global/L2 -> shared ring (cp.async.bulk).
+//   warps 12-15 epilogue 2: TMEM(H2) -> +b2, ReLU -> layer 3 (256 -> 2A) in FP32 FMAs -> logits in smem.
+// All hand-offs are mbarriers (full/empty rings for A and B stages, H1/H2 full/free, X full, logits).
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace msacl {
+
+constexpr int TCM = 128;            // envs per tile
+constexpr int TC_HID = 256;
+constexpr int KC2 = 32;             // K per A/B stage
+constexpr int NCH = TC_HID / KC2;   // 8 chunks per tile-step
+constexpr int NA = 4, NB = 3;       // ring depths
+constexpr int A_HALF = TCM * KC2 * 2;       // 8 KB  (a1 or a2 image of a stage)
+constexpr int B_HALF = TC_HID * KC2 * 2;    // 16 KB (b1 or b2 image of a stage)
+constexpr int A_LBO = TCM * 16, B_LBO = TC_HID * 16, SBO = 128;
+constexpr int X_HALF = TCM * 16 * 2;        // 4 KB  (x1 or x2: 128 rows x 16 k)
+constexpr int W1_HALF = TC_HID * 16 * 2;    // 8 KB
+constexpr int TC_THREADS = 576;
+constexpr int W2P_BYTES = NCH * 2 * B_HALF; // 256 KB packed W2 (hi/lo chunk images)
+constexpr int W1P_BYTES = 2 * W1_HALF;
+
+struct TcBars {
+  unsigned long long xfull[2], logits[2];
+  unsigned long long h1full, h1free, h2full, h2free;
+  unsigned long long afull[NA], afree[NA], bfull[NB], bfree[NB];
+  uint32_t tmem_slot;
+};
+
+template <int ID>
+struct TcSmem {
+  using E = Env<ID>;
+  static constexpr int A2 = 2 * E::A;
+  alignas(128) unsigned char bstage[NB][2 * B_HALF];
+  alignas(128) unsigned char astage[NA][2 * A_HALF];
+  alignas(128) unsigned char w1p[W1P_BYTES];
+  alignas(128) unsigned char xop[2][2 * X_HALF];
+  alignas(16) float w3[8 * TC_HID];
+  alignas(16) float b2[TC_HID];
+  alignas(16) float b3[8];
+  alignas(16) float logits[2][8 * TCM];
+  TcBars bars;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {   // {hi:lo} packed, RNE
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 8 floats -> hi image (8 bf16) and lo image (8 bf16 of the residuals)
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    h[p] = pack_bf16x2_rn(v[2 * p], v[2 * p + 1]);
+    const float r0 = v[2 * p] - __uint_as_float(h[p] << 16);
+    const float r1 = v[2 * p + 1] - __uint_as_float(h[p] & 0xFFFF0000u);
+    l[p] = pack_bf16x2_rn(r0, r1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- one-time packing of the actor weights into UMMA operand images (device, per weight upload)
+// w1p: [hi|lo] x [2 kb][256 n][8 k] bf16, K index d < D = W1[n][d], K index D = b1[n], rest 0
+// w2p: 8 chunks x [hi|lo] x [4 kb][256 n][8 k] bf16, K-major (B[n][k] = W2[n][k] = w2t[k][n])
+__global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, unsigned char* __restrict__ w1p, unsigned char* __restrict__ w2p) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  // W2: one thread per (chunk c, kb, n): 8 * 4 * 256 = 8192 threads
+  if (gid < NCH * 4 * TC_HID) {
+    const int n = gid % TC_HID, kb = (gid / TC_HID) % 4, c = gid / (TC_HID * 4);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = actor.w2t[(size_t)(c * KC2 + kb * 8 + j) * TC_HID + n];
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    unsigned char* base = w2p + (size_t)c * 2 * B_HALF + kb * B_LBO + n * 16;
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + B_HALF) = lo;
+  }
+  // W1 (+ bias column): one thread per (kb, n): 512 threads
+  if (gid < 2 * TC_HID) {
+    const int n = gid % TC_HID, kb = gid / TC_HID;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kb * 8 + j;
+      v[j] = k < D ? actor.w1[n * D + k] : (k == D ? actor.b1[n] : 0.f);
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    unsigned char* base = w1p + kb * B_LBO + n * 16;
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + W1_HALF) = lo;
+  }
+}
+
+template <int ID>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char* __restrict__ w1p_g,
+                  const unsigned char* __restrict__ w2p_g, int K, uint32_t step_base, int n_step, float reward_scale,
+                  float cost_scale, const float* __restrict__ eps, int deterministic, msacl_transitions_t out, double* stats) {
+  using E = Env<ID>;
+  using S = TcSmem<ID>;
+  constexpr int D = E::D, A = E::A, A2 = 2 * A;
+  static_assert(D < 16, "layer-1 K block holds obs + bias column");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- one-time setup
+  for (int i = tid; i < W1P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm.w1p)[i] = reinterpret_cast<const uint4*>(w1p_g)[i];
+  for (int i = tid; i < 8 * TC_HID; i += TC_THREADS) sm.w3[i] = i < A2 * TC_HID ? actor.w3[i] : 0.f;
+  for (int i = tid; i < TC_HID; i += TC_THREADS) sm.b2[i] = actor.b2[i];
+  if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
+  if (tid == 0) {
+    TcBars& b = sm.bars;
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&b.xfull[s], TCM); tc::mbar_init(&b.logits[s], TCM); }
+    tc::mbar_init(&b.h1full, 1); tc::mbar_init(&b.h1free, TCM); tc::mbar_init(&b.h2full, 1); tc::mbar_init(&b.h2free, TCM);
+    for (int i = 0; i < NA; ++i) { tc::mbar_init(&b.afull[i], TCM); tc::mbar_init(&b.afree[i], 1); }
+    for (int i = 0; i < NB; ++i) { tc::mbar_init(&b.bfull[i], 1); tc::mbar_init(&b.bfree[i], 1); }
+    tc::mbar_fence_init();
+  }
+  if (warp == 16) tc::tmem_alloc(&sm.bars.tmem_slot, 512);
+  tc::fence_async_smem();      // w1p image was written with generic stores, read by UMMA
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sm.bars.tmem_slot;
+  const uint32_t tmem_h1 = tmem, tmem_h2 = tmem + 256;
+
+  const int64_t num_tiles = (st.n + TCM - 1) / TCM;
+  const int64_t num_pairs = (num_tiles + 1) / 2;
+  auto tiles_in_pair = [&](int64_t pair) { return (int)((num_tiles - 2 * pair) < 2 ? (num_tiles - 2 * pair) : 2); };
+
+  if (warp < 8) {
+    // =========================== env warps ===========================
+    const int s = warp >> 2;
+    const int r = tid & (TCM - 1);
+    uint32_t lcount = 0;
+    auto write_xop = [&](const float* obs, bool valid) {
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = (k < D) ? (valid ? obs[k < D ? k : 0] : 0.f) : (k == D ? 1.f : 0.f);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = v[kb * 8 + j];
+        uint4 hi, lo;
+        split8(w, hi, lo);
+        *reinterpret_cast<uint4*>(sm.xop[s] + kb * A_LBO + r * 16) = hi;
+        *reinterpret_cast<uint4*>(sm.xop[s] + X_HALF + kb * A_LBO + r * 16) = lo;
+      }
+      tc::fence_async_smem();
+      tc::mbar_arrive(&sm.bars.xfull[s]);
+    };
+    for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + s;
+      if (tile >= num_tiles) break;
+      const int64_t gi = tile * TCM + r;
+      const bool owner = gi < st.n;
+      EnvRegs<ID> e;
+      if (owner) e.load(st, gi);
+      write_xop(e.obs(), owner);
+      for (int k = 0; k < K; ++k) {
+        tc::mbar_wait(&sm.bars.logits[s], lcount & 1);
+        ++lcount;
+        if (owner) {
+          const int64_t row = (int64_t)k * st.n + gi;
+          if (out.obs) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) out.obs[row * D + d] = e.obs()[d];
+          }
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
+          if (!deterministic) {
+            if (eps) {
+#pragma unroll
+              for (int j = 0; j < A; ++j) z[j] = eps[row * A + j];
+            } else {
+              action_noise4(st.seed, st.env_base + (uint64_t)gi, step_base + (uint32_t)k, z);
+            }
+          }
+          float act[A];
+          float lp_gauss = 0.f, lp_tanh = 0.f, lp_scale = 0.f;
+#pragma unroll
+          for (int j = 0; j < A; ++j) {
+            const float mean = sm.logits[s][j * TCM + r];
+            const float ls = sm.logits[s][(A + j) * TCM + r];
+            const float sd = expf(fminf(fmaxf(ls, actor.min_log_std), actor.max_log_std));
+            const float half = (E::act_high(j) - E::act_low(j)) / 2.0f;
+            const float mid = (E::act_high(j) + E::act_low(j)) / 2.0f;
+            const float u = deterministic ? mean : (sd * z[j] + mean);
+            const float th = tanhf(u);
+            const float a_lim = half * th + mid;
+            const float diff = u - mean;
+            const float g = ((-(diff * diff)) / (2.0f * (sd * sd)) - logf(sd)) - 0.91893853320467267f;
+            const float t = logf(1.000001f - th * th);
+            const float sc = logf(half);
+            lp_gauss = (j == 0) ? g : lp_gauss + g;
+            lp_tanh = (j == 0) ? t : lp_tanh + t;
+            lp_scale = (j == 0) ? sc : lp_scale + sc;
+            act[j] = fminf(fmaxf(a_lim, E::act_low(j)), E::act_high(j));
+          }
+          const float logp = (lp_gauss - lp_tanh) - lp_scale;
+          const float rew = E::step(e.sf, e.sd, act);
+          const bool term = e.out_of_bounds();
+          e.step += 1;
+          const bool trunc = e.step >= st.max_step;
+          const bool done = term || trunc;
+          e.ep_return += rew;
+          e.ep_len += 1;
+          const float rew_s = rew * reward_scale;
+          const float cost = np_rowsum_sq<D>(e.obs()) * cost_scale;
+          e.run = min(e.run + 1, n_step);
+          const bool emit = e.run >= n_step;
+          if (out.act) {
+#pragma unroll
+            for (int j = 0; j < A; ++j) out.act[row * A + j] = act[j];
+          }
+          if (out.obs2) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) out.obs2[row * D + d] = e.obs()[d];
+          }
+          if (out.rew) out.rew[row] = rew_s;
+          if (out.cost) out.cost[row] = cost;
+          if (out.done) out.done[row] = done ? 1 : 0;
+          if (out.logp) out.logp[row] = logp;
+          if (out.emit) out.emit[row] = emit ? 1 : 0;
+          if (stats && done) {
+            atomicAdd(&stats[0], 1.0);
+            atomicAdd(&stats[1], (double)e.ep_return);
+            atomicAdd(&stats[2], (double)e.ep_len);
+            atomicAdd(&stats[term ? 3 : 4], 1.0);
+          }
+          if (done) {
+            e.episode += 1;
+            e.run = 0;
+            e.reset(st.seed, st.env_base + (uint64_t)gi);
+          }
+        }
+        if (k + 1 < K) write_xop(e.obs(), owner);
+      }
+      if (owner) e.store(st, gi);
+    }
+  } else if (warp < 12) {
+    // =========================== epilogue 1: H1 -> ReLU -> bf16 hi/lo -> A stages ===========================
+    const int r = tid - 256;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ts = 0;
+    for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+      const int nt = tiles_in_pair(pair);
+      for (int k = 0; k < K; ++k)
+        for (int s = 0; s < nt; ++s, ++ts) {
+          tc::mbar_wait(&sm.bars.h1full, ts & 1);
+          tc::tc_fence_after();
+          for (int c = 0; c < NCH; ++c) {
+            const uint32_t ai = ts * NCH + c, stg = ai % NA;
+            if (ai >= NA) tc::mbar_wait(&sm.bars.afree[stg], ((ai / NA) - 1) & 1);
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_h1 + lane_addr + (uint32_t)(c * 32), v);
+            tc::tmem_ld_wait();
+            if (c == NCH - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h1free); }
+            unsigned char* base = sm.astage[stg] + r * 16;
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+              float w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w[j] = fmaxf(__uint_as_float(v[kb * 8 + j]), 0.f);
+              uint4 hi, lo;
+              split8(w, hi, lo);
+              *reinterpret_cast<uint4*>(base + kb * A_LBO) = hi;
+              *reinterpret_cast<uint4*>(base + A_HALF + kb * A_LBO) = lo;
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(&sm.bars.afull[stg]);
+          }
+        }
+    }
+  } else if (warp < 16) {
+    // =========================== epilogue 2: H2 -> +b2, ReLU -> layer 3 -> logits ===========================
+    const int r = tid - 384;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ts = 0;
+    for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+      const int nt = tiles_in_pair(pair);
+      for (int k = 0; k < K; ++k)
+        for (int s = 0; s < nt; ++s, ++ts) {
+          tc::mbar_wait(&sm.bars.h2full, ts & 1);
+          tc::tc_fence_after();
+          float acc[A2];
+#pragma unroll
+          for (int j = 0; j < A2; ++j) acc[j] = sm.b3[j];
+          for (int cb = 0; cb < TC_HID / 32; ++cb) {
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_h2 + lane_addr + (uint32_t)(cb * 32), v);
+            tc::tmem_ld_wait();
+            if (cb == TC_HID / 32 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h2free); }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cb * 32 + 4 * q]);
+              const float h0 = fmaxf(__uint_as_float(v[4 * q + 0]) + bb.x, 0.f);
+              const float h1 = fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f);
+              const float h2 = fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f);
+              const float h3 = fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f);
+#pragma unroll
+              for (int j = 0; j < A2; ++j) {
+                const float4 w = *reinterpret_cast<const float4*>(&sm.w3[j * TC_HID + cb * 32 + 4 * q]);
+                acc[j] = __fmaf_rn(h0, w.x, acc[j]);
+                acc[j] = __fmaf_rn(h1, w.y, acc[j]);
+                acc[j] = __fmaf_rn(h2, w.z, acc[j]);
+                acc[j] = __fmaf_rn(h3, w.w, acc[j]);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < A2; ++j) sm.logits[s][j * TCM + r] = acc[j];
+          tc::mbar_arrive(&sm.bars.logits[s]);
+        }
+    }
+  } else if (warp == 16) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(TCM, TC_HID);
+      const uint64_t dw1 = tc::make_smem_desc(tc::smem_u32(sm.w1p), B_LBO, SBO);
+      const uint64_t dw2 = tc::make_smem_desc(tc::smem_u32(sm.w1p + W1_HALF), B_LBO, SBO);
+      uint32_t ts = 0, xcount[2] = {0, 0};
+      for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        const int nt = tiles_in_pair(pair);
+        for (int k = 0; k < K; ++k)
+          for (int s = 0; s < nt; ++s, ++ts) {
+            // ---- layer 1: H1 = [obs | 1 | 0] . [W1 | b1 | 0]^T  (K = 16, three products)
+            tc::mbar_wait(&sm.bars.xfull[s], xcount[s] & 1);
+            ++xcount[s];
+            if (ts > 0) tc::mbar_wait(&sm.bars.h1free, (ts - 1) & 1);
+            tc::tc_fence_after();
+            const uint64_t dx1 = tc::make_smem_desc(tc::smem_u32(sm.xop[s]), A_LBO, SBO);
+            const uint64_t dx2 = tc::make_smem_desc(tc::smem_u32(sm.xop[s] + X_HALF), A_LBO, SBO);
+            tc::umma_bf16(tmem_h1, dx1, dw1, idesc, 0u);
+            tc::umma_bf16(tmem_h1, dx1, dw2, idesc, 1u);
+            tc::umma_bf16(tmem_h1, dx2, dw1, idesc, 1u);
+            tc::umma_commit(&sm.bars.h1full);
+            // ---- layer 2: H2 = relu(H1) . W2^T over 8 K-chunks of 32
+            for (int c = 0; c < NCH; ++c) {
+              const uint32_t ai = ts * NCH + c, as = ai % NA, bs = ai % NB;
+              tc::mbar_wait(&sm.bars.afull[as], (ai / NA) & 1);
+              tc::mbar_wait(&sm.bars.bfull[bs], (ai / NB) & 1);
+              if (c == 0 && ts > 0) tc::mbar_wait(&sm.bars.h2free, (ts - 1) & 1);
+              tc::tc_fence_after();
+              const uint32_t abase = tc::smem_u32(sm.astage[as]), bbase = tc::smem_u32(sm.bstage[bs]);
+#pragma unroll
+              for (int j = 0; j < KC2 / 16; ++j) {
+                const uint64_t da1 = tc::make_smem_desc(abase + j * 2 * A_LBO, A_LBO, SBO);
+                const uint64_t da2 = tc::make_smem_desc(abase + A_HALF + j * 2 * A_LBO, A_LBO, SBO);
+                const uint64_t db1 = tc::make_smem_desc(bbase + j * 2 * B_LBO, B_LBO, SBO);
+                const uint64_t db2 = tc::make_smem_desc(bbase + B_HALF + j * 2 * B_LBO, B_LBO, SBO);
+                tc::umma_bf16(tmem_h2, da1, db1, idesc, (c > 0 || j > 0) ? 1u : 0u);
+                tc::umma_bf16(tmem_h2, da1, db2, idesc, 1u);
+                tc::umma_bf16(tmem_h2, da2, db1, idesc, 1u);
+              }
+              tc::umma_commit(&sm.bars.afree[as]);
+              tc::umma_commit(&sm.bars.bfree[bs]);
+            }
+            tc::umma_commit(&sm.bars.h2full);
+          }
+      }
+    }
+  } else {
+    // =========================== TMA producer: W2 chunk images ===========================
+    if (lane == 0) {
+      int64_t tile_steps = 0;
+      for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) tile_steps += (int64_t)tiles_in_pair(pair) * K;
+      const int64_t total = tile_steps * NCH;
+      for (int64_t i = 0; i < total; ++i) {
+        const uint32_t bs = (uint32_t)(i % NB);
+        if (i >= NB) tc::mbar_wait(&sm.bars.bfree[bs], (uint32_t)(((i / NB) - 1) & 1));
+        tc::mbar_expect_tx(&sm.bars.bfull[bs], 2 * B_HALF);
+        tc::tma_bulk_g2s(sm.bstage[bs], w2p_g + (size_t)(i % NCH) * 2 * B_HALF, 2 * B_HALF, &sm.bars.bfull[bs]);
+      }
+    }
+  }
+  // ---- teardown
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace msacl
+
+using namespace msacl;
+
+extern "C" int msacl_tc_pack_bytes(int64_t* w1p_bytes, int64_t* w2p_bytes) {
+  if (w1p_bytes) *w1p_bytes = W1P_BYTES;
+  if (w2p_bytes) *w2p_bytes = W2P_BYTES;
+  return MSACL_OK;
+}
+
+extern "C" int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, void* w1p, void* w2p, void* stream) {
+  if (!actor || !w1p || !w2p || obs_dim < 1 || obs_dim > 15) { set_error("tc_pack_actor: bad argument"); return MSACL_ERR_BAD_ARG; }
+  tc_pack_actor_kernel<<<(NCH * 4 * TC_HID + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*actor, obs_dim, (unsigned char*)w1p, (unsigned char*)w2p);
+  return check_launch("tc_pack_actor");
+}
+
+extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_actor_t* actor, const void* w1p,
+                                      const void* w2p, int32_t K, uint32_t step_base, int32_t n_step, float reward_scale,
+                                      float cost_scale, const float* eps, int32_t deterministic,
+                                      const msacl_transitions_t* out, double* stats, void* stream) {
+  if (!st || !actor || !out || !w1p || !w2p || st->n <= 0 || K <= 0 || n_step <= 0) { set_error("rollout_fused_tc: bad argument"); return MSACL_ERR_BAD_ARG; }
+  if ((reinterpret_cast<uintptr_t>(w2p) & 15) || (reinterpret_cast<uintptr_t>(w1p) & 15)) { set_error("rollout_fused_tc: packed weights must be 16-byte aligned"); return MSACL_ERR_BAD_ARG; }
+  const int64_t pairs = ((st->n + TCM - 1) / TCM + 1) / 2;
+  const unsigned grid = (unsigned)(pairs < kNumSMs ? pairs : kNumSMs);
+  MSACL_DISPATCH_ENV(st->env_id, {
+    const size_t smem = sizeof(TcSmem<ID>) + 128;
+    auto kern = rollout_tc_kernel<ID>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("rollout_fused_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
+    kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*st, *actor, (const unsigned char*)w1p, (const unsigned char*)w2p, K,
+                                                          step_base, n_step, reward_scale, cost_scale, eps, deterministic, *out, stats);
+  });
+  return check_launch("rollout_fused_tc");
+}

@@ -51,6 +51,18 @@ class ActorWeights:
                                w3=self.w3.data_ptr(), b3=self.b3.data_ptr(), min_log_std=float(min_log_std),
                                max_log_std=float(max_log_std))
 
+    def tc_images(self):
+        """UMMA operand images (split-bf16 W1|b1 and W2 chunk images) for the tensor-core kernel."""
+        if getattr(self, "_tc", None) is None:
+            lib = _lib.load()
+            n1, n2 = C.c_int64(0), C.c_int64(0)
+            _lib.check(lib.msacl_tc_pack_bytes(C.byref(n1), C.byref(n2)))
+            w1p = torch.empty(n1.value, dtype=torch.uint8, device=self.w1.device)
+            w2p = torch.empty(n2.value, dtype=torch.uint8, device=self.w1.device)
+            _lib.check(lib.msacl_tc_pack_actor(C.byref(self.desc), self.obs_dim, w1p.data_ptr(), w2p.data_ptr(), _lib.current_stream()))
+            self._tc = (w1p, w2p)
+        return self._tc
+
     @classmethod
     def from_policy(cls, policy, device="cuda"):
         """policy: a reference-style StochaPolicy (RL/apprfunc/mlp.py:111-136): `.policy` is an
@@ -120,7 +132,8 @@ class FusedRollout:
     """Owns env state + transition buffers and launches msacl_rollout_fused."""
 
     def __init__(self, env_name, num_envs, horizon, n_step=20, reward_scale=100.0, cost_scale=100.0, seed=0, env_base=0,
-                 device="cuda", max_step=None, state=None):
+                 device="cuda", max_step=None, state=None, engine="ffma"):
+        self.engine = engine
         self.spec = get_spec(env_name)
         self.state = state or EnvStateBuffers(env_name, num_envs, seed=seed, env_base=env_base, device=device, max_step=max_step)
         self.n, self.K, self.n_step = self.state.n, int(horizon), int(n_step)
@@ -129,8 +142,9 @@ class FusedRollout:
         self.stats = torch.zeros(8, dtype=torch.float64, device=self.state.device)
         self.global_step = 0
 
-    def run(self, actor: ActorWeights, eps=None, deterministic=False, write=True):
-        """One K-step chunk.  eps: optional CUDA float32 [K, n, act_dim] explicit N(0,1) draws."""
+    def run(self, actor: ActorWeights, eps=None, deterministic=False, write=True, engine=None):
+        """One K-step chunk.  eps: optional CUDA float32 [K, n, act_dim] explicit N(0,1) draws.
+        engine: "ffma" (FP32 FFMA actor) or "tc" (tcgen05 split-bf16 actor); default self.engine."""
         if actor.obs_dim != self.spec.obs_dim or actor.act_dim != self.spec.act_dim:
             raise ValueError("actor dimensions do not match the environment")
         tr = self.tr
@@ -139,10 +153,18 @@ class FusedRollout:
         if eps is not None:
             eps = eps.contiguous()
             assert tuple(eps.shape) == (self.K, self.n, self.spec.act_dim) and eps.is_cuda
-        _lib.check(_lib.load().msacl_rollout_fused(
-            C.byref(self.state.desc), C.byref(actor.desc), self.K, self.global_step & 0xFFFFFFFF, self.n_step,
-            self.reward_scale, self.cost_scale, None if eps is None else eps.data_ptr(), 1 if deterministic else 0,
-            C.byref(out), self.stats.data_ptr(), _lib.current_stream()))
+        engine = engine or self.engine
+        common = (self.K, self.global_step & 0xFFFFFFFF, self.n_step, self.reward_scale, self.cost_scale,
+                  None if eps is None else eps.data_ptr(), 1 if deterministic else 0, C.byref(out), self.stats.data_ptr(),
+                  _lib.current_stream())
+        if engine == "tc":
+            w1p, w2p = actor.tc_images()
+            _lib.check(_lib.load().msacl_rollout_fused_tc(C.byref(self.state.desc), C.byref(actor.desc), w1p.data_ptr(),
+                                                         w2p.data_ptr(), *common))
+        elif engine == "ffma":
+            _lib.check(_lib.load().msacl_rollout_fused(C.byref(self.state.desc), C.byref(actor.desc), *common))
+        else:
+            raise ValueError(f"unknown rollout engine {engine!r}")
         self.global_step += self.K
         return DeviceWindowBatch(tr, self.n_step)
 
