@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--inner", type=int, default=16, help="env steps per fused launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replay-batch", type=int, default=256)
+    ap.add_argument("--engine", default="tc", choices=["tc", "ffma"],
+                    help="actor engine: tcgen05 split-bf16 tensor cores (default) or FP32 FFMA")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -181,7 +183,7 @@ def main():
         dw = [p.to(dev, non_blocking=True) for p in host_w]
         return ActorWeights([(dw[0], dw[1]), (dw[2], dw[3]), (dw[4], dw[5])], device=dev)
 
-    ro = FusedRollout(args.env, n, K, n_step=n_step, seed=0, env_base=rank * n, device=dev)
+    ro = FusedRollout(args.env, n, K, n_step=n_step, seed=0, env_base=rank * n, device=dev, engine=args.engine)
     ro.state.reset()
     actor = upload_actor()
     stream = torch.cuda.current_stream()
@@ -228,7 +230,7 @@ def main():
         batch = ro.run(a)                                # fused K-step rollout
         buf.add_batch(batch)                             # n-step windows -> device replay ring
         sub = buf.sample_batch(Bq)                       # replay batch for the learner
-        stats = ro.stats.clone()
+        stats = ro.stats[:8].clone()
         if world > 1:                                    # NCCL: replay-batch all-gather + episode statistics all-reduce
             sub = mdist.all_gather_replay_batch(sub)
             stats = mdist.all_reduce_stats(stats)
@@ -283,16 +285,31 @@ def main():
     bytes_per_step = transition_bytes(D, A)
     state_bytes = 2 * (4 * spec.sf_rows + 8 * spec.sd_rows + 20)      # read + write once per launch
     hbm_gbs = (bytes_per_step * n * K + state_bytes * n) / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "fp32_ffma", "achieved": achieved_tflops, "peak": ffma_peak, "unit": "TFLOP/s",
-                "frac": achieved_tflops / ffma_peak, "traffic": None,
-                "peak_source": "measured in this run: msacl_ffma_probe (8 independent FFMA chains/thread, 2x256 threads/SM); "
-                               "MEASURED_PEAKS.json has no FP32 figure (theoretical 148*128*2*1.965 GHz = 74.4)",
-                "register_tiled_sgemm_ceiling_tflops": ffma_outer, "register_tiled_ffma2_ceiling_tflops": ffma2_outer,
-                "kernel": f"rollout_fused_kernel<{args.env}>", "kernel_ms": kern_ms,
-                "algorithmic_flops_per_env_step": flops_per_step,
-                "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
-                        "algorithmic_bytes_per_env_step": bytes_per_step + state_bytes / K,
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tensor_burst = float(peaks.get("bf16_tflops", 1590.0))
+    hbm_info = {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
+                "algorithmic_bytes_per_env_step": bytes_per_step + state_bytes / K,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
+    if args.engine == "ffma":
+        roofline = {"bound": "fp32_ffma", "achieved": achieved_tflops, "peak": ffma_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tflops / ffma_peak, "traffic": None,
+                    "peak_source": "measured in this run: msacl_ffma_probe (8 independent FFMA chains/thread, 2x256 threads/SM); "
+                                   "MEASURED_PEAKS.json has no FP32 figure (theoretical 148*128*2*1.965 GHz = 74.4)",
+                    "register_tiled_sgemm_ceiling_tflops": ffma_outer, "register_tiled_ffma2_ceiling_tflops": ffma2_outer,
+                    "kernel": f"rollout_fused_kernel<{args.env}>", "kernel_ms": kern_ms,
+                    "algorithmic_flops_per_env_step": flops_per_step, "hbm": hbm_info}
+    else:
+        # tensor path: algorithmic FLOPs (one FP32-equivalent pass) against the measured dense bf16 peak; the
+        # split-bf16 scheme issues 3 UMMAs per algorithmic product, so tensor-pipe utilisation is ~3x `frac`.
+        roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tflops / tensor_peak, "traffic": None,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
+                                    else "fallback 1.4 PFLOP/s sustained"),
+                    "peak_burst": tensor_burst, "tensor_issue_factor": 3,
+                    "tensor_pipe_frac_incl_split": 3 * achieved_tflops * (1 - 2 * 256 * 2 * A / flops_per_step) / tensor_peak,
+                    "fp32_ffma_peak_tflops": ffma_peak,
+                    "kernel": f"rollout_tc_kernel<{args.env}>", "kernel_ms": kern_ms,
+                    "algorithmic_flops_per_env_step": flops_per_step, "hbm": hbm_info}
 
     if rank == 0:
         cpu = None
@@ -301,10 +318,11 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if args.engine == "ffma" else "bf16x3 (split-bf16 tensor-core products, f32 accumulate; f32/f64 dynamics)",
+            "data": "synthetic",
             "config": {"workload": f"{args.env} fused rollout (actor MLP + TanhGauss sample + env ODE step + reward/cost + autoreset), "
                                    f"{n} envs/GPU (BASELINE config 5 per-GPU share), {K} env steps per launch, transitions written to HBM",
-                       "envs_per_gpu": n, "inner_steps": K, "n_step": n_step, "l2": "inputs larger than L2 (state + transitions per launch >> 126 MB)",
+                       "engine": args.engine, "envs_per_gpu": n, "inner_steps": K, "n_step": n_step, "l2": "inputs larger than L2 (state + transitions per launch >> 126 MB)",
                        "parallelism": f"env-sharded x{world}, no step-path collective"},
             "clocks": clk, "gpu_launches": args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

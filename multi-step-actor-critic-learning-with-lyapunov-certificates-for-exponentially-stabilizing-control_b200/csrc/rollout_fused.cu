@@ -305,6 +305,7 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
     // =========================== env warps ===========================
     const int T = (tid - NGEMM) >> 6;        // tile slot owned by this warp pair
     const int et = (tid - NGEMM) & (TM - 1); // env within the tile
+    float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_term = 0.f, st_trunc = 0.f;
     for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
       const int64_t tile = NTILE * pair + T;
       if (tile >= num_tiles) break;          // CTA-uniform per warp pair; GEMM warps skip this slot too
@@ -386,11 +387,9 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
           if (out.done) out.done[row] = done ? 1 : 0;
           if (out.logp) out.logp[row] = logp;
           if (out.emit) out.emit[row] = emit ? 1 : 0;
-          if (stats && done) {
-            atomicAdd(&stats[0], 1.0);
-            atomicAdd(&stats[1], (double)r.ep_return);
-            atomicAdd(&stats[2], (double)r.ep_len);
-            atomicAdd(&stats[term ? 3 : 4], 1.0);
+          if (done) {      // episode statistics: per-thread partials, reduced once per launch (no hot atomics)
+            st_ep += 1.f; st_ret += r.ep_return; st_len += (float)r.ep_len;
+            if (term) st_term += 1.f; else st_trunc += 1.f;
           }
           if (done) {
             r.episode += 1;
@@ -406,6 +405,15 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
         }
       }
       if (owner) r.store(st, gi);
+    }
+    if (stats) {
+      float v[5] = {st_ep, st_ret, st_len, st_term, st_trunc};
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        if (lane == 0 && v[q] != 0.f) atomicAdd(&stats[q], (double)v[q]);
+      }
     }
   }
 }

@@ -24,6 +24,14 @@
 
 namespace msacl {
 
+#ifdef MSACL_TC_TIMING
+#define TC_T0(var) const long long var = clock64()
+#define TC_ACC(slot, t0) do { if (stats) atomicAdd(&stats[slot], (double)(clock64() - (t0))); } while (0)
+#else
+#define TC_T0(var) do {} while (0)
+#define TC_ACC(slot, t0) do {} while (0)
+#endif
+
 constexpr int TCM = 128;            // envs per tile
 constexpr int TC_HID = 256;
 constexpr int KC2 = 32;             // K per A/B stage
@@ -34,7 +42,8 @@ constexpr int B_HALF = TC_HID * KC2 * 2;    // 16 KB (b1 or b2 image of a stage)
 constexpr int A_LBO = TCM * 16, B_LBO = TC_HID * 16, SBO = 128;
 constexpr int X_HALF = TCM * 16 * 2;        // 4 KB  (x1 or x2: 128 rows x 16 k)
 constexpr int W1_HALF = TC_HID * 16 * 2;    // 8 KB
-constexpr int TC_THREADS = 576;
+constexpr int TC_THREADS = 640;          // 5 warpgroups: env0, env1, epilogue 1, epilogue 2, {MMA, TMA, 2 idle}
+constexpr int ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40;   // setmaxnreg targets (launch: 96/thread)
 constexpr int W2P_BYTES = NCH * 2 * B_HALF; // 256 KB packed W2 (hi/lo chunk images)
 constexpr int W1P_BYTES = 2 * W1_HALF;
 
@@ -153,9 +162,11 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
 
   if (warp < 8) {
     // =========================== env warps ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ENV_REGS));
     const int s = warp >> 2;
     const int r = tid & (TCM - 1);
     uint32_t lcount = 0;
+    float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_term = 0.f, st_trunc = 0.f;
     auto write_xop = [&](const float* obs, bool valid) {
       float v[16];
 #pragma unroll
@@ -182,8 +193,14 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       if (owner) e.load(st, gi);
       write_xop(e.obs(), owner);
       for (int k = 0; k < K; ++k) {
+#ifdef MSACL_TC_TIMING
+        const long long t_w0 = clock64();
+#endif
         tc::mbar_wait(&sm.bars.logits[s], lcount & 1);
         ++lcount;
+#ifdef MSACL_TC_TIMING
+        const long long t_w1 = clock64();
+#endif
         if (owner) {
           const int64_t row = (int64_t)k * st.n + gi;
           if (out.obs) {
@@ -221,7 +238,11 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
             act[j] = fminf(fmaxf(a_lim, E::act_low(j)), E::act_high(j));
           }
           const float logp = (lp_gauss - lp_tanh) - lp_scale;
+#ifdef MSACL_TC_SKIP_ENV
+          const float rew = act[0];
+#else
           const float rew = E::step(e.sf, e.sd, act);
+#endif
           const bool term = e.out_of_bounds();
           e.step += 1;
           const bool trunc = e.step >= st.max_step;
@@ -232,37 +253,59 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           const float cost = np_rowsum_sq<D>(e.obs()) * cost_scale;
           e.run = min(e.run + 1, n_step);
           const bool emit = e.run >= n_step;
+          float obs2[D];                                  // real_next_obs (pre-reset)
+#pragma unroll
+          for (int d = 0; d < D; ++d) obs2[d] = e.obs()[d];
+          if (done) {      // episode statistics: per-thread partials, reduced once per launch (no hot atomics)
+            st_ep += 1.f; st_ret += e.ep_return; st_len += (float)e.ep_len;
+            if (term) st_term += 1.f; else st_trunc += 1.f;
+            e.episode += 1;
+            e.run = 0;
+            e.reset(st.seed, st.env_base + (uint64_t)gi);
+          }
+          // hand the next observation to the tensor pipeline FIRST: the proxy fence inside write_xop
+          // waits for this thread's outstanding memory operations, so the (uncoalesced) transition
+          // stores are issued after it and drain while the MLP of this tile is already running
+          if (k + 1 < K) write_xop(e.obs(), true);
           if (out.act) {
 #pragma unroll
             for (int j = 0; j < A; ++j) out.act[row * A + j] = act[j];
           }
           if (out.obs2) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) out.obs2[row * D + d] = e.obs()[d];
+            for (int d = 0; d < D; ++d) out.obs2[row * D + d] = obs2[d];
           }
           if (out.rew) out.rew[row] = rew_s;
           if (out.cost) out.cost[row] = cost;
           if (out.done) out.done[row] = done ? 1 : 0;
           if (out.logp) out.logp[row] = logp;
           if (out.emit) out.emit[row] = emit ? 1 : 0;
-          if (stats && done) {
-            atomicAdd(&stats[0], 1.0);
-            atomicAdd(&stats[1], (double)e.ep_return);
-            atomicAdd(&stats[2], (double)e.ep_len);
-            atomicAdd(&stats[term ? 3 : 4], 1.0);
-          }
-          if (done) {
-            e.episode += 1;
-            e.run = 0;
-            e.reset(st.seed, st.env_base + (uint64_t)gi);
-          }
+        } else if (k + 1 < K) {
+          write_xop(e.obs(), false);
         }
-        if (k + 1 < K) write_xop(e.obs(), owner);
+#ifdef MSACL_TC_TIMING
+        if (stats && r == 0) {
+          const long long t_e = clock64();
+          atomicAdd(&stats[5], (double)(t_e - t_w1));
+          atomicAdd(&stats[6], (double)(t_w1 - t_w0));
+          atomicAdd(&stats[7], 1.0);
+        }
+#endif
       }
       if (owner) e.store(st, gi);
     }
+    if (stats) {
+      float v[5] = {st_ep, st_ret, st_len, st_term, st_trunc};
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        if (lane == 0 && v[q] != 0.f) atomicAdd(&stats[q], (double)v[q]);
+      }
+    }
   } else if (warp < 12) {
     // =========================== epilogue 1: H1 -> ReLU -> bf16 hi/lo -> A stages ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
     const int r = tid - 256;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ts = 0;
@@ -270,11 +313,16 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       const int nt = tiles_in_pair(pair);
       for (int k = 0; k < K; ++k)
         for (int s = 0; s < nt; ++s, ++ts) {
+          TC_T0(t_a);
           tc::mbar_wait(&sm.bars.h1full, ts & 1);
           tc::tc_fence_after();
+          if (r == 0) TC_ACC(8, t_a);                 // epi1: wait for H1
+          TC_T0(t_b);
           for (int c = 0; c < NCH; ++c) {
             const uint32_t ai = ts * NCH + c, stg = ai % NA;
+            TC_T0(t_c);
             if (ai >= NA) tc::mbar_wait(&sm.bars.afree[stg], ((ai / NA) - 1) & 1);
+            if (r == 0) TC_ACC(10, t_c);              // epi1: wait for a free A stage
             uint32_t v[32];
             tc::tmem_ld32(tmem_h1 + lane_addr + (uint32_t)(c * 32), v);
             tc::tmem_ld_wait();
@@ -293,10 +341,12 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
             tc::fence_async_smem();
             tc::mbar_arrive(&sm.bars.afull[stg]);
           }
+          if (r == 0) TC_ACC(9, t_b);                 // epi1: chunk loop total
         }
     }
   } else if (warp < 16) {
     // =========================== epilogue 2: H2 -> +b2, ReLU -> layer 3 -> logits ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
     const int r = tid - 384;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ts = 0;
@@ -304,8 +354,11 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       const int nt = tiles_in_pair(pair);
       for (int k = 0; k < K; ++k)
         for (int s = 0; s < nt; ++s, ++ts) {
+          TC_T0(t_a);
           tc::mbar_wait(&sm.bars.h2full, ts & 1);
           tc::tc_fence_after();
+          if (r == 0) TC_ACC(11, t_a);                // epi2: wait for H2
+          TC_T0(t_b);
           float acc[A2];
 #pragma unroll
           for (int j = 0; j < A2; ++j) acc[j] = sm.b3[j];
@@ -334,9 +387,12 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
 #pragma unroll
           for (int j = 0; j < A2; ++j) sm.logits[s][j * TCM + r] = acc[j];
           tc::mbar_arrive(&sm.bars.logits[s]);
+          if (r == 0) TC_ACC(12, t_b);                // epi2: compute
         }
     }
-  } else if (warp == 16) {
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MISC_REGS));
+    if (warp == 16) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(TCM, TC_HID);
@@ -348,9 +404,13 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         for (int k = 0; k < K; ++k)
           for (int s = 0; s < nt; ++s, ++ts) {
             // ---- layer 1: H1 = [obs | 1 | 0] . [W1 | b1 | 0]^T  (K = 16, three products)
+            TC_T0(t_x);
             tc::mbar_wait(&sm.bars.xfull[s], xcount[s] & 1);
             ++xcount[s];
+            TC_ACC(13, t_x);                          // MMA: wait for X
+            TC_T0(t_h);
             if (ts > 0) tc::mbar_wait(&sm.bars.h1free, (ts - 1) & 1);
+            TC_ACC(14, t_h);                          // MMA: wait for H1 free
             tc::tc_fence_after();
             const uint64_t dx1 = tc::make_smem_desc(tc::smem_u32(sm.xop[s]), A_LBO, SBO);
             const uint64_t dx2 = tc::make_smem_desc(tc::smem_u32(sm.xop[s] + X_HALF), A_LBO, SBO);
@@ -361,9 +421,15 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
             // ---- layer 2: H2 = relu(H1) . W2^T over 8 K-chunks of 32
             for (int c = 0; c < NCH; ++c) {
               const uint32_t ai = ts * NCH + c, as = ai % NA, bs = ai % NB;
+              TC_T0(t_1);
               tc::mbar_wait(&sm.bars.afull[as], (ai / NA) & 1);
+              TC_ACC(15, t_1);                        // MMA: wait for A chunk
+              TC_T0(t_2);
               tc::mbar_wait(&sm.bars.bfull[bs], (ai / NB) & 1);
+              TC_ACC(16, t_2);                        // MMA: wait for B chunk
+              TC_T0(t_3);
               if (c == 0 && ts > 0) tc::mbar_wait(&sm.bars.h2free, (ts - 1) & 1);
+              TC_ACC(17, t_3);                        // MMA: wait for H2 free
               tc::tc_fence_after();
               const uint32_t abase = tc::smem_u32(sm.astage[as]), bbase = tc::smem_u32(sm.bstage[bs]);
 #pragma unroll
@@ -380,10 +446,13 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
               tc::umma_commit(&sm.bars.bfree[bs]);
             }
             tc::umma_commit(&sm.bars.h2full);
+#ifdef MSACL_TC_TIMING
+            if (stats) atomicAdd(&stats[18], 1.0);
+#endif
           }
       }
     }
-  } else {
+    } else if (warp == 17) {
     // =========================== TMA producer: W2 chunk images ===========================
     if (lane == 0) {
       int64_t tile_steps = 0;
@@ -395,6 +464,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         tc::mbar_expect_tx(&sm.bars.bfull[bs], 2 * B_HALF);
         tc::tma_bulk_g2s(sm.bstage[bs], w2p_g + (size_t)(i % NCH) * 2 * B_HALF, 2 * B_HALF, &sm.bars.bfull[bs]);
       }
+    }
     }
   }
   // ---- teardown

@@ -209,6 +209,24 @@ __global__ void __launch_bounds__(256) ffma2_probe_outer_kernel(int iters, const
   if (s == 123.456f) sink[0] = s;
 }
 
+// mode 3: FP64 DFMA throughput (8 independent chains per thread)
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, float* sink) {
+  double a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = (double)(threadIdx.x + j) * 1e-3;
+  const double x = (double)sink[64] * 1e-9 + 1.0, y = (double)sink[65] * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = __fma_rn(a[j], x, y);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == 123.456) sink[0] = (float)s;
+}
+
 }  // namespace msacl
 
 using namespace msacl;
@@ -268,7 +286,7 @@ extern "C" int msacl_advantage_normalize(int64_t B, const float* adv_raw, const 
 }
 
 extern "C" int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, void* stream) {
-  if (iters <= 0 || !sink || mode < 0 || mode > 2) { set_error("ffma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
+  if (iters <= 0 || !sink || mode < 0 || mode > 3) { set_error("ffma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
   const unsigned grid = 2 * kNumSMs * 4;
   if (mode == 0) {
     ffma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
@@ -276,9 +294,12 @@ extern "C" int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double
   } else if (mode == 1) {
     ffma_probe_outer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink + 64, sink);   // sink[64..128) = operand source
     if (flops) *flops = 2.0 * 128.0 * (double)iters * 256.0 * (double)grid;
-  } else {
+  } else if (mode == 2) {
     ffma2_probe_outer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink + 64, sink);
     if (flops) *flops = 2.0 * 128.0 * (double)iters * 256.0 * (double)grid;
+  } else {
+    dfma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (flops) *flops = 2.0 * 32.0 * (double)iters * 256.0 * (double)grid;
   }
   return check_launch("ffma_probe");
 }

@@ -139,7 +139,7 @@ class FusedRollout:
         self.n, self.K, self.n_step = self.state.n, int(horizon), int(n_step)
         self.reward_scale, self.cost_scale = float(reward_scale), float(cost_scale)
         self.tr = TransitionBuffers(self.spec, self.n, self.K, self.n_step, self.state.device)
-        self.stats = torch.zeros(8, dtype=torch.float64, device=self.state.device)
+        self.stats = torch.zeros(32, dtype=torch.float64, device=self.state.device)   # [0:8) documented, rest diagnostic
         self.global_step = 0
 
     def run(self, actor: ActorWeights, eps=None, deterministic=False, write=True, engine=None):
