@@ -86,3 +86,54 @@ def test_tc_rollout_multi_step_large(name, n):
         np.testing.assert_allclose(fb["act"][k][same], fa["act"][k][same], rtol=0, atol=2e-3 * span)
         np.testing.assert_allclose(fb["obs2"][k][same], fa["obs2"][k][same], rtol=1e-3, atol=2e-2)
     assert same.mean() > 0.99
+
+
+def test_tc_rollout_against_reference_golden_sampler_run():
+    """The reference sampler's own recorded steps (weights, obs, eps -> action, log-prob, next obs)
+    replayed through the tensor-core kernel.  Tolerance (split-bf16 actor): actions 1e-4 * range,
+    next observation 1e-3 (5e-3 Quad), done flags exact away from the bounds."""
+    from conftest import load_golden
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    for name in oenv.ENV_NAMES:
+        g = load_golden(f"sampler_{name}.npz")
+        spec = oenv.SPECS[name]
+        T, N = g["step_eps"].shape[:2]
+        aw = ActorWeights([(g[f"W{i}"], g[f"b{i}"]) for i in range(3)])
+        ro = FusedRollout(name, N, 1, n_step=int(g["n_step"]), max_step=int(g["max_step"]), engine="tc")
+        post = {k[5:]: g[k] for k in g if k.startswith("post_")}
+        prev = {k[5:]: g[k] for k in g if k.startswith("init_")}
+        span = float((spec.act_high - spec.act_low).max())
+        for t in range(T):
+            if name == "QuadTracking":
+                ro.state.set_quad_state(prev["x"], prev["v"], prev["R"], prev["Om"], t=prev["t"], Rd_last=prev["Rd_last"],
+                                        obs=prev["obs"], step=prev["step"])
+            else:
+                ro.state.set_box_state(prev["obs"], prev["step"])
+            ro.run(aw, eps=torch.as_tensor(g["step_eps"][t][None]).cuda())
+            out = {k: v[ro.tr.H].cpu().numpy() for k, v in ro.tr.fields().items()}
+            np.testing.assert_allclose(out["act"], g["step_act"][t], rtol=0, atol=1e-4 * span)
+            tol = 5e-3 if name == "QuadTracking" else 1e-3
+            np.testing.assert_allclose(out["obs2"], g["step_obs2"][t], rtol=1e-4, atol=tol)
+            near = (np.abs(g["step_obs2"][t] - spec.obs_low) < 1e-2).any(1) | (np.abs(g["step_obs2"][t] - spec.obs_high) < 1e-2).any(1)
+            assert np.array_equal(out["done"].astype(bool)[~near], (g["step_done"][t] > 0)[~near])
+            prev = {k: post[k][t] for k in post}
+
+
+def test_tc_statistics_and_determinism():
+    """Episode statistics are reduced per launch; two identical launches give identical results."""
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    name, n, K = "Pendulum", 5000, 12
+    spec = oenv.SPECS[name]
+    aw = ActorWeights(oactor.init_policy_weights(spec.obs_dim, spec.act_dim, seed=1))
+    outs = []
+    for rep in range(2):
+        ro = FusedRollout(name, n, K, n_step=4, seed=9, engine="tc")
+        ro.state.reset()
+        ro.run(aw)
+        f = {k: v[ro.tr.H:].clone() for k, v in ro.tr.fields().items()}
+        outs.append((f, ro.stats.clone()))
+    for k in outs[0][0]:
+        assert torch.equal(outs[0][0][k], outs[1][0][k]), k
+    st = outs[0][1].cpu().numpy()
+    done = outs[0][0]["done"].cpu().numpy().astype(bool)
+    assert st[0] == done.sum() and st[3] + st[4] == st[0] and st[0] > 0
