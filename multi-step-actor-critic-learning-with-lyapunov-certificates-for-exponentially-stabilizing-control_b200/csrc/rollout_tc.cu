@@ -36,36 +36,41 @@ constexpr int TCM = 128;            // envs per tile
 constexpr int TC_HID = 256;
 constexpr int KC2 = 32;             // K per A/B stage
 constexpr int NCH = TC_HID / KC2;   // 8 chunks per tile-step
-constexpr int NA = 4, NB = 3;       // ring depths
+constexpr int NB = 3;               // W2 ring depth
 constexpr int A_HALF = TCM * KC2 * 2;       // 8 KB  (a1 or a2 image of a stage)
 constexpr int B_HALF = TC_HID * KC2 * 2;    // 16 KB (b1 or b2 image of a stage)
 constexpr int A_LBO = TCM * 16, B_LBO = TC_HID * 16, SBO = 128;
 constexpr int X_HALF = TCM * 16 * 2;        // 4 KB  (x1 or x2: 128 rows x 16 k)
 constexpr int W1_HALF = TC_HID * 16 * 2;    // 8 KB
-constexpr int TC_THREADS = 640;          // 5 warpgroups: env0, env1, epilogue 1, epilogue 2, {MMA, TMA, 2 idle}
-constexpr int ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40;   // setmaxnreg targets (launch: 96/thread)
+// Launch geometry per number of tile slots in flight: NS env warpgroups + epilogue 1 + epilogue 2 +
+// {MMA, TMA, 2 idle warps}.  Registers are rebalanced with setmaxnreg (65536 per SM in total).
+template <int NS> struct TcCfg;
+template <> struct TcCfg<2> { static constexpr int THREADS = 640, ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40, NA = 4; };
+template <> struct TcCfg<3> { static constexpr int THREADS = 768, ENV_REGS = 112, EPI_REGS = 56, MISC_REGS = 32, NA = 4; };   // launch 80: 12*32 <= 8*24 + 4*48
+template <> struct TcCfg<4> { static constexpr int THREADS = 896, ENV_REGS = 88, EPI_REGS = 56, MISC_REGS = 32, NA = 3; };    // launch 72: 16*16 <= 8*16 + 4*40
+constexpr int NA_MAX = 4;
 constexpr int W2P_BYTES = NCH * 2 * B_HALF; // 256 KB packed W2 (hi/lo chunk images)
 constexpr int W1P_BYTES = 2 * W1_HALF;
 
 struct TcBars {
-  unsigned long long xfull[2], logits[2];
+  unsigned long long xfull[4], logits[4];
   unsigned long long h1full, h1free, h2full, h2free;
-  unsigned long long afull[NA], afree[NA], bfull[NB], bfree[NB];
+  unsigned long long afull[NA_MAX], afree[NA_MAX], bfull[NB], bfree[NB];
   uint32_t tmem_slot;
 };
 
-template <int ID>
+template <int ID, int NS>
 struct TcSmem {
   using E = Env<ID>;
   static constexpr int A2 = 2 * E::A;
   alignas(128) unsigned char bstage[NB][2 * B_HALF];
-  alignas(128) unsigned char astage[NA][2 * A_HALF];
+  alignas(128) unsigned char astage[TcCfg<NS>::NA][2 * A_HALF];
   alignas(128) unsigned char w1p[W1P_BYTES];
-  alignas(128) unsigned char xop[2][2 * X_HALF];
+  alignas(128) unsigned char xop[NS][2 * X_HALF];
   alignas(16) float w3[8 * TC_HID];
   alignas(16) float b2[TC_HID];
   alignas(16) float b3[8];
-  alignas(16) float logits[2][8 * TCM];
+  alignas(16) float logits[NS][2 * Env<ID>::A * TCM];
   TcBars bars;
 };
 
@@ -122,14 +127,17 @@ __global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, unsigned char* 
   }
 }
 
-template <int ID>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int ID, int NS>
+__global__ void __launch_bounds__(TcCfg<NS>::THREADS, 1)
 rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char* __restrict__ w1p_g,
                   const unsigned char* __restrict__ w2p_g, int K, uint32_t step_base, int n_step, float reward_scale,
                   float cost_scale, const float* __restrict__ eps, int deterministic, msacl_transitions_t out, double* stats) {
   using E = Env<ID>;
-  using S = TcSmem<ID>;
+  using S = TcSmem<ID, NS>;
+  using CFG = TcCfg<NS>;
   constexpr int D = E::D, A = E::A, A2 = 2 * A;
+  constexpr int TC_THREADS = CFG::THREADS, NA = CFG::NA;
+  constexpr int W_EPI1 = 4 * NS, W_EPI2 = 4 * NS + 4, W_MMA = 4 * NS + 8, W_TMA = 4 * NS + 9;
   static_assert(D < 16, "layer-1 K block holds obs + bias column");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
@@ -142,13 +150,13 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
   if (tid == 0) {
     TcBars& b = sm.bars;
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&b.xfull[s], TCM); tc::mbar_init(&b.logits[s], TCM); }
+    for (int s = 0; s < NS; ++s) { tc::mbar_init(&b.xfull[s], TCM); tc::mbar_init(&b.logits[s], TCM); }
     tc::mbar_init(&b.h1full, 1); tc::mbar_init(&b.h1free, TCM); tc::mbar_init(&b.h2full, 1); tc::mbar_init(&b.h2free, TCM);
     for (int i = 0; i < NA; ++i) { tc::mbar_init(&b.afull[i], TCM); tc::mbar_init(&b.afree[i], 1); }
     for (int i = 0; i < NB; ++i) { tc::mbar_init(&b.bfull[i], 1); tc::mbar_init(&b.bfree[i], 1); }
     tc::mbar_fence_init();
   }
-  if (warp == 16) tc::tmem_alloc(&sm.bars.tmem_slot, 512);
+  if (warp == W_MMA) tc::tmem_alloc(&sm.bars.tmem_slot, 512);
   tc::fence_async_smem();      // w1p image was written with generic stores, read by UMMA
   tc::tc_fence_before();
   __syncthreads();
@@ -157,13 +165,13 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   const uint32_t tmem_h1 = tmem, tmem_h2 = tmem + 256;
 
   const int64_t num_tiles = (st.n + TCM - 1) / TCM;
-  const int64_t num_pairs = (num_tiles + 1) / 2;
-  auto tiles_in_pair = [&](int64_t pair) { return (int)((num_tiles - 2 * pair) < 2 ? (num_tiles - 2 * pair) : 2); };
+  const int64_t num_pairs = (num_tiles + NS - 1) / NS;      // "pair" = group of NS tiles in flight
+  auto tiles_in_pair = [&](int64_t pair) { return (int)((num_tiles - NS * pair) < NS ? (num_tiles - NS * pair) : NS); };
 
-  if (warp < 8) {
+  if (warp < W_EPI1) {
     // =========================== env warps ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ENV_REGS));
-    const int s = warp >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CFG::ENV_REGS));
+    const int s = warp >> 2;                 // tile slot of this env warpgroup
     const int r = tid & (TCM - 1);
     uint32_t lcount = 0;
     float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_term = 0.f, st_trunc = 0.f;
@@ -185,7 +193,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       tc::mbar_arrive(&sm.bars.xfull[s]);
     };
     for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-      const int64_t tile = 2 * pair + s;
+      const int64_t tile = NS * pair + s;
       if (tile >= num_tiles) break;
       const int64_t gi = tile * TCM + r;
       const bool owner = gi < st.n;
@@ -303,10 +311,10 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         if (lane == 0 && v[q] != 0.f) atomicAdd(&stats[q], (double)v[q]);
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < W_EPI2) {
     // =========================== epilogue 1: H1 -> ReLU -> bf16 hi/lo -> A stages ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
-    const int r = tid - 256;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CFG::EPI_REGS));
+    const int r = tid - W_EPI1 * 32;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ts = 0;
     for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
@@ -344,10 +352,10 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           if (r == 0) TC_ACC(9, t_b);                 // epi1: chunk loop total
         }
     }
-  } else if (warp < 16) {
+  } else if (warp < W_MMA) {
     // =========================== epilogue 2: H2 -> +b2, ReLU -> layer 3 -> logits ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
-    const int r = tid - 384;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CFG::EPI_REGS));
+    const int r = tid - W_EPI2 * 32;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ts = 0;
     for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
@@ -391,14 +399,14 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         }
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MISC_REGS));
-    if (warp == 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CFG::MISC_REGS));
+    if (warp == W_MMA) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(TCM, TC_HID);
       const uint64_t dw1 = tc::make_smem_desc(tc::smem_u32(sm.w1p), B_LBO, SBO);
       const uint64_t dw2 = tc::make_smem_desc(tc::smem_u32(sm.w1p + W1_HALF), B_LBO, SBO);
-      uint32_t ts = 0, xcount[2] = {0, 0};
+      uint32_t ts = 0, xcount[NS] = {};
       for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
         const int nt = tiles_in_pair(pair);
         for (int k = 0; k < K; ++k)
@@ -452,7 +460,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           }
       }
     }
-    } else if (warp == 17) {
+    } else if (warp == W_TMA) {
     // =========================== TMA producer: W2 chunk images ===========================
     if (lane == 0) {
       int64_t tile_steps = 0;
@@ -470,7 +478,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   // ---- teardown
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 16) tc::tmem_dealloc(tmem, 512);
+  if (warp == W_MMA) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace msacl
@@ -495,15 +503,18 @@ extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_a
                                       const msacl_transitions_t* out, double* stats, void* stream) {
   if (!st || !actor || !out || !w1p || !w2p || st->n <= 0 || K <= 0 || n_step <= 0) { set_error("rollout_fused_tc: bad argument"); return MSACL_ERR_BAD_ARG; }
   if ((reinterpret_cast<uintptr_t>(w2p) & 15) || (reinterpret_cast<uintptr_t>(w1p) & 15)) { set_error("rollout_fused_tc: packed weights must be 16-byte aligned"); return MSACL_ERR_BAD_ARG; }
-  const int64_t pairs = ((st->n + TCM - 1) / TCM + 1) / 2;
-  const unsigned grid = (unsigned)(pairs < kNumSMs ? pairs : kNumSMs);
+  const int64_t tiles = (st->n + TCM - 1) / TCM;
   MSACL_DISPATCH_ENV(st->env_id, {
-    const size_t smem = sizeof(TcSmem<ID>) + 128;
-    auto kern = rollout_tc_kernel<ID>;
+    // QuadTracking keeps ~50 state registers per env -> 3 slots; the box envs run 4 slots
+    constexpr int NS = (ID == kQuadTracking) ? 3 : 4;
+    const int64_t groups = (tiles + NS - 1) / NS;
+    const unsigned grid = (unsigned)(groups < kNumSMs ? groups : kNumSMs);
+    const size_t smem = sizeof(TcSmem<ID, NS>) + 128;
+    auto kern = rollout_tc_kernel<ID, NS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("rollout_fused_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
-    kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*st, *actor, (const unsigned char*)w1p, (const unsigned char*)w2p, K,
-                                                          step_base, n_step, reward_scale, cost_scale, eps, deterministic, *out, stats);
+    kern<<<grid, TcCfg<NS>::THREADS, smem, (cudaStream_t)stream>>>(*st, *actor, (const unsigned char*)w1p, (const unsigned char*)w2p, K,
+                                                                  step_base, n_step, reward_scale, cost_scale, eps, deterministic, *out, stats);
   });
   return check_launch("rollout_fused_tc");
 }
