@@ -5,7 +5,7 @@ upstream project; `msacl_b200.py` at the repo root aliases it).
 """
 from .specs import ENV_NAMES, SPECS, get_spec  # noqa: F401
 
-__all__ = ["ENV_NAMES", "SPECS", "get_spec", "create_envs", "create_sampler", "create_buffer", "load_library"]
+__all__ = ["ENV_NAMES", "SPECS", "get_spec", "create_envs", "create_sampler", "create_buffer", "create_alg", "load_library"]
 
 
 def load_library():
@@ -34,3 +34,12 @@ def create_buffer(**kwargs):
     if name not in ("nstep_replay_buffer", "b200_nstep_replay_buffer"):
         raise KeyError(f"No registered buffer with id: {name}")
     return B200NstepReplayBuffer(**kwargs)
+
+
+def create_alg(**kwargs):
+    """Drop-in for RL/create_pkg/create_alg.py:50-79 (algorithm 'msacl')."""
+    from .algorithm import B200MSACL
+    name = kwargs.get("algorithm", "msacl")
+    if name not in ("msacl", "msacl_b200"):
+        raise KeyError(f"No registered algorithm with id: {name}")
+    return B200MSACL(**kwargs)

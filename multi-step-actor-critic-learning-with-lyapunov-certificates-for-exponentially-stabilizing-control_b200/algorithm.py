@@ -1,0 +1,240 @@
+"""MSACL learner on the GPU -- drop-in for `RL.algorithm.msacl` (`ApproxContainer`, `MSACL`).
+
+Same constructor kwargs, same `networks` attribute surface (policy, q1, q2, q1_target, q2_target,
+lyapunov, log_alpha, the five Adam optimisers, `create_action_distributions`), same
+`model_update(data, iteration) -> dict | None` contract and TensorBoard tags
+(RL/algorithm/msacl.py:23-68, 75-164, 174-224).  State-dict keys match the reference
+(`q1.q.0.weight`, `policy.policy.0.weight`, `policy.act_high_lim`, `lyapunov.lya.0.weight`, ...), so
+reference checkpoints (`apprfunc_*.pkl`) load unchanged.
+
+Network forwards/backwards are plain PyTorch (`nn.Linear` -> cuBLAS); everything between the
+network outputs and the scalar losses runs in the kernels of csrc/targets.cu (soft-TD backup,
+Lyapunov risk with analytic backward, stability advantage).  V(obs) is evaluated once per Lyapunov
+update instead of twice (the reference's two forwards at :289 and :317 are identical).
+"""
+import math
+import time
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.optim import Adam
+
+from . import targets as tg
+
+EPS = 1e-6   # RL/utils/act_distribution_cls.py:7
+TB = {"loss_critic": "Loss/Critic loss-RL iter", "loss_lyapunov": "Loss/Lyapunov loss-RL iter",
+      "loss_actor": "Loss/Actor loss-RL iter", "alg_time": "Time/Algorithm time [ms]-RL iter"}   # tensorboard_setup.py:13-40
+_ACT = {"relu": nn.ReLU, "tanh": nn.Tanh, "elu": nn.ELU, "gelu": nn.GELU, "selu": nn.SELU, "sigmoid": nn.Sigmoid, "linear": nn.Identity}
+
+
+def mlp(sizes, activation, output_activation=nn.Identity):
+    """RL/apprfunc/mlp.py:18-33 (same module indices, hence the same state-dict keys)."""
+    layers = []
+    for j in range(len(sizes) - 1):
+        layers += [nn.Linear(sizes[j], sizes[j + 1]), (activation if j < len(sizes) - 2 else output_activation)()]
+    return nn.Sequential(*layers)
+
+
+class TanhGauss:
+    """TanhGaussDistribution (act_distribution_cls.py:30-95) on explicit mean/std tensors."""
+
+    def __init__(self, logits, low, high):
+        self.mean, self.std = torch.chunk(logits, 2, dim=-1)
+        self.half, self.mid = (high - low) / 2, (high + low) / 2
+
+    def _normal_logp(self, u):
+        var = self.std ** 2
+        return (-((u - self.mean) ** 2) / (2 * var) - self.std.log() - math.log(math.sqrt(2 * math.pi))).sum(-1)
+
+    def rsample(self, eps=None):
+        eps = torch.randn_like(self.mean) if eps is None else eps
+        u = self.mean + self.std * eps
+        th = torch.tanh(u)
+        logp = self._normal_logp(u) - torch.log(1 + EPS - th ** 2).sum(-1) - torch.log(self.half).sum(-1)
+        return self.half * th + self.mid, logp
+
+    sample = rsample
+
+    def log_prob(self, act):
+        u = torch.atanh((1 - EPS) * (2 * act - 2 * self.mid) / (2 * self.half))
+        return self._normal_logp(u) - torch.log(self.half * (1 + EPS - torch.tanh(u) ** 2)).sum(-1)
+
+    def mode(self):
+        return self.half * torch.tanh(self.mean) + self.mid
+
+
+class ActionValue(nn.Module):
+    def __init__(self, obs_dim, act_dim, hidden, act):
+        super().__init__()
+        self.q = mlp([obs_dim + act_dim] + list(hidden) + [1], act)
+
+    def forward(self, obs, a):
+        return self.q(torch.cat([obs, a], dim=-1)).squeeze(-1)
+
+
+class LyapunovValue(nn.Module):
+    def __init__(self, obs_dim, hidden, out_dim, act):
+        super().__init__()
+        self.lya = mlp([obs_dim] + list(hidden) + [out_dim], act)
+
+    def forward(self, obs):
+        return (self.lya(obs) ** 2).sum(-1)
+
+
+class StochaPolicy(nn.Module):
+    def __init__(self, obs_dim, act_dim, hidden, act, low, high, min_log_std=-20.0, max_log_std=1.0):
+        super().__init__()
+        self.policy = mlp([obs_dim] + list(hidden) + [2 * act_dim], act)
+        self.min_log_std, self.max_log_std = float(min_log_std), float(max_log_std)
+        self.register_buffer("act_high_lim", torch.as_tensor(np.asarray(high, dtype=np.float32)))
+        self.register_buffer("act_low_lim", torch.as_tensor(np.asarray(low, dtype=np.float32)))
+
+    def forward(self, obs):
+        mean, log_std = torch.chunk(self.policy(obs), 2, dim=-1)
+        return torch.cat((mean, torch.clamp(log_std, self.min_log_std, self.max_log_std).exp()), dim=-1)
+
+
+class ApproxContainer(nn.Module):
+    def __init__(self, **kw):
+        super().__init__()
+        D, A = kw["obs_dim"], kw["act_dim"]
+        va = _ACT[kw.get("value_hidden_activation", "relu")]
+        self.q1 = ActionValue(D, A, kw.get("value_hidden_sizes", [256, 256]), va)
+        self.q2 = ActionValue(D, A, kw.get("value_hidden_sizes", [256, 256]), va)
+        self.q1_target, self.q2_target = deepcopy(self.q1), deepcopy(self.q2)
+        for p in list(self.q1_target.parameters()) + list(self.q2_target.parameters()):
+            p.requires_grad = False
+        self.lyapunov = LyapunovValue(D, kw.get("lyapunov_hidden_sizes", [256, 256]), kw.get("lyapunov_output_dim", 256),
+                                      _ACT[kw.get("lyapunov_hidden_activation", "tanh")])
+        self.policy = StochaPolicy(D, A, kw.get("policy_hidden_sizes", [256, 256]), _ACT[kw.get("policy_hidden_activation", "relu")],
+                                   kw["action_low_limit"], kw["action_high_limit"], kw.get("policy_min_log_std", -20.0),
+                                   kw.get("policy_max_log_std", 1.0))
+        self.log_alpha = nn.Parameter(torch.tensor(1.0, dtype=torch.float32))
+        self.q1_optimizer = Adam(self.q1.parameters(), lr=kw["q_learning_rate"])
+        self.q2_optimizer = Adam(self.q2.parameters(), lr=kw["q_learning_rate"])
+        self.lyapunov_optimizer = Adam(self.lyapunov.parameters(), lr=kw["lyapunov_learning_rate"])
+        self.policy_optimizer = Adam(self.policy.parameters(), lr=kw["policy_learning_rate"])
+        self.alpha_optimizer = Adam([self.log_alpha], lr=kw["alpha_learning_rate"])
+
+    def create_action_distributions(self, logits):
+        return TanhGauss(logits, self.policy.act_low_lim, self.policy.act_high_lim)
+
+
+class B200MSACL:
+    def __init__(self, gamma=0.99, retrace_lambda=0.95, lya_eta=0.15, tau=0.005, alpha=math.e, target_entropy=None,
+                 policy_frequency=2, target_network_frequency=1, lya_diff_scale=1.0, lya_zero_scale=1.0,
+                 lya_positive_scale=1.0, device="cuda", **kwargs):
+        self.device = torch.device(device)
+        self.networks = ApproxContainer(**kwargs).to(self.device)
+        self.gamma, self.retrace_lambda, self.lya_eta, self.tau = gamma, retrace_lambda, lya_eta, tau
+        self.policy_frequency, self.target_network_frequency = policy_frequency, target_network_frequency
+        self.n_step = kwargs["n_step"]
+        self.auto_alpha = not kwargs.get("disable_auto_alpha", False)
+        self.set_alpha_bound, self.alpha_bound = kwargs.get("set_alpha_bound", False), kwargs.get("alpha_bound", 2.0)
+        self.networks.log_alpha.data.fill_(math.log(alpha))
+        if target_entropy is None:                                  # msacl.py:126-130
+            target_entropy = -kwargs["act_dim"] - (1 if kwargs.get("env_name") == "QuadTracking" else 0)
+        self.target_entropy = target_entropy
+        self.lya_diff_scale, self.lya_positive_scale = lya_diff_scale, lya_positive_scale
+        self.alpha1, self.alpha2 = kwargs.get("alpha1", 1.0), kwargs.get("alpha2", 2.0)
+        self.clip_coef = kwargs.get("clip_coef", 0.1)
+        self.coef = tg.Coefficients(self.n_step, lya_eta, retrace_lambda, self.alpha1, self.alpha2, device=self.device)
+
+    def _get_alpha(self, requires_grad=False):
+        a = self.networks.log_alpha.exp()
+        return a if requires_grad else a.item()
+
+    # ---- msacl.py:174-224
+    def model_update(self, data, global_iteration, noise=None):
+        """noise: optional iterator of N(0,1) tensors [B, n, A] used by the rsample calls in order
+        (q update, then each policy update) -- parity tests inject the reference's draws."""
+        start = time.time()
+        noise = iter(noise) if noise is not None else None
+        nxt = (lambda: next(noise)) if noise is not None else (lambda: None)
+        data = {k: v.to(self.device, non_blocking=True) for k, v in data.items()}
+        loss_q, q1_mean, q2_mean = self._q_update(data, nxt())
+        if global_iteration % self.target_network_frequency == 0:
+            self._target_update()
+        loss_lya = self._lyapunov_update(data)
+        if global_iteration % self.policy_frequency == 0:
+            for _ in range(self.policy_frequency):
+                loss_policy, entropy = self._policy_update(data, nxt())
+                if self.auto_alpha:
+                    self._alpha_update(entropy)
+            return {"MSACL/entropy-RL iter": entropy.item(), "MSACL/alpha-RL iter": self._get_alpha(),
+                    "MSACL/q1_mean-RL iter": q1_mean.item(), "MSACL/q2_mean-RL iter": q2_mean.item(),
+                    TB["loss_critic"]: loss_q.item(), TB["loss_lyapunov"]: loss_lya.item(), TB["loss_actor"]: loss_policy.item(),
+                    TB["alg_time"]: (time.time() - start) * 1000}
+        return None
+
+    def _q_update(self, d, eps):
+        net = self.networks
+        q1, q2 = net.q1(d["obs"], d["act"]), net.q2(d["obs"], d["act"])
+        with torch.no_grad():
+            dist = net.create_action_distributions(net.policy(d["obs2"]))
+            next_act, next_logp = dist.rsample(eps)
+            backup = tg.q_backup(d["rew"], d["done"], net.q1_target(d["obs2"], next_act), net.q2_target(d["obs2"], next_act),
+                                 next_logp, self.gamma, self._get_alpha())            # csrc/targets.cu
+        loss_q = ((q1 - backup) ** 2).mean() + ((q2 - backup) ** 2).mean()
+        net.q1_optimizer.zero_grad(); net.q2_optimizer.zero_grad()
+        loss_q.backward()
+        net.q1_optimizer.step(); net.q2_optimizer.step()
+        return loss_q.detach(), q1.detach().mean(), q2.detach().mean()
+
+    def _lyapunov_update(self, d):
+        net = self.networks
+        with torch.no_grad():
+            logp = net.create_action_distributions(net.policy(d["obs"])).log_prob(d["act"])
+        loss = tg.lyapunov_risk(d["obs"], d["obs2"], logp, d["logp"], net.lyapunov(d["obs"]), net.lyapunov(d["obs2"]),
+                                self.coef, self.lya_diff_scale, self.lya_positive_scale)       # csrc/targets.cu
+        net.lyapunov_optimizer.zero_grad()
+        loss.backward()
+        net.lyapunov_optimizer.step()
+        return loss.detach()
+
+    def _policy_update(self, d, eps):
+        net = self.networks
+        for p in list(net.q1.parameters()) + list(net.q2.parameters()):
+            p.requires_grad = False
+        dist = net.create_action_distributions(net.policy(d["obs"]))
+        new_act, new_act_logp = dist.rsample(eps)
+        min_q = torch.min(net.q1(d["obs"], new_act), net.q2(d["obs"], new_act))
+        loss_policy_q = (min_q - self._get_alpha() * new_act_logp).mean()
+        new_logp = dist.log_prob(d["act"])
+        with torch.no_grad():
+            start_lya = net.lyapunov(d["obs"][:, 0].contiguous())
+            lya_obs2 = net.lyapunov(d["obs2"])
+        _, adv = tg.stability_advantage(start_lya, lya_obs2, self.coef)                        # csrc/targets.cu
+        loss_policy_lya = tg.clipped_surrogate(new_logp[:, 0], d["logp"][:, 0], adv, self.clip_coef)
+        loss = -loss_policy_q - loss_policy_lya
+        net.policy_optimizer.zero_grad()
+        loss.backward()
+        net.policy_optimizer.step()
+        entropy = -new_act_logp.mean().detach()
+        for p in list(net.q1.parameters()) + list(net.q2.parameters()):
+            p.requires_grad = True
+        return loss.detach(), entropy
+
+    def _alpha_update(self, entropy):
+        net = self.networks
+        loss_alpha = self._get_alpha(True) * (entropy - self.target_entropy)
+        net.alpha_optimizer.zero_grad()
+        loss_alpha.backward()
+        net.alpha_optimizer.step()
+        if self.set_alpha_bound:
+            with torch.no_grad():
+                net.log_alpha.clamp_(max=math.log(self.alpha_bound))
+
+    def _target_update(self):
+        net = self.networks
+        with torch.no_grad():
+            polyak = 1 - self.tau
+            for src, dst in ((net.q1, net.q1_target), (net.q2, net.q2_target)):
+                for p, pt in zip(src.parameters(), dst.parameters()):
+                    pt.data.mul_(polyak)
+                    pt.data.add_((1 - polyak) * p.data)
+
+
+MSACL = B200MSACL

@@ -45,11 +45,29 @@ lyapunov_risk_kernel(int64_t B, int n, int D, const float* __restrict__ obs, con
     const int64_t e = b * n + lane;
     float ratio = 1.f, v1 = 0.f, v2 = 0.f, op = 0.f, op2 = 0.f;
     if (act) {
-      ratio = fminf(fmaxf(expf(logp_new[e] - logp_old[e]), 0.f), 1.f);   // clamp(ratio, 0, 1) :284-285
+      // issue every load of this lane before the first use (memory-level parallelism)
+      const float ln = logp_new[e], lo_ = logp_old[e];
       v1 = lya_obs[e]; v2 = lya_obs2[e];
       const float* o = obs + e * D;
       const float* q = obs2 + e * D;
-      for (int d = 0; d < D; ++d) { op = __fmaf_rn(o[d], o[d], op); op2 = __fmaf_rn(q[d], q[d], op2); }
+      if ((D & 3) == 0) {            // rows are 16-byte aligned: vector loads
+        for (int d = 0; d < D; d += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(o + d);
+          const float4 c = *reinterpret_cast<const float4*>(q + d);
+          op = __fmaf_rn(a.x, a.x, op); op = __fmaf_rn(a.y, a.y, op); op = __fmaf_rn(a.z, a.z, op); op = __fmaf_rn(a.w, a.w, op);
+          op2 = __fmaf_rn(c.x, c.x, op2); op2 = __fmaf_rn(c.y, c.y, op2); op2 = __fmaf_rn(c.z, c.z, op2); op2 = __fmaf_rn(c.w, c.w, op2);
+        }
+      } else if ((D & 1) == 0) {
+        for (int d = 0; d < D; d += 2) {
+          const float2 a = *reinterpret_cast<const float2*>(o + d);
+          const float2 c = *reinterpret_cast<const float2*>(q + d);
+          op = __fmaf_rn(a.x, a.x, op); op = __fmaf_rn(a.y, a.y, op);
+          op2 = __fmaf_rn(c.x, c.x, op2); op2 = __fmaf_rn(c.y, c.y, op2);
+        }
+      } else {
+        for (int d = 0; d < D; ++d) { op = __fmaf_rn(o[d], o[d], op); op2 = __fmaf_rn(q[d], q[d], op2); }
+      }
+      ratio = fminf(fmaxf(expf(ln - lo_), 0.f), 1.f);   // clamp(ratio, 0, 1) :284-285
     }
     // inclusive cumprod over the window (:286)
     float c = ratio;

@@ -130,6 +130,19 @@ window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_fl
   }
 }
 
+// One warp per sampled window; every field of a window is a contiguous run of floats.  With
+// n_step % 4 == 0 (reference default 20) all runs are multiples of 16 bytes and 16-byte aligned,
+// so the copy is done with float4 (else scalar).
+__device__ __forceinline__ void copy_run(float* __restrict__ dst, const float* __restrict__ src, int count, int lane, bool vec) {
+  if (vec) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int e = lane; e < count / 4; e += 32) d4[e] = s4[e];
+  } else {
+    for (int e = lane; e < count; e += 32) dst[e] = src[e];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ring_gather_kernel(msacl_ring_t ring, const int64_t* __restrict__ idx, int64_t B, msacl_ring_t batch) {
   const int lane = threadIdx.x & 31;
@@ -137,17 +150,14 @@ ring_gather_kernel(msacl_ring_t ring, const int64_t* __restrict__ idx, int64_t B
   if (b >= B) return;
   const int64_t s = idx[b];
   const int ns = ring.n_step, D = ring.obs_dim, A = ring.act_dim;
-  for (int e = lane; e < ns * D; e += 32) {
-    batch.obs[b * ns * D + e] = ring.obs[s * ns * D + e];
-    batch.obs2[b * ns * D + e] = ring.obs2[s * ns * D + e];
-  }
-  for (int e = lane; e < ns * A; e += 32) batch.act[b * ns * A + e] = ring.act[s * ns * A + e];
-  for (int e = lane; e < ns; e += 32) {
-    batch.rew[b * ns + e] = ring.rew[s * ns + e];
-    batch.cost[b * ns + e] = ring.cost[s * ns + e];
-    batch.done[b * ns + e] = ring.done[s * ns + e];
-    batch.logp[b * ns + e] = ring.logp[s * ns + e];
-  }
+  const bool vec = (ns & 3) == 0;
+  copy_run(batch.obs + b * ns * D, ring.obs + s * ns * D, ns * D, lane, vec);
+  copy_run(batch.obs2 + b * ns * D, ring.obs2 + s * ns * D, ns * D, lane, vec);
+  copy_run(batch.act + b * ns * A, ring.act + s * ns * A, ns * A, lane, vec);
+  copy_run(batch.rew + b * ns, ring.rew + s * ns, ns, lane, vec);
+  copy_run(batch.cost + b * ns, ring.cost + s * ns, ns, lane, vec);
+  copy_run(batch.done + b * ns, ring.done + s * ns, ns, lane, vec);
+  copy_run(batch.logp + b * ns, ring.logp + s * ns, ns, lane, vec);
 }
 
 }  // namespace msacl

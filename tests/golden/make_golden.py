@@ -327,7 +327,50 @@ def msacl_case(name="TwoLink", B=48, n_step=20, seed=11):
     return out
 
 
+# ------------------------------------------------------------------ D. one full MSACL.model_update
+def msacl_update_case(name="TwoLink", B=32, n_step=20, seed=21):
+    """State dict before, batch, the three rsample noise tensors (q update, two policy updates), the
+    returned tb_info losses and the state dict after `MSACL.model_update(data, 2)`."""
+    from RL.create_pkg.create_alg import create_alg
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    args = base_args(name, 4, n_step)
+    args["replay_batch_size"] = B
+    alg = create_alg(**args)
+    net = alg.networks
+    D, A = args["obs_dim"], args["act_dim"]
+    g = torch.Generator().manual_seed(seed)
+    lo = torch.as_tensor(args["action_low_limit"]); hi = torch.as_tensor(args["action_high_limit"])
+    obs = torch.randn(B, n_step, D, generator=g) * 0.4
+    obs2 = obs + 0.05 * torch.randn(B, n_step, D, generator=g)
+    obs2[: B // 3] *= 0.6
+    act = (lo + (hi - lo) * torch.rand(B, n_step, A, generator=g)).clamp(lo * 0.98, hi * 0.98)
+    data = dict(obs=obs, act=act, rew=-torch.rand(B, n_step, generator=g) * 50, cost=torch.rand(B, n_step, generator=g),
+                obs2=obs2, done=(torch.rand(B, n_step, generator=g) < 0.1).float(), logp=torch.randn(B, n_step, generator=g) - 1.0)
+    out = {"data_" + k: v.numpy().astype(f32) for k, v in data.items()}
+    out.update(act_low=args["action_low_limit"], act_high=args["action_high_limit"])
+    for k, v in net.state_dict().items():
+        out["before_" + k] = v.detach().numpy().copy()
+    st = torch.get_rng_state()
+    for i in range(3):
+        out[f"eps_{i}"] = torch.empty(B, n_step, A).normal_().numpy().astype(f32)
+    torch.set_rng_state(st)
+    tb = alg.model_update(data, 2)
+    for k, v in tb.items():
+        if "time" not in k.lower():
+            out["tb_" + k.replace("/", "_").replace(" ", "_")] = f32(v)
+    out["tb_keys"] = np.array([k for k in tb if "time" not in k.lower()])
+    for k, v in net.state_dict().items():
+        out["after_" + k] = v.detach().numpy().copy()
+    out["state_keys"] = np.array(list(net.state_dict().keys()))
+    return out
+
+
 def main():
+    if "--only-update" in sys.argv:
+        path = os.path.join(HERE, "msacl_update_TwoLink.npz")
+        np.savez_compressed(path, **msacl_update_case())
+        print("wrote", path)
+        return
     rng = np.random.default_rng(20261018)
     for name in ENVS:
         path = os.path.join(HERE, f"env_step_{name}.npz")
@@ -341,6 +384,9 @@ def main():
         print("wrote", path, "windows:", len(data["win_rew"]), "dones:", int(data["step_done"].sum()))
     path = os.path.join(HERE, "msacl_targets_TwoLink.npz")
     np.savez_compressed(path, **msacl_case())
+    print("wrote", path)
+    path = os.path.join(HERE, "msacl_update_TwoLink.npz")
+    np.savez_compressed(path, **msacl_update_case())
     print("wrote", path)
 
 
