@@ -1,0 +1,58 @@
+"""Greedy policy evaluation on the fused rollout kernel -- drop-in for `Evaluator.run_parallel_episodes`
+(RL/trainer/evaluator.py:141-204): `num_eval_episode` env instances are reset and stepped with the
+distribution's mode() action (act_distribution_cls.py:90-95) until every instance has finished its FIRST
+episode; per instance the scaled reward / cost are averaged over the steps of that episode, and the mean
+and (population) std over instances are returned: (TRM, TRS, TCM, TCS).
+"""
+import torch
+
+from .sampler import ActorWeights, FusedRollout
+
+
+class B200Evaluator:
+    def __init__(self, **kwargs):
+        self.env_id = kwargs["env_name"]
+        self.num_eval_episode = int(kwargs["num_eval_episode"])
+        self.reward_scale, self.cost_scale = kwargs["reward_scale"], kwargs["cost_scale"]
+        self.device = torch.device(kwargs.get("device", "cuda"))
+        self.chunk = int(kwargs.get("eval_chunk_steps", 50))
+        self.engine = kwargs.get("rollout_engine", "tc")
+        self.max_step = kwargs.get("max_step")
+        self.networks = kwargs.get("networks")
+        self.seed = int(kwargs.get("eval_env_seed") or 0)
+        self._resets = 0
+
+    def load_state_dict(self, state_dict):
+        self.networks.load_state_dict(state_dict)
+
+    def run_parallel_episodes(self, actor: ActorWeights = None, state_init=None):
+        actor = actor or ActorWeights.from_policy(self.networks.policy, device=self.device)
+        n = self.num_eval_episode
+        ro = FusedRollout(self.env_id, n, self.chunk, n_step=1, reward_scale=self.reward_scale, cost_scale=self.cost_scale,
+                          seed=self.seed, device=self.device, max_step=self.max_step, engine=self.engine)
+        ro.state.episode.fill_(self._resets)          # envs.reset(seed=None): a fresh set of initial states per call
+        self._resets += 1
+        ro.state.reset()
+        if state_init is not None:
+            state_init(ro.state)
+        finished = torch.zeros(n, dtype=torch.bool, device=self.device)
+        ret_sum = torch.zeros(n, dtype=torch.float64, device=self.device)
+        cost_sum, count = torch.zeros_like(ret_sum), torch.zeros_like(ret_sum)
+        limit = (self.max_step or ro.spec.max_step) + self.chunk
+        steps = 0
+        while not bool(finished.all()) and steps < limit:
+            ro.run(actor, deterministic=True)
+            tr = ro.tr
+            done = tr.done[tr.H:].bool()
+            cum = torch.cumsum(done.to(torch.int32), dim=0)
+            mask = (~finished)[None, :] & ((cum - done.to(torch.int32)) == 0)     # steps up to and incl. the first done
+            ret_sum += (tr.rew[tr.H:].double() * mask).sum(0)
+            cost_sum += (tr.cost[tr.H:].double() * mask).sum(0)
+            count += mask.sum(0)
+            finished |= cum[-1] > 0
+            steps += self.chunk
+        ep_ret, ep_cost = ret_sum / count, cost_sum / count
+        return (float(ep_ret.mean()), float(ep_ret.std(unbiased=False)), float(ep_cost.mean()), float(ep_cost.std(unbiased=False)))
+
+    def run_evaluation(self, iteration=0):
+        return self.run_parallel_episodes()
