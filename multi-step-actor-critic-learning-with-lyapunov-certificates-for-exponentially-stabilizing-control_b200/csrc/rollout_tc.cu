@@ -67,12 +67,18 @@ struct TcSmem {
   alignas(128) unsigned char astage[TcCfg<NS>::NA][2 * A_HALF];
   alignas(128) unsigned char w1p[W1P_BYTES];
   alignas(128) unsigned char xop[NS][2 * X_HALF];
-  alignas(16) float w3[8 * TC_HID];
+  alignas(16) float w3t[TC_HID * 8];       // layer-3 weights transposed: [unit n][output j] (zero padded to 8)
   alignas(16) float b2[TC_HID];
   alignas(16) float b3[8];
   alignas(16) float logits[NS][2 * Env<ID>::A * TCM];
   TcBars bars;
 };
+
+// packed FP32 FMA (FFMA2): two IEEE fma.rn per instruction; pack2(a, a) folds into the scalar-broadcast operand form
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {   // {hi:lo} packed, RNE
   uint32_t r;
@@ -145,7 +151,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
 
   // ---- one-time setup
   for (int i = tid; i < W1P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm.w1p)[i] = reinterpret_cast<const uint4*>(w1p_g)[i];
-  for (int i = tid; i < 8 * TC_HID; i += TC_THREADS) sm.w3[i] = i < A2 * TC_HID ? actor.w3[i] : 0.f;
+  for (int i = tid; i < 8 * TC_HID; i += TC_THREADS) { const int n = i >> 3, j = i & 7; sm.w3t[i] = j < A2 ? actor.w3[j * TC_HID + n] : 0.f; }
   for (int i = tid; i < TC_HID; i += TC_THREADS) sm.b2[i] = actor.b2[i];
   if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
   if (tid == 0) {
@@ -367,9 +373,10 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           tc::tc_fence_after();
           if (r == 0) TC_ACC(11, t_a);                // epi2: wait for H2
           TC_T0(t_b);
-          float acc[A2];
+          constexpr int NP = (A2 + 1) / 2;          // logit pairs (j, j+1) accumulated with packed FFMA2
+          u64 acc[NP];
 #pragma unroll
-          for (int j = 0; j < A2; ++j) acc[j] = sm.b3[j];
+          for (int q = 0; q < NP; ++q) acc[q] = pack2(sm.b3[2 * q], sm.b3[2 * q + 1]);
           for (int cb = 0; cb < TC_HID / 32; ++cb) {
             uint32_t v[32];
             tc::tmem_ld32(tmem_h2 + lane_addr + (uint32_t)(cb * 32), v);
@@ -378,22 +385,32 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cb * 32 + 4 * q]);
-              const float h0 = fmaxf(__uint_as_float(v[4 * q + 0]) + bb.x, 0.f);
-              const float h1 = fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f);
-              const float h2 = fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f);
-              const float h3 = fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f);
+              const float hv[4] = {fmaxf(__uint_as_float(v[4 * q + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f),
+                                   fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f)};
 #pragma unroll
-              for (int j = 0; j < A2; ++j) {
-                const float4 w = *reinterpret_cast<const float4*>(&sm.w3[j * TC_HID + cb * 32 + 4 * q]);
-                acc[j] = __fmaf_rn(h0, w.x, acc[j]);
-                acc[j] = __fmaf_rn(h1, w.y, acc[j]);
-                acc[j] = __fmaf_rn(h2, w.z, acc[j]);
-                acc[j] = __fmaf_rn(h3, w.w, acc[j]);
+              for (int c = 0; c < 4; ++c) {
+                const float* wrow = &sm.w3t[(cb * 32 + 4 * q + c) * 8];      // all lanes read the same address: broadcast
+                const u64 hh = pack2(hv[c], hv[c]);
+                if constexpr (NP >= 1) {
+                  const float4 w0 = *reinterpret_cast<const float4*>(wrow);
+                  acc[0] = fma2(hh, pack2(w0.x, w0.y), acc[0]);
+                  if constexpr (NP >= 2) acc[1] = fma2(hh, pack2(w0.z, w0.w), acc[1]);
+                }
+                if constexpr (NP >= 3) {
+                  const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
+                  acc[2] = fma2(hh, pack2(w1.x, w1.y), acc[2]);
+                  if constexpr (NP >= 4) acc[3] = fma2(hh, pack2(w1.z, w1.w), acc[3]);
+                }
               }
             }
           }
 #pragma unroll
-          for (int j = 0; j < A2; ++j) sm.logits[s][j * TCM + r] = acc[j];
+          for (int q = 0; q < NP; ++q) {
+            float lo, hi;
+            unpack2(acc[q], lo, hi);
+            sm.logits[s][(2 * q) * TCM + r] = lo;
+            if (2 * q + 1 < A2) sm.logits[s][(2 * q + 1) * TCM + r] = hi;
+          }
           tc::mbar_arrive(&sm.bars.logits[s]);
           if (r == 0) TC_ACC(12, t_b);                // epi2: compute
         }
