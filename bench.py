@@ -285,6 +285,10 @@ def main():
     bytes_per_step = transition_bytes(D, A)
     state_bytes = 2 * (4 * spec.sf_rows + 8 * spec.sd_rows + 20)      # read + write once per launch
     hbm_gbs = (bytes_per_step * n * K + state_bytes * n) / (kern_ms * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel: ncu --set full capture of this kernel (profiles/r1_tc_rollout_summary.md,
+    # profiles/r1_v3_rollout_fused_summary.md: dram read+write = 325 MB / 323 MB for 2^21 env-steps) -> bytes per env-step
+    ncu_traffic_per_env_step = {"tc": 155.0, "ffma": 154.0}[args.engine] if args.env == "QuadTracking" else None
+    traffic = None if ncu_traffic_per_env_step is None else ncu_traffic_per_env_step * n * K
     tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     tensor_burst = float(peaks.get("bf16_tflops", 1590.0))
     hbm_info = {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
@@ -292,7 +296,7 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
     if args.engine == "ffma":
         roofline = {"bound": "fp32_ffma", "achieved": achieved_tflops, "peak": ffma_peak, "unit": "TFLOP/s",
-                    "frac": achieved_tflops / ffma_peak, "traffic": None,
+                    "frac": achieved_tflops / ffma_peak, "traffic": traffic,
                     "peak_source": "measured in this run: msacl_ffma_probe (8 independent FFMA chains/thread, 2x256 threads/SM); "
                                    "MEASURED_PEAKS.json has no FP32 figure (theoretical 148*128*2*1.965 GHz = 74.4)",
                     "register_tiled_sgemm_ceiling_tflops": ffma_outer, "register_tiled_ffma2_ceiling_tflops": ffma2_outer,
@@ -302,7 +306,8 @@ def main():
         # tensor path: algorithmic FLOPs (one FP32-equivalent pass) against the measured dense bf16 peak; the
         # split-bf16 scheme issues 3 UMMAs per algorithmic product, so tensor-pipe utilisation is ~3x `frac`.
         roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": achieved_tflops / tensor_peak, "traffic": None,
+                    "frac": achieved_tflops / tensor_peak, "traffic": traffic,
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel, scaled per env-step from the profiled launch",
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
                                     else "fallback 1.4 PFLOP/s sustained"),
                     "peak_burst": tensor_burst, "tensor_issue_factor": 3,

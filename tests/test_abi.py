@@ -60,3 +60,18 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(Exception):
         msacl_b200.create_envs(env_name="VanderPol", env_num=4, env_seed=0)
+
+
+def test_error_codes_without_gpu_work():
+    """Argument validation happens on the host before any launch (no C++ exceptions across the ABI)."""
+    import ctypes as C
+    lib = msacl_b200.load_library()
+    st = _lib.EnvState(env_id=0, max_step=1000, n=0, stride=0)
+    assert lib.msacl_env_reset(C.byref(st), None) == -2 and b"invalid env state" in lib.msacl_last_error()
+    assert lib.msacl_env_step(C.byref(st), None, None, None, None, None, None, None) == -2
+    assert lib.msacl_q_backup(0, None, None, None, None, None, 0.99, 0.2, None, None) == -2
+    assert lib.msacl_lyapunov_risk(4, 33, 2, *([None] * 9), 1.0, 2.0, 10.0, 1.0, *([None] * 5), None) == -2
+    assert b"n_step must be <= 32" in lib.msacl_last_error()
+    assert lib.msacl_action_noise(0, 0, 8, 5, 0, None, None) == -2
+    n1, n2 = C.c_int64(0), C.c_int64(0)
+    assert lib.msacl_tc_pack_bytes(C.byref(n1), C.byref(n2)) == 0 and (n1.value, n2.value) == (16384, 262144)

@@ -178,3 +178,50 @@ def test_deterministic_mode_is_tanh_mean():
     mean, _ = oactor.policy_forward(w, obs)
     want = np.clip(oactor.tanh_gauss_mode(mean, spec.act_low, spec.act_high), spec.act_low, spec.act_high)
     np.testing.assert_allclose(ro.tr.act[ro.tr.H].cpu().numpy(), want, rtol=0, atol=1e-3)
+
+
+@pytest.mark.parametrize("engine", ["ffma", "tc"])
+@pytest.mark.parametrize("name", ["Pendulum", "QuadTracking"])
+def test_sharding_invariance_bit_exact(name, engine):
+    """Multi-GPU contract: env ids are sharded by rank, RNG is keyed by the GLOBAL env id and
+    there is no cross-env coupling, so one shard of n envs and two shards of n/2 give bit-identical transitions."""
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    n, K, seed = 3000, 5, 17
+    spec = oenv.SPECS[name]
+    aw = ActorWeights(oactor.init_policy_weights(spec.obs_dim, spec.act_dim, seed=4))
+    whole = FusedRollout(name, n, K, n_step=3, seed=seed, env_base=0, engine=engine, max_step=4)
+    whole.state.reset(); whole.run(aw)
+    parts = []
+    for lo, hi in ((0, 1777), (1777, n)):
+        ro = FusedRollout(name, hi - lo, K, n_step=3, seed=seed, env_base=lo, engine=engine, max_step=4)
+        ro.state.reset(); ro.run(aw)
+        parts.append(ro)
+    for k, v in whole.tr.fields().items():
+        cat = torch.cat([p.tr.fields()[k][p.tr.H:] for p in parts], dim=1)
+        assert torch.equal(v[whole.tr.H:], cat), k
+    assert torch.equal(whole.state.sf, torch.cat([p.state.sf for p in parts], dim=1))
+    assert torch.equal(whole.state.episode, torch.cat([p.state.episode for p in parts]))
+    assert float(whole.stats[0]) == sum(float(p.stats[0]) for p in parts) > 0
+
+
+@pytest.mark.parametrize("engine", ["ffma", "tc"])
+def test_full_size_invariants_quad(engine):
+    """BASELINE config-5 per-GPU size (2^21 QuadTracking envs): size-independent properties of a K=3 chunk."""
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    n, K = 1 << 21, 3
+    spec = oenv.SPECS["QuadTracking"]
+    aw = ActorWeights(oactor.init_policy_weights(spec.obs_dim, spec.act_dim, seed=0))
+    ro = FusedRollout("QuadTracking", n, K, n_step=2, seed=1, engine=engine)
+    ro.state.reset(); ro.run(aw)
+    f = {k: v[ro.tr.H:] for k, v in ro.tr.fields().items()}
+    for k in ("obs", "act", "rew", "cost", "obs2", "logp"):
+        assert bool(torch.isfinite(f[k]).all()), k
+    lo, hi = torch.as_tensor(spec.act_low).cuda(), torch.as_tensor(spec.act_high).cuda()
+    assert bool(((f["act"] >= lo) & (f["act"] <= hi)).all())
+    cont = ~f["done"][:-1].bool()
+    assert torch.equal(f["obs"][1:][cont], f["obs2"][:-1][cont])            # next step starts from real_next_obs unless reset
+    assert bool((f["cost"] >= 0).all()) and bool((f["rew"] <= 1000.0 + 1e-3).all())
+    # cost = 100 * |obs2|^2 (rew_plus_cost.py:20-21) recomputed with torch
+    np.testing.assert_allclose(f["cost"][0, :4096].cpu().numpy(), (100.0 * (f["obs2"][0, :4096] ** 2).sum(-1)).cpu().numpy(), rtol=1e-5)
+    assert torch.equal(f["emit"][0], torch.zeros_like(f["emit"][0])) and int(f["emit"][1].sum()) == n - int(f["done"][0].sum())
+    assert torch.equal(ro.state.step.cpu(), torch.full((n,), K, dtype=torch.int32)) or int(f["done"].sum()) > 0
