@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-fmad=false",            # dynamics must round like NumPy scalar math; GEMMs call __fmaf_rn explicitly
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
     "-shared",
-] + (["-DMSACL_TC_TIMING"] if os.environ.get("MSACL_TC_TIMING") else []) + (["-DMSACL_TC_SKIP_ENV"] if os.environ.get("MSACL_TC_SKIP_ENV") else []) + (["-DMSACL_EXP_NODIV"] if os.environ.get("MSACL_EXP_NODIV") else []) + (["-DMSACL_EXP_NOSTATS"] if os.environ.get("MSACL_EXP_NOSTATS") else [])
+] + (["-DMSACL_TC_TIMING"] if os.environ.get("MSACL_TC_TIMING") else [])   # role timers for tools/tc_timing.py
 
 
 def _digest():

@@ -202,21 +202,11 @@ template <> struct Env<kTwoLink> {
       const double b1 = ((double)a[0] - Cq1) - (double)G1;
       const double b2 = ((double)a[1] - Cq2) - (double)G2;
       const double m11 = (double)M11, m12 = (double)M12;
-#ifdef MSACL_EXP_NODIV
-      double r11 = (double)(1.0f / (float)m11); r11 = r11 * (2.0 - m11 * r11); r11 = r11 * (2.0 - m11 * r11);
-      const double l21 = m12 * r11;
-      const double u22 = M22 - l21 * m12;
-      const double y2 = b2 - l21 * b1;
-      double r22 = (double)(1.0f / (float)u22); r22 = r22 * (2.0 - u22 * r22); r22 = r22 * (2.0 - u22 * r22);
-      const double x2 = y2 * r22;
-      const double x1 = (b1 - m12 * x2) * r11;
-#else
       const double l21 = m12 / m11;
       const double u22 = M22 - l21 * m12;
       const double y2 = b2 - l21 * b1;
       const double x2 = y2 / u22;
       const double x1 = (b1 - m12 * x2) / m11;
-#endif
       o[0] = (float)((double)th1 + q1 * kDtD);
       o[1] = (float)((double)th2 + q2 * kDtD);
       o[2] = (float)((double)d1 + x1 * kDtD);

@@ -24,6 +24,8 @@
 
 namespace msacl {
 
+// Role timers for tools/tc_timing.py (build with MSACL_TC_TIMING=1): cycles spent by each warp role waiting on /
+// working between hand-offs, accumulated into stats[5..18].
 #ifdef MSACL_TC_TIMING
 #define TC_T0(var) const long long var = clock64()
 #define TC_ACC(slot, t0) do { if (stats) atomicAdd(&stats[slot], (double)(clock64() - (t0))); } while (0)
@@ -252,11 +254,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
             act[j] = fminf(fmaxf(a_lim, E::act_low(j)), E::act_high(j));
           }
           const float logp = (lp_gauss - lp_tanh) - lp_scale;
-#ifdef MSACL_TC_SKIP_ENV
-          const float rew = act[0];
-#else
           const float rew = E::step(e.sf, e.sd, act);
-#endif
           const bool term = e.out_of_bounds();
           e.step += 1;
           const bool trunc = e.step >= st.max_step;
@@ -377,19 +375,19 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           u64 acc[NP];
 #pragma unroll
           for (int q = 0; q < NP; ++q) acc[q] = pack2(sm.b3[2 * q], sm.b3[2 * q + 1]);
-          for (int cb = 0; cb < TC_HID / 32; ++cb) {
-            uint32_t v[32];
-            tc::tmem_ld32(tmem_h2 + lane_addr + (uint32_t)(cb * 32), v);
+          for (int cb = 0; cb < TC_HID / 16; ++cb) {      // 16 columns per TMEM load: leaves registers to prefetch W3 rows
+            uint32_t v[16];
+            tc::tmem_ld16(tmem_h2 + lane_addr + (uint32_t)(cb * 16), v);
             tc::tmem_ld_wait();
-            if (cb == TC_HID / 32 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h2free); }
+            if (cb == TC_HID / 16 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h2free); }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cb * 32 + 4 * q]);
+            for (int q = 0; q < 4; ++q) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cb * 16 + 4 * q]);
               const float hv[4] = {fmaxf(__uint_as_float(v[4 * q + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f),
                                    fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f)};
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const float* wrow = &sm.w3t[(cb * 32 + 4 * q + c) * 8];      // all lanes read the same address: broadcast
+                const float* wrow = &sm.w3t[(cb * 16 + 4 * q + c) * 8];      // all lanes read the same address: broadcast
                 const u64 hh = pack2(hv[c], hv[c]);
                 if constexpr (NP >= 1) {
                   const float4 w0 = *reinterpret_cast<const float4*>(wrow);

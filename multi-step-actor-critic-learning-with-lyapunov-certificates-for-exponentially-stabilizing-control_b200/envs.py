@@ -120,8 +120,8 @@ class B200VectorEnv:
         st = self.state
         if seed is not None:
             st.desc.seed = int(seed) & (2 ** 64 - 1)
-        # every reset() call starts a fresh block of episodes so repeated resets differ
-        st.episode.add_(1) if self._resets else None
+        if self._resets:          # every reset() call starts a fresh block of episodes so repeated resets differ
+            st.episode.add_(1)
         self._resets += 1
         st.reset()
         return st.obs.cpu().numpy(), {}
