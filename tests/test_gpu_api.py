@@ -141,3 +141,24 @@ def test_noise_params_rejected():
     with pytest.raises(RuntimeError):
         msacl_b200.create_sampler(env_name="VanderPol", env_num=4, sample_batch_size=2, reward_scale=1.0, cost_scale=1.0,
                                   noise_params={"std": 0.1}, n_step=2)
+
+
+@pytest.mark.parametrize("engine", ["tc", "ffma"])
+def test_reference_default_config_sizes(engine):
+    """BASELINE config 1 sizes (example/msacl_train.py defaults): env_num=4, sample_batch_size=20, n_step=20."""
+    import msacl_b200
+    kw = dict(env_name="VanderPol", env_num=4, env_seed=1, sample_batch_size=20, action_type="continu", reward_scale=100.0,
+              cost_scale=100.0, noise_params=None, target_value=0.0, n_step=20, gamma=0.99, retrace_lambda=0.95,
+              obs_dim=2, act_dim=1, buffer_max_size=1000, rollout_engine=engine)
+    sampler = msacl_b200.create_sampler(**kw)
+    buffer = msacl_b200.create_buffer(**kw)
+    sampler.networks = _Networks(2, 1).cuda()
+    total = 0
+    for it in range(4):
+        data, _ = sampler.sample()
+        total += len(data)
+        buffer.add_batch(data)
+    assert sampler.get_total_sample_number() == 4 * 80
+    assert buffer.size == total and 0 < total <= 4 * 80 - 4 * 19
+    b = buffer.sample_batch(256)
+    assert b["obs"].shape == (256, 20, 2) and torch.isfinite(b["rew"]).all()
