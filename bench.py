@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--inner", type=int, default=16, help="env steps per fused launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replay-batch", type=int, default=256)
+    ap.add_argument("--e2e-full-d2h", action="store_true",
+                    help="also time a variant that copies EVERY transition of the chunk to pinned host memory")
     ap.add_argument("--engine", default="tc", choices=["tc", "ffma"],
                     help="actor engine: tcgen05 split-bf16 tensor cores (default) or FP32 FFMA")
     args = ap.parse_args()
@@ -255,6 +257,34 @@ def main():
         e2e_ms = float(tt.item())
     e2e_value = steps_total / (e2e_ms * 1e-3)
 
+    # ---------------- optional: the same step but with every transition of the chunk copied to the host
+    e2e_full = None
+    if args.e2e_full_d2h:
+        tr = ro.tr
+        dev_fields = {k: v[tr.H:] for k, v in tr.fields().items()}
+        host_fields = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in dev_fields.items()}
+        full_bytes = sum(v.numel() * v.element_size() for v in host_fields.values())
+
+        def full_step():
+            a = upload_actor()
+            ro.run(a)
+            for k in host_fields:
+                host_fields[k].copy_(dev_fields[k], non_blocking=True)
+            stream.synchronize()
+
+        for _ in range(2):
+            full_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            full_step()
+        f1.record(stream)
+        barrier()
+        full_ms = f0.elapsed_time(f1)
+        e2e_full = {"value": steps_total / (full_ms * 1e-3), "unit": UNIT, "ms_per_step": full_ms / args.steps,
+                    "d2h_bytes_per_step": full_bytes, "what": "rollout + D2H of all K x n transition records (pinned host memory)"}
+
     # ---------------- roofline of the dominant kernel (rollout_fused_kernel): FP32 FFMA pipe
     flops_per_step = actor_flops(D, A) + DYN_FLOPS[args.env]
     achieved_tflops = flops_per_step * n * K / (kern_ms * 1e-3) / 1e12
@@ -338,6 +368,8 @@ def main():
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        if e2e_full is not None:
+            out["e2e_full_transition_d2h"] = e2e_full
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
