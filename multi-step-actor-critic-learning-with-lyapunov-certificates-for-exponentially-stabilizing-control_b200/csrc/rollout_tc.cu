@@ -7,17 +7,19 @@
 //     x.w ~= x1.w1 + x1.w2 + x2.w1                 (three UMMAs, FP32 accumulation in TMEM)
 // Relative error of a product ~1e-5 (vs 4e-3 for single-pass bf16); tolerances in tests/test_gpu_tc.py.
 //
-// One persistent CTA per SM, 18 warps, two 128-env tiles (slots) in flight:
-//   warps 0-7   env warps: thread = env instance (slot = warp/4), state in registers for all K steps;
-//               sample action, integrate the ODE, reward/cost/autoreset, write the transition, and write
-//               the next observation as the layer-1 A operand (16-wide K block: obs, 1.0 for the bias, 0).
-//   warp 16     MMA issuer (one elected thread): layer 1 = 3 UMMAs (K=16, bias folded in as a K column),
-//               layer 2 = 8 K-chunks x 2 k-steps x 3 UMMAs of 128x256x16, accumulators in TMEM
-//               (H1: columns 0-255, H2: columns 256-511); tcgen05.commit signals mbarriers.
-//   warps 8-11  epilogue 1: TMEM(H1) -> ReLU -> split to bf16 hi/lo -> shared-memory A stages (UMMA
-//               canonical K-major layout, thread = row, 16-byte conflict-free stores).
-//   warp 17     TMA producer: pre-split W2 chunk images (32 KB) global/L2 -> shared ring (cp.async.bulk).
-//   warps 12-15 epilogue 2: TMEM(H2) -> +b2, ReLU -> layer 3 (256 -> 2A) in FP32 FMAs -> logits in smem.
+// One persistent CTA per SM, NS 128-env tiles (slots) in flight, warp-specialised:
+//   env warps (4*NS)  thread = env instance, state in registers for all K steps; sample action, integrate the ODE,
+//                     reward/cost/autoreset, write the next observation as the layer-1 A operand (16-wide K block:
+//                     obs, 1.0 for the bias, 0), then the transition.
+//   MMA warp          one elected thread: layer 1 = 3 UMMAs (K=16, bias folded in as a K column), layer 2 =
+//                     16 k-steps x 3 UMMAs of 128x256x16, accumulators in TMEM (H1: columns 0-255, H2: 256-511);
+//                     with L3TC also layer 3 = 16 k-steps x 3 UMMAs of 128x16x16 whose accumulator re-uses the
+//                     first 16 columns of H2 once epilogue 2 has read them.  tcgen05.commit signals mbarriers.
+//   epilogue 1 (4)    TMEM(H1) -> ReLU -> split to bf16 hi/lo -> shared-memory A stages (UMMA canonical K-major
+//                     layout, thread = row, 16-byte conflict-free stores).
+//   TMA warp          pre-split W2 k-step images (16 KB) global/L2 -> shared ring (cp.async.bulk).
+//   epilogue 2 (4)    L3TC: TMEM(H2) -> +b2, ReLU -> split -> A stages of layer 3, then TMEM(logits) -> +b3 -> smem.
+//                     else: TMEM(H2) -> +b2, ReLU -> layer 3 (256 -> 2A) in packed FP32 FMAs -> logits in smem.
 // All hand-offs are mbarriers (full/empty rings for A and B stages, H1/H2 full/free, X full, logits).
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -34,42 +36,80 @@ namespace msacl {
 #define TC_ACC(slot, t0) do {} while (0)
 #endif
 
+#ifndef MSACL_TC_L3TC
+#define MSACL_TC_L3TC false         // true: layer 3 on the tensor cores too (measured: no gain for QuadTracking, slower for the box envs)
+#endif
+// Debug watchdog (build with MSACL_TC_WATCHDOG=1, tools/tc_watchdog.py): every mbarrier wait gives up after ~1.5 s,
+// the first one to do so records {site, aux, block, parity, thread} in stats[25..29] and raises stats[24]; all other
+// waits then fall through, so a protocol deadlock ends the launch (with garbage results) instead of hanging the GPU.
+#ifdef MSACL_TC_WATCHDOG
+__device__ __forceinline__ void wd_wait(void* bar, uint32_t parity, int site, uint32_t aux, double* stats) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(&stats[24]);
+  while (!tc::mbar_test(bar, parity)) {
+    if ((++spins & 1023u) == 0u) {
+      if (*flag != 0ull) return;
+      if (clock64() - t0 > 3000000000LL) {
+        if (atomicCAS(reinterpret_cast<unsigned long long*>(&stats[24]), 0ull, 0x3FF0000000000000ull) == 0ull) {
+          stats[25] = site; stats[26] = aux; stats[27] = blockIdx.x; stats[28] = parity; stats[29] = threadIdx.x;
+          __threadfence();
+        }
+        return;
+      }
+    }
+  }
+}
+#define TC_WAIT(bar, par, site, aux) wd_wait(bar, par, site, (uint32_t)(aux), stats)
+#else
+#define TC_WAIT(bar, par, site, aux) tc::mbar_wait(bar, par)
+#endif
+
 constexpr int TCM = 128;            // envs per tile
 constexpr int TC_HID = 256;
-constexpr int KC2 = 32;             // K per A/B stage
-constexpr int NCH = TC_HID / KC2;   // 8 chunks per tile-step
-constexpr int NB = 3;               // W2 ring depth
+constexpr int KC2 = 32;             // K per A stage
+constexpr int NCH = TC_HID / KC2;   // 8 A chunks per tile-step
+constexpr int KCB = 16;             // K per W2 stage (one UMMA k-step)
+constexpr int NCHB = TC_HID / KCB;  // 16 W2 stages per tile-step
+constexpr int NB = 4;               // W2 ring depth
+constexpr int NA2 = 2;              // layer-3 A ring depth
 constexpr int A_HALF = TCM * KC2 * 2;       // 8 KB  (a1 or a2 image of a stage)
-constexpr int B_HALF = TC_HID * KC2 * 2;    // 16 KB (b1 or b2 image of a stage)
+constexpr int B_HALF = TC_HID * KCB * 2;    // 8 KB  (b1 or b2 image of a stage)
 constexpr int A_LBO = TCM * 16, B_LBO = TC_HID * 16, SBO = 128;
 constexpr int X_HALF = TCM * 16 * 2;        // 4 KB  (x1 or x2: 128 rows x 16 k)
 constexpr int W1_HALF = TC_HID * 16 * 2;    // 8 KB
+constexpr int N3 = 16;                      // layer-3 UMMA N (2A <= 8 real rows, zero padded)
+constexpr int W3_LBO = N3 * 16;
+constexpr int W3_HALF = N3 * TC_HID * 2;    // 8 KB  (hi or lo image of W3: 16 rows x 256 k)
 // Launch geometry per number of tile slots in flight: NS env warpgroups + epilogue 1 + epilogue 2 +
 // {MMA, TMA, 2 idle warps}.  Registers are rebalanced with setmaxnreg (65536 per SM in total).
 template <int NS> struct TcCfg;
-template <> struct TcCfg<2> { static constexpr int THREADS = 640, ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40, NA = 4; };
-template <> struct TcCfg<3> { static constexpr int THREADS = 768, ENV_REGS = 112, EPI_REGS = 56, MISC_REGS = 32, NA = 4; };   // launch 80: 12*32 <= 8*24 + 4*48
-template <> struct TcCfg<4> { static constexpr int THREADS = 896, ENV_REGS = 88, EPI_REGS = 56, MISC_REGS = 32, NA = 3; };    // launch 72: 16*16 <= 8*16 + 4*40
+// Per warp: launch regs * warps >= sum of the budgets below, or setmaxnreg.inc never returns; and all four warps of a
+// warpgroup must execute the same setmaxnreg (the {MMA, TMA, idle, idle} group shares MISC_REGS).
+template <> struct TcCfg<2> { static constexpr int THREADS = 640, ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40, NA = 4; };   // launch 96*20 = 1920 >= 8*152 + 8*64 + 4*40
+template <> struct TcCfg<3> { static constexpr int THREADS = 768, ENV_REGS = 112, EPI_REGS = 56, MISC_REGS = 32, NA = 3; };   // launch 80*24 = 1920 = 12*112 + 8*56 + 4*32
+template <> struct TcCfg<4> { static constexpr int THREADS = 896, ENV_REGS = 88, EPI_REGS = 56, MISC_REGS = 40, NA = 3; };    // launch 72*28 = 2016 = 16*88 + 8*56 + 4*40
 constexpr int NA_MAX = 4;
-constexpr int W2P_BYTES = NCH * 2 * B_HALF; // 256 KB packed W2 (hi/lo chunk images)
-constexpr int W1P_BYTES = 2 * W1_HALF;
+constexpr int W2P_BYTES = NCHB * 2 * B_HALF;          // 256 KB packed W2 (hi/lo k-step images)
+constexpr int W1P_BYTES = 2 * W1_HALF + 2 * W3_HALF;  // 32 KB: W1|b1 images followed by the W3 images
 
 struct TcBars {
   unsigned long long xfull[4], logits[4];
-  unsigned long long h1full, h1free, h2full, h2free;
-  unsigned long long afull[NA_MAX], afree[NA_MAX], bfull[NB], bfree[NB];
+  unsigned long long h1full, h1free, h2full, h2free, l3full;
+  unsigned long long afull[NA_MAX], afree[NA_MAX], a2full[NA2], a2free[NA2], bfull[NB], bfree[NB];
   uint32_t tmem_slot;
 };
 
-template <int ID, int NS>
+template <int ID, int NS, bool L3TC>
 struct TcSmem {
   using E = Env<ID>;
   static constexpr int A2 = 2 * E::A;
   alignas(128) unsigned char bstage[NB][2 * B_HALF];
   alignas(128) unsigned char astage[TcCfg<NS>::NA][2 * A_HALF];
-  alignas(128) unsigned char w1p[W1P_BYTES];
+  alignas(128) unsigned char a2stage[L3TC ? NA2 : 1][L3TC ? 2 * A_HALF : 128];
+  alignas(128) unsigned char w1p[L3TC ? W1P_BYTES : 2 * W1_HALF];   // W1|b1 images (+ W3 images)
   alignas(128) unsigned char xop[NS][2 * X_HALF];
-  alignas(16) float w3t[TC_HID * 8];       // layer-3 weights transposed: [unit n][output j] (zero padded to 8)
+  alignas(16) float w3t[L3TC ? 8 : TC_HID * 8];   // FP32 layer 3: weights transposed [unit n][output j] (zero padded to 8)
   alignas(16) float b2[TC_HID];
   alignas(16) float b3[8];
   alignas(16) float logits[NS][2 * Env<ID>::A * TCM];
@@ -102,16 +142,17 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 }
 
 // ---- one-time packing of the actor weights into UMMA operand images (device, per weight upload)
-// w1p: [hi|lo] x [2 kb][256 n][8 k] bf16, K index d < D = W1[n][d], K index D = b1[n], rest 0
-// w2p: 8 chunks x [hi|lo] x [4 kb][256 n][8 k] bf16, K-major (B[n][k] = W2[n][k] = w2t[k][n])
-__global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, unsigned char* __restrict__ w1p, unsigned char* __restrict__ w2p) {
+// w1p: [hi|lo] x [2 kb][256 n][8 k] bf16, K index d < D = W1[n][d], K index D = b1[n], rest 0;
+//      followed by W3: [hi|lo] x [32 kb][16 n][8 k] bf16 (rows n >= 2A are zero)
+// w2p: 16 k-steps x [hi|lo] x [2 kb][256 n][8 k] bf16, K-major (B[n][k] = W2[n][k] = w2t[k][n])
+__global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, int A2, unsigned char* __restrict__ w1p, unsigned char* __restrict__ w2p) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  // W2: one thread per (chunk c, kb, n): 8 * 4 * 256 = 8192 threads
-  if (gid < NCH * 4 * TC_HID) {
-    const int n = gid % TC_HID, kb = (gid / TC_HID) % 4, c = gid / (TC_HID * 4);
+  // W2: one thread per (k-step c, kb, n): 16 * 2 * 256 = 8192 threads
+  if (gid < NCHB * 2 * TC_HID) {
+    const int n = gid % TC_HID, kb = (gid / TC_HID) % 2, c = gid / (TC_HID * 2);
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = actor.w2t[(size_t)(c * KC2 + kb * 8 + j) * TC_HID + n];
+    for (int j = 0; j < 8; ++j) v[j] = actor.w2t[(size_t)(c * KCB + kb * 8 + j) * TC_HID + n];
     uint4 hi, lo;
     split8(v, hi, lo);
     unsigned char* base = w2p + (size_t)c * 2 * B_HALF + kb * B_LBO + n * 16;
@@ -133,15 +174,27 @@ __global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, unsigned char* 
     *reinterpret_cast<uint4*>(base) = hi;
     *reinterpret_cast<uint4*>(base + W1_HALF) = lo;
   }
+  // W3: one thread per (kb, n): 32 * 16 = 512 threads
+  if (gid < (TC_HID / 8) * N3) {
+    const int n = gid % N3, kb = gid / N3;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = n < A2 ? actor.w3[n * TC_HID + kb * 8 + j] : 0.f;
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    unsigned char* base = w1p + 2 * W1_HALF + kb * W3_LBO + n * 16;
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + W3_HALF) = lo;
+  }
 }
 
-template <int ID, int NS>
+template <int ID, int NS, bool L3TC>
 __global__ void __launch_bounds__(TcCfg<NS>::THREADS, 1)
 rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char* __restrict__ w1p_g,
                   const unsigned char* __restrict__ w2p_g, int K, uint32_t step_base, int n_step, float reward_scale,
                   float cost_scale, const float* __restrict__ eps, int deterministic, msacl_transitions_t out, double* stats) {
   using E = Env<ID>;
-  using S = TcSmem<ID, NS>;
+  using S = TcSmem<ID, NS, L3TC>;
   using CFG = TcCfg<NS>;
   constexpr int D = E::D, A = E::A, A2 = 2 * A;
   constexpr int TC_THREADS = CFG::THREADS, NA = CFG::NA;
@@ -152,14 +205,18 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // ---- one-time setup
-  for (int i = tid; i < W1P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm.w1p)[i] = reinterpret_cast<const uint4*>(w1p_g)[i];
-  for (int i = tid; i < 8 * TC_HID; i += TC_THREADS) { const int n = i >> 3, j = i & 7; sm.w3t[i] = j < A2 ? actor.w3[j * TC_HID + n] : 0.f; }
+  for (int i = tid; i < (int)sizeof(sm.w1p) / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm.w1p)[i] = reinterpret_cast<const uint4*>(w1p_g)[i];
+  if constexpr (!L3TC) {
+    for (int i = tid; i < 8 * TC_HID; i += TC_THREADS) { const int n = i >> 3, j = i & 7; sm.w3t[i] = j < A2 ? actor.w3[j * TC_HID + n] : 0.f; }
+  }
   for (int i = tid; i < TC_HID; i += TC_THREADS) sm.b2[i] = actor.b2[i];
   if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
   if (tid == 0) {
     TcBars& b = sm.bars;
     for (int s = 0; s < NS; ++s) { tc::mbar_init(&b.xfull[s], TCM); tc::mbar_init(&b.logits[s], TCM); }
     tc::mbar_init(&b.h1full, 1); tc::mbar_init(&b.h1free, TCM); tc::mbar_init(&b.h2full, 1); tc::mbar_init(&b.h2free, TCM);
+    tc::mbar_init(&b.l3full, 1);
+    for (int i = 0; i < NA2; ++i) { tc::mbar_init(&b.a2full[i], TCM); tc::mbar_init(&b.a2free[i], 1); }
     for (int i = 0; i < NA; ++i) { tc::mbar_init(&b.afull[i], TCM); tc::mbar_init(&b.afree[i], 1); }
     for (int i = 0; i < NB; ++i) { tc::mbar_init(&b.bfull[i], 1); tc::mbar_init(&b.bfree[i], 1); }
     tc::mbar_fence_init();
@@ -212,7 +269,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
 #ifdef MSACL_TC_TIMING
         const long long t_w0 = clock64();
 #endif
-        tc::mbar_wait(&sm.bars.logits[s], lcount & 1);
+        TC_WAIT(&sm.bars.logits[s], lcount & 1, 1, lcount);
         ++lcount;
 #ifdef MSACL_TC_TIMING
         const long long t_w1 = clock64();
@@ -326,14 +383,14 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       for (int k = 0; k < K; ++k)
         for (int s = 0; s < nt; ++s, ++ts) {
           TC_T0(t_a);
-          tc::mbar_wait(&sm.bars.h1full, ts & 1);
+          TC_WAIT(&sm.bars.h1full, ts & 1, 2, ts);
           tc::tc_fence_after();
           if (r == 0) TC_ACC(8, t_a);                 // epi1: wait for H1
           TC_T0(t_b);
           for (int c = 0; c < NCH; ++c) {
             const uint32_t ai = ts * NCH + c, stg = ai % NA;
             TC_T0(t_c);
-            if (ai >= NA) tc::mbar_wait(&sm.bars.afree[stg], ((ai / NA) - 1) & 1);
+            if (ai >= NA) TC_WAIT(&sm.bars.afree[stg], ((ai / NA) - 1) & 1, 3, ai);
             if (r == 0) TC_ACC(10, t_c);              // epi1: wait for a free A stage
             uint32_t v[32];
             tc::tmem_ld32(tmem_h1 + lane_addr + (uint32_t)(c * 32), v);
@@ -367,10 +424,50 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       for (int k = 0; k < K; ++k)
         for (int s = 0; s < nt; ++s, ++ts) {
           TC_T0(t_a);
-          tc::mbar_wait(&sm.bars.h2full, ts & 1);
+          TC_WAIT(&sm.bars.h2full, ts & 1, 4, ts);
           tc::tc_fence_after();
           if (r == 0) TC_ACC(11, t_a);                // epi2: wait for H2
           TC_T0(t_b);
+          if constexpr (L3TC) {
+            // H2 -> +b2, ReLU -> bf16 hi/lo -> layer-3 A stages; the logits come back through TMEM
+            for (int c = 0; c < NCH; ++c) {
+              const uint32_t ai = ts * NCH + c, stg = ai % NA2;
+              TC_T0(t_c);
+              if (ai >= NA2) TC_WAIT(&sm.bars.a2free[stg], ((ai / NA2) - 1) & 1, 5, ai);
+              if (r == 0) TC_ACC(20, t_c);            // epi2: wait for a free layer-3 A stage
+              uint32_t v[32];
+              tc::tmem_ld32(tmem_h2 + lane_addr + (uint32_t)(c * 32), v);
+              tc::tmem_ld_wait();
+              unsigned char* base = sm.a2stage[stg] + r * 16;
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&sm.b2[c * 32 + kb * 8]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&sm.b2[c * 32 + kb * 8 + 4]);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = fmaxf(__uint_as_float(v[kb * 8 + j]) + bb[j], 0.f);
+                uint4 hi, lo;
+                split8(w, hi, lo);
+                *reinterpret_cast<uint4*>(base + kb * A_LBO) = hi;
+                *reinterpret_cast<uint4*>(base + A_HALF + kb * A_LBO) = lo;
+              }
+              tc::fence_async_smem();
+              tc::tc_fence_before();     // chunk 0: the layer-3 accumulator overwrites H2 columns 0-15 after this arrive
+              tc::mbar_arrive(&sm.bars.a2full[stg]);
+            }
+            TC_T0(t_l);
+            TC_WAIT(&sm.bars.l3full, ts & 1, 6, ts);
+            tc::tc_fence_after();
+            if (r == 0) TC_ACC(21, t_l);              // epi2: wait for the layer-3 UMMAs
+            uint32_t lg[8];
+            tc::tmem_ld8(tmem_h2 + lane_addr, lg);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&sm.bars.h2free);
+#pragma unroll
+            for (int j = 0; j < A2; ++j) sm.logits[s][j * TCM + r] = __uint_as_float(lg[j]) + sm.b3[j];
+          } else {
           constexpr int NP = (A2 + 1) / 2;          // logit pairs (j, j+1) accumulated with packed FFMA2
           u64 acc[NP];
 #pragma unroll
@@ -409,66 +506,113 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
             sm.logits[s][(2 * q) * TCM + r] = lo;
             if (2 * q + 1 < A2) sm.logits[s][(2 * q + 1) * TCM + r] = hi;
           }
+          }
           tc::mbar_arrive(&sm.bars.logits[s]);
           if (r == 0) TC_ACC(12, t_b);                // epi2: compute
         }
     }
   } else {
+    // (setmaxnreg must be executed with the same value by all four warps of a warpgroup)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CFG::MISC_REGS));
     if (warp == W_MMA) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(TCM, TC_HID);
-      const uint64_t dw1 = tc::make_smem_desc(tc::smem_u32(sm.w1p), B_LBO, SBO);
-      const uint64_t dw2 = tc::make_smem_desc(tc::smem_u32(sm.w1p + W1_HALF), B_LBO, SBO);
-      uint32_t ts = 0, xcount[NS] = {};
-      for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+      const uint32_t idesc3 = tc::make_idesc_bf16(TCM, N3);
+      const uint32_t w1base = tc::smem_u32(sm.w1p), w3base = w1base + 2 * W1_HALF;
+      // layer 1 of tile-step `t1` (slot s, xn = number of X operands that slot has produced before):
+      // H1 = [obs | 1 | 0] . [W1 | b1 | 0]^T  (K = 16, three products)
+      auto issue_l1 = [&](int s, uint32_t xn, uint32_t t1) {
+        TC_T0(t_x);
+        TC_WAIT(&sm.bars.xfull[s], xn & 1, 7, t1);
+        TC_ACC(13, t_x);                              // MMA: wait for X
+        TC_T0(t_h);
+        if (t1 > 0) TC_WAIT(&sm.bars.h1free, (t1 - 1) & 1, 8, t1);
+        TC_ACC(14, t_h);                              // MMA: wait for H1 free
+        tc::tc_fence_after();
+        const uint64_t dw1 = tc::make_smem_desc(w1base, B_LBO, SBO);
+        const uint64_t dw2 = tc::make_smem_desc(w1base + W1_HALF, B_LBO, SBO);
+        const uint64_t dx1 = tc::make_smem_desc(tc::smem_u32(sm.xop[s]), A_LBO, SBO);
+        const uint64_t dx2 = tc::make_smem_desc(tc::smem_u32(sm.xop[s] + X_HALF), A_LBO, SBO);
+        tc::umma_bf16(tmem_h1, dx1, dw1, idesc, 0u);
+        tc::umma_bf16(tmem_h1, dx1, dw2, idesc, 1u);
+        tc::umma_bf16(tmem_h1, dx2, dw1, idesc, 1u);
+        tc::umma_commit(&sm.bars.h1full);
+      };
+      uint32_t ts = 0, pi = 0;                        // tile-step counter, local group counter
+      for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++pi) {
         const int nt = tiles_in_pair(pair);
         for (int k = 0; k < K; ++k)
           for (int s = 0; s < nt; ++s, ++ts) {
-            // ---- layer 1: H1 = [obs | 1 | 0] . [W1 | b1 | 0]^T  (K = 16, three products)
-            TC_T0(t_x);
-            tc::mbar_wait(&sm.bars.xfull[s], xcount[s] & 1);
-            ++xcount[s];
-            TC_ACC(13, t_x);                          // MMA: wait for X
-            TC_T0(t_h);
-            if (ts > 0) tc::mbar_wait(&sm.bars.h1free, (ts - 1) & 1);
-            TC_ACC(14, t_h);                          // MMA: wait for H1 free
-            tc::tc_fence_after();
-            const uint64_t dx1 = tc::make_smem_desc(tc::smem_u32(sm.xop[s]), A_LBO, SBO);
-            const uint64_t dx2 = tc::make_smem_desc(tc::smem_u32(sm.xop[s] + X_HALF), A_LBO, SBO);
-            tc::umma_bf16(tmem_h1, dx1, dw1, idesc, 0u);
-            tc::umma_bf16(tmem_h1, dx1, dw2, idesc, 1u);
-            tc::umma_bf16(tmem_h1, dx2, dw1, idesc, 1u);
-            tc::umma_commit(&sm.bars.h1full);
-            // ---- layer 2: H2 = relu(H1) . W2^T over 8 K-chunks of 32
+            if (ts == 0) issue_l1(0, 0u, 0u);
+            // ---- layer 2: H2 = relu(H1) . W2^T over 8 A chunks x 2 k-steps
+#pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
-              const uint32_t ai = ts * NCH + c, as = ai % NA, bs = ai % NB;
+              const uint32_t ai = ts * NCH + c, as = ai % NA;
               TC_T0(t_1);
-              tc::mbar_wait(&sm.bars.afull[as], (ai / NA) & 1);
+              TC_WAIT(&sm.bars.afull[as], (ai / NA) & 1, 9, ai);
               TC_ACC(15, t_1);                        // MMA: wait for A chunk
-              TC_T0(t_2);
-              tc::mbar_wait(&sm.bars.bfull[bs], (ai / NB) & 1);
-              TC_ACC(16, t_2);                        // MMA: wait for B chunk
               TC_T0(t_3);
-              if (c == 0 && ts > 0) tc::mbar_wait(&sm.bars.h2free, (ts - 1) & 1);
+              if (c == 0 && ts > 0) TC_WAIT(&sm.bars.h2free, (ts - 1) & 1, 10, ts);
               TC_ACC(17, t_3);                        // MMA: wait for H2 free
-              tc::tc_fence_after();
-              const uint32_t abase = tc::smem_u32(sm.astage[as]), bbase = tc::smem_u32(sm.bstage[bs]);
+              const uint32_t abase = tc::smem_u32(sm.astage[as]);
 #pragma unroll
-              for (int j = 0; j < KC2 / 16; ++j) {
+              for (int j = 0; j < KC2 / KCB; ++j) {
+                const uint32_t bi = ai * (KC2 / KCB) + j, bs = bi % NB;
+                TC_T0(t_2);
+                TC_WAIT(&sm.bars.bfull[bs], (bi / NB) & 1, 11, bi);
+                TC_ACC(16, t_2);                      // MMA: wait for B stage
+                tc::tc_fence_after();
+                const uint32_t bbase = tc::smem_u32(sm.bstage[bs]);
                 const uint64_t da1 = tc::make_smem_desc(abase + j * 2 * A_LBO, A_LBO, SBO);
                 const uint64_t da2 = tc::make_smem_desc(abase + A_HALF + j * 2 * A_LBO, A_LBO, SBO);
-                const uint64_t db1 = tc::make_smem_desc(bbase + j * 2 * B_LBO, B_LBO, SBO);
-                const uint64_t db2 = tc::make_smem_desc(bbase + B_HALF + j * 2 * B_LBO, B_LBO, SBO);
+                const uint64_t db1 = tc::make_smem_desc(bbase, B_LBO, SBO);
+                const uint64_t db2 = tc::make_smem_desc(bbase + B_HALF, B_LBO, SBO);
                 tc::umma_bf16(tmem_h2, da1, db1, idesc, (c > 0 || j > 0) ? 1u : 0u);
                 tc::umma_bf16(tmem_h2, da1, db2, idesc, 1u);
                 tc::umma_bf16(tmem_h2, da2, db1, idesc, 1u);
+                tc::umma_commit(&sm.bars.bfree[bs]);
               }
               tc::umma_commit(&sm.bars.afree[as]);
-              tc::umma_commit(&sm.bars.bfree[bs]);
             }
             tc::umma_commit(&sm.bars.h2full);
+            // ---- successor tile-step: its layer 1 goes ahead of this tile's layer 3 whenever it belongs to another
+            //      slot (its X operand then cannot depend on logits that are still to be produced)
+            int s2 = s + 1, k2 = k;
+            int64_t pair2 = pair;
+            uint32_t pi2 = pi;
+            if (s2 == nt) { s2 = 0; if (++k2 == K) { k2 = 0; pair2 += gridDim.x; ++pi2; } }
+            const bool has_next = pair2 < num_pairs;
+            const uint32_t xn2 = pi2 * (uint32_t)K + (uint32_t)k2;
+            // (only if that X operand is already there: never stall this tile's logits behind another slot's env phase)
+            const bool early = has_next && (!L3TC || (nt > 1 && tc::mbar_test(&sm.bars.xfull[s2], xn2 & 1)));
+            if (early) issue_l1(s2, xn2, ts + 1);
+            if constexpr (L3TC) {
+              // ---- layer 3: logits = relu(H2 + b2) . W3^T, N = 16, accumulator in H2 columns 0-15
+#pragma unroll 1
+              for (int c = 0; c < NCH; ++c) {
+                const uint32_t ai = ts * NCH + c, as = ai % NA2;
+                TC_T0(t_4);
+                TC_WAIT(&sm.bars.a2full[as], (ai / NA2) & 1, 12, ai);
+                TC_ACC(19, t_4);                      // MMA: wait for a layer-3 A chunk
+                tc::tc_fence_after();
+                const uint32_t abase = tc::smem_u32(sm.a2stage[as]);
+#pragma unroll
+                for (int j = 0; j < KC2 / 16; ++j) {
+                  const uint32_t wb = w3base + (uint32_t)(c * (KC2 / 16) + j) * 2 * W3_LBO;
+                  const uint64_t da1 = tc::make_smem_desc(abase + j * 2 * A_LBO, A_LBO, SBO);
+                  const uint64_t da2 = tc::make_smem_desc(abase + A_HALF + j * 2 * A_LBO, A_LBO, SBO);
+                  const uint64_t dw31 = tc::make_smem_desc(wb, W3_LBO, SBO);
+                  const uint64_t dw32 = tc::make_smem_desc(wb + W3_HALF, W3_LBO, SBO);
+                  tc::umma_bf16(tmem_h2, da1, dw31, idesc3, (c > 0 || j > 0) ? 1u : 0u);
+                  tc::umma_bf16(tmem_h2, da1, dw32, idesc3, 1u);
+                  tc::umma_bf16(tmem_h2, da2, dw31, idesc3, 1u);
+                }
+                tc::umma_commit(&sm.bars.a2free[as]);
+              }
+              tc::umma_commit(&sm.bars.l3full);
+            }
+            if (has_next && !early) issue_l1(s2, xn2, ts + 1);
 #ifdef MSACL_TC_TIMING
             if (stats) atomicAdd(&stats[18], 1.0);
 #endif
@@ -480,12 +624,12 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
     if (lane == 0) {
       int64_t tile_steps = 0;
       for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) tile_steps += (int64_t)tiles_in_pair(pair) * K;
-      const int64_t total = tile_steps * NCH;
+      const int64_t total = tile_steps * NCHB;
       for (int64_t i = 0; i < total; ++i) {
         const uint32_t bs = (uint32_t)(i % NB);
-        if (i >= NB) tc::mbar_wait(&sm.bars.bfree[bs], (uint32_t)(((i / NB) - 1) & 1));
+        if (i >= NB) TC_WAIT(&sm.bars.bfree[bs], (uint32_t)(((i / NB) - 1) & 1), 13, i);
         tc::mbar_expect_tx(&sm.bars.bfull[bs], 2 * B_HALF);
-        tc::tma_bulk_g2s(sm.bstage[bs], w2p_g + (size_t)(i % NCH) * 2 * B_HALF, 2 * B_HALF, &sm.bars.bfull[bs]);
+        tc::tma_bulk_g2s(sm.bstage[bs], w2p_g + (size_t)(i % NCHB) * 2 * B_HALF, 2 * B_HALF, &sm.bars.bfull[bs]);
       }
     }
     }
@@ -506,9 +650,9 @@ extern "C" int msacl_tc_pack_bytes(int64_t* w1p_bytes, int64_t* w2p_bytes) {
   return MSACL_OK;
 }
 
-extern "C" int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, void* w1p, void* w2p, void* stream) {
-  if (!actor || !w1p || !w2p || obs_dim < 1 || obs_dim > 15) { set_error("tc_pack_actor: bad argument"); return MSACL_ERR_BAD_ARG; }
-  tc_pack_actor_kernel<<<(NCH * 4 * TC_HID + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*actor, obs_dim, (unsigned char*)w1p, (unsigned char*)w2p);
+extern "C" int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, int32_t act_dim, void* w1p, void* w2p, void* stream) {
+  if (!actor || !w1p || !w2p || obs_dim < 1 || obs_dim > 15 || act_dim < 1 || act_dim > 4) { set_error("tc_pack_actor: bad argument"); return MSACL_ERR_BAD_ARG; }
+  tc_pack_actor_kernel<<<(NCHB * 2 * TC_HID + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*actor, obs_dim, 2 * act_dim, (unsigned char*)w1p, (unsigned char*)w2p);
   return check_launch("tc_pack_actor");
 }
 
@@ -524,8 +668,10 @@ extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_a
     constexpr int NS = (ID == kQuadTracking) ? 3 : 4;
     const int64_t groups = (tiles + NS - 1) / NS;
     const unsigned grid = (unsigned)(groups < kNumSMs ? groups : kNumSMs);
-    const size_t smem = sizeof(TcSmem<ID, NS>) + 128;
-    auto kern = rollout_tc_kernel<ID, NS>;
+    constexpr bool L3TC = MSACL_TC_L3TC;
+    static_assert(sizeof(TcSmem<ID, NS, L3TC>) + 128 <= 232448, "shared-memory layout exceeds the 227 KB per-CTA limit");
+    const size_t smem = sizeof(TcSmem<ID, NS, L3TC>) + 128;
+    auto kern = rollout_tc_kernel<ID, NS, L3TC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("rollout_fused_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
     kern<<<grid, TcCfg<NS>::THREADS, smem, (cudaStream_t)stream>>>(*st, *actor, (const unsigned char*)w1p, (const unsigned char*)w2p, K,
