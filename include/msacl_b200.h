@@ -133,8 +133,7 @@ int msacl_rollout_fused(const msacl_env_state_t* st, const msacl_actor_t* actor,
  * relative (tolerances in tests/test_gpu_tc.py).  w1p / w2p are the operand images produced by
  * msacl_tc_pack_actor (sizes from msacl_tc_pack_bytes); repack after every weight update. */
 int msacl_tc_pack_bytes(int64_t* w1p_bytes, int64_t* w2p_bytes);
-int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, int32_t act_dim, void* w1p, void* w2p,
-                        void* stream);
+int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, void* w1p, void* w2p, void* stream);
 int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_actor_t* actor, const void* w1p, const void* w2p,
                            int32_t K, uint32_t step_base, int32_t n_step, float reward_scale, float cost_scale,
                            const float* eps, int32_t deterministic, const msacl_transitions_t* out, double* stats,
@@ -206,6 +205,11 @@ int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, vo
  * split-bf16 scheme (splits = 1: plain bf16; 3: a1*b1 + a1*b2 + a2*b1), FP32 accumulation in TMEM.
  * Exercises the descriptor / TMEM plumbing of the tensor-core rollout path. */
 int msacl_selftest_tc_gemm(const float* A, const float* W, float* D, int32_t splits, void* stream);
+
+/* Diagnostic: average cycles per 128x256x16 bf16 UMMA when one thread per SM issues `iters` groups of three
+ * back to back from no-swizzle K-major shared-memory operands (mode 0), or while the CTA's other warps
+ * stream 16-byte shared-memory stores (mode 1).  cycles_per_umma: device double[1]. */
+int msacl_umma_probe(int32_t mode, int32_t iters, double* cycles_per_umma, void* stream);
 
 const char* msacl_last_error(void);
 int msacl_abi_version(void);

@@ -51,7 +51,7 @@ SIGNATURES = {
     "msacl_rollout_fused": (C.c_int, [C.POINTER(EnvState), C.POINTER(Actor), C.c_int32, C.c_uint32, C.c_int32,
                                       C.c_float, C.c_float, vp, C.c_int32, C.POINTER(Transitions), vp, vp]),
     "msacl_tc_pack_bytes": (C.c_int, [c_i64p, c_i64p]),
-    "msacl_tc_pack_actor": (C.c_int, [C.POINTER(Actor), C.c_int32, C.c_int32, vp, vp, vp]),
+    "msacl_tc_pack_actor": (C.c_int, [C.POINTER(Actor), C.c_int32, vp, vp, vp]),
     "msacl_rollout_fused_tc": (C.c_int, [C.POINTER(EnvState), C.POINTER(Actor), vp, vp, C.c_int32, C.c_uint32, C.c_int32,
                                          C.c_float, C.c_float, vp, C.c_int32, C.POINTER(Transitions), vp, vp]),
     "msacl_action_noise": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32, vp, vp]),
@@ -65,6 +65,7 @@ SIGNATURES = {
     "msacl_advantage_normalize": (C.c_int, [C.c_int64, vp, vp, vp, vp]),
     "msacl_selftest_tc_gemm": (C.c_int, [vp, vp, vp, C.c_int32, vp]),
     "msacl_ffma_probe": (C.c_int, [C.c_int32, C.c_int32, vp, c_f64p, vp]),
+    "msacl_umma_probe": (C.c_int, [C.c_int32, C.c_int32, vp, vp]),
 }
 
 

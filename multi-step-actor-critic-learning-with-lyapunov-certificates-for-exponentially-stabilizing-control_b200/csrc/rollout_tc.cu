@@ -7,20 +7,20 @@
 //     x.w ~= x1.w1 + x1.w2 + x2.w1                 (three UMMAs, FP32 accumulation in TMEM)
 // Relative error of a product ~1e-5 (vs 4e-3 for single-pass bf16); tolerances in tests/test_gpu_tc.py.
 //
-// One persistent CTA per SM, NS 128-env tiles (slots) in flight, warp-specialised:
+// One persistent CTA per SM, NS = 3 tiles of 128 envs (slots) in flight, warp-specialised:
 //   env warps (4*NS)  thread = env instance, state in registers for all K steps; sample action, integrate the ODE,
 //                     reward/cost/autoreset, write the next observation as the layer-1 A operand (16-wide K block:
 //                     obs, 1.0 for the bias, 0), then the transition.
 //   MMA warp          one elected thread: layer 1 = 3 UMMAs (K=16, bias folded in as a K column), layer 2 =
-//                     16 k-steps x 3 UMMAs of 128x256x16, accumulators in TMEM (H1: columns 0-255, H2: 256-511);
-//                     with L3TC also layer 3 = 16 k-steps x 3 UMMAs of 128x16x16 whose accumulator re-uses the
-//                     first 16 columns of H2 once epilogue 2 has read them.  tcgen05.commit signals mbarriers.
-//   epilogue 1 (4)    TMEM(H1) -> ReLU -> split to bf16 hi/lo -> shared-memory A stages (UMMA canonical K-major
-//                     layout, thread = row, 16-byte conflict-free stores).
+//                     16 k-steps x 3 UMMAs of 128x256x16, FP32 accumulators in TMEM.  TMEM is used as TWO 256-column
+//                     buffers; tile-step t keeps both its H1 and its H2 in buffer t&1 (H2 overwrites H1 once
+//                     epilogue 1 has drained it), so the MLP of tile-step t+1 runs while epilogue 2 of t reads.
+//   epilogue 1 (4)    TMEM(H1) -> ReLU -> split to bf16 hi/lo -> the shared-memory A operand of layer 2 (the whole
+//                     128x256 tile is resident: 8 stages of 16 KB in the UMMA canonical K-major layout, thread = row).
 //   TMA warp          pre-split W2 k-step images (16 KB) global/L2 -> shared ring (cp.async.bulk).
-//   epilogue 2 (4)    L3TC: TMEM(H2) -> +b2, ReLU -> split -> A stages of layer 3, then TMEM(logits) -> +b3 -> smem.
-//                     else: TMEM(H2) -> +b2, ReLU -> layer 3 (256 -> 2A) in packed FP32 FMAs -> logits in smem.
-// All hand-offs are mbarriers (full/empty rings for A and B stages, H1/H2 full/free, X full, logits).
+//   epilogue 2 (4)    TMEM(H2) -> +b2, ReLU -> layer 3 (256 -> 2A) in packed FP32 FMAs -> logits in shared memory.
+// All hand-offs are mbarriers (per-stage full/free for A and B, per-buffer full/free for H2, H1 full/free, X full,
+// logits); tcgen05.commit signals the ones the tensor pipe produces.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -36,9 +36,6 @@ namespace msacl {
 #define TC_ACC(slot, t0) do {} while (0)
 #endif
 
-#ifndef MSACL_TC_L3TC
-#define MSACL_TC_L3TC false         // true: layer 3 on the tensor cores too (measured: no gain for QuadTracking, slower for the box envs)
-#endif
 // Debug watchdog (build with MSACL_TC_WATCHDOG=1, tools/tc_watchdog.py): every mbarrier wait gives up after ~1.5 s,
 // the first one to do so records {site, aux, block, parity, thread} in stats[25..29] and raises stats[24]; all other
 // waits then fall through, so a protocol deadlock ends the launch (with garbage results) instead of hanging the GPU.
@@ -68,51 +65,41 @@ __device__ __forceinline__ void wd_wait(void* bar, uint32_t parity, int site, ui
 constexpr int TCM = 128;            // envs per tile
 constexpr int TC_HID = 256;
 constexpr int KC2 = 32;             // K per A stage
-constexpr int NCH = TC_HID / KC2;   // 8 A chunks per tile-step
+constexpr int NCH = TC_HID / KC2;   // 8 A stages = the whole layer-2 A operand of a tile
 constexpr int KCB = 16;             // K per W2 stage (one UMMA k-step)
 constexpr int NCHB = TC_HID / KCB;  // 16 W2 stages per tile-step
-constexpr int NB = 4;               // W2 ring depth
-constexpr int NA2 = 2;              // layer-3 A ring depth
+constexpr int NB = 3;               // W2 ring depth
 constexpr int A_HALF = TCM * KC2 * 2;       // 8 KB  (a1 or a2 image of a stage)
 constexpr int B_HALF = TC_HID * KCB * 2;    // 8 KB  (b1 or b2 image of a stage)
 constexpr int A_LBO = TCM * 16, B_LBO = TC_HID * 16, SBO = 128;
 constexpr int X_HALF = TCM * 16 * 2;        // 4 KB  (x1 or x2: 128 rows x 16 k)
 constexpr int W1_HALF = TC_HID * 16 * 2;    // 8 KB
-constexpr int N3 = 16;                      // layer-3 UMMA N (2A <= 8 real rows, zero padded)
-constexpr int W3_LBO = N3 * 16;
-constexpr int W3_HALF = N3 * TC_HID * 2;    // 8 KB  (hi or lo image of W3: 16 rows x 256 k)
 // Launch geometry per number of tile slots in flight: NS env warpgroups + epilogue 1 + epilogue 2 +
-// {MMA, TMA, 2 idle warps}.  Registers are rebalanced with setmaxnreg (65536 per SM in total).
-template <int NS> struct TcCfg;
-// Per warp: launch regs * warps >= sum of the budgets below, or setmaxnreg.inc never returns; and all four warps of a
+// {MMA, TMA, 2 idle warps}.  Registers are rebalanced with setmaxnreg (65536 per SM in total).  Per warp:
+// launch regs * warps >= sum of the budgets below, or setmaxnreg.inc never returns; and all four warps of a
 // warpgroup must execute the same setmaxnreg (the {MMA, TMA, idle, idle} group shares MISC_REGS).
-template <> struct TcCfg<2> { static constexpr int THREADS = 640, ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40, NA = 4; };   // launch 96*20 = 1920 >= 8*152 + 8*64 + 4*40
-template <> struct TcCfg<3> { static constexpr int THREADS = 768, ENV_REGS = 112, EPI_REGS = 56, MISC_REGS = 32, NA = 3; };   // launch 80*24 = 1920 = 12*112 + 8*56 + 4*32
-template <> struct TcCfg<4> { static constexpr int THREADS = 896, ENV_REGS = 88, EPI_REGS = 56, MISC_REGS = 40, NA = 3; };    // launch 72*28 = 2016 = 16*88 + 8*56 + 4*40
-constexpr int NA_MAX = 4;
-constexpr int W2P_BYTES = NCHB * 2 * B_HALF;          // 256 KB packed W2 (hi/lo k-step images)
-constexpr int W1P_BYTES = 2 * W1_HALF + 2 * W3_HALF;  // 32 KB: W1|b1 images followed by the W3 images
+template <int NS> struct TcCfg;
+template <> struct TcCfg<2> { static constexpr int THREADS = 640, ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40; };   // launch 96*20 = 1920 >= 8*152 + 8*64 + 4*40
+template <> struct TcCfg<3> { static constexpr int THREADS = 768, ENV_REGS = 112, EPI_REGS = 56, MISC_REGS = 32; };   // launch 80*24 = 1920 = 12*112 + 8*56 + 4*32
+constexpr int W2P_BYTES = NCHB * 2 * B_HALF;   // 256 KB packed W2 (hi/lo k-step images)
+constexpr int W1P_BYTES = 2 * W1_HALF;
 
 struct TcBars {
   unsigned long long xfull[4], logits[4];
-  unsigned long long h1full, h1free, h2full, h2free, l3full;
-  unsigned long long afull[NA_MAX], afree[NA_MAX], a2full[NA2], a2free[NA2], bfull[NB], bfree[NB];
+  unsigned long long h1full[2], h1free[2], h2full[2], h2free[2];   // per TMEM buffer
+  unsigned long long afull[NCH], afree[NCH], bfull[NB], bfree[NB];
   uint32_t tmem_slot;
 };
 
-template <int ID, int NS, bool L3TC>
+template <int ID, int NS>
 struct TcSmem {
-  using E = Env<ID>;
-  static constexpr int A2 = 2 * E::A;
-  alignas(128) unsigned char bstage[NB][2 * B_HALF];
-  alignas(128) unsigned char astage[TcCfg<NS>::NA][2 * A_HALF];
-  alignas(128) unsigned char a2stage[L3TC ? NA2 : 1][L3TC ? 2 * A_HALF : 128];
-  alignas(128) unsigned char w1p[L3TC ? W1P_BYTES : 2 * W1_HALF];   // W1|b1 images (+ W3 images)
-  alignas(128) unsigned char xop[NS][2 * X_HALF];
-  alignas(16) float w3t[L3TC ? 8 : TC_HID * 8];   // FP32 layer 3: weights transposed [unit n][output j] (zero padded to 8)
+  alignas(128) unsigned char bstage[NB][2 * B_HALF];     //  48 KB
+  alignas(128) unsigned char astage[NCH][2 * A_HALF];    // 128 KB
+  alignas(128) unsigned char w1p[W1P_BYTES];             //  16 KB
+  alignas(128) unsigned char xop[NS][2 * X_HALF];        //   8 KB per slot; doubles as the slot's logits [2A][128] f32
+  alignas(16) float w3t[TC_HID * 8];       // layer-3 weights transposed: [unit n][output j] (zero padded to 8)
   alignas(16) float b2[TC_HID];
   alignas(16) float b3[8];
-  alignas(16) float logits[NS][2 * Env<ID>::A * TCM];
   TcBars bars;
 };
 
@@ -142,10 +129,9 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 }
 
 // ---- one-time packing of the actor weights into UMMA operand images (device, per weight upload)
-// w1p: [hi|lo] x [2 kb][256 n][8 k] bf16, K index d < D = W1[n][d], K index D = b1[n], rest 0;
-//      followed by W3: [hi|lo] x [32 kb][16 n][8 k] bf16 (rows n >= 2A are zero)
+// w1p: [hi|lo] x [2 kb][256 n][8 k] bf16, K index d < D = W1[n][d], K index D = b1[n], rest 0
 // w2p: 16 k-steps x [hi|lo] x [2 kb][256 n][8 k] bf16, K-major (B[n][k] = W2[n][k] = w2t[k][n])
-__global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, int A2, unsigned char* __restrict__ w1p, unsigned char* __restrict__ w2p) {
+__global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, unsigned char* __restrict__ w1p, unsigned char* __restrict__ w2p) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   // W2: one thread per (k-step c, kb, n): 16 * 2 * 256 = 8192 threads
   if (gid < NCHB * 2 * TC_HID) {
@@ -174,50 +160,39 @@ __global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, int A2, unsigne
     *reinterpret_cast<uint4*>(base) = hi;
     *reinterpret_cast<uint4*>(base + W1_HALF) = lo;
   }
-  // W3: one thread per (kb, n): 32 * 16 = 512 threads
-  if (gid < (TC_HID / 8) * N3) {
-    const int n = gid % N3, kb = gid / N3;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = n < A2 ? actor.w3[n * TC_HID + kb * 8 + j] : 0.f;
-    uint4 hi, lo;
-    split8(v, hi, lo);
-    unsigned char* base = w1p + 2 * W1_HALF + kb * W3_LBO + n * 16;
-    *reinterpret_cast<uint4*>(base) = hi;
-    *reinterpret_cast<uint4*>(base + W3_HALF) = lo;
-  }
 }
 
-template <int ID, int NS, bool L3TC>
+template <int ID, int NS>
 __global__ void __launch_bounds__(TcCfg<NS>::THREADS, 1)
 rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char* __restrict__ w1p_g,
                   const unsigned char* __restrict__ w2p_g, int K, uint32_t step_base, int n_step, float reward_scale,
                   float cost_scale, const float* __restrict__ eps, int deterministic, msacl_transitions_t out, double* stats) {
   using E = Env<ID>;
-  using S = TcSmem<ID, NS, L3TC>;
+  using S = TcSmem<ID, NS>;
   using CFG = TcCfg<NS>;
   constexpr int D = E::D, A = E::A, A2 = 2 * A;
-  constexpr int TC_THREADS = CFG::THREADS, NA = CFG::NA;
+  constexpr int TC_THREADS = CFG::THREADS;
   constexpr int W_EPI1 = 4 * NS, W_EPI2 = 4 * NS + 4, W_MMA = 4 * NS + 8, W_TMA = 4 * NS + 9;
   static_assert(D < 16, "layer-1 K block holds obs + bias column");
+  static_assert(A2 * TCM * 4 <= 2 * X_HALF, "logits alias the X-operand region");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto logits_of = [&](int s) { return reinterpret_cast<float*>(sm.xop[s]); };
 
   // ---- one-time setup
-  for (int i = tid; i < (int)sizeof(sm.w1p) / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm.w1p)[i] = reinterpret_cast<const uint4*>(w1p_g)[i];
-  if constexpr (!L3TC) {
-    for (int i = tid; i < 8 * TC_HID; i += TC_THREADS) { const int n = i >> 3, j = i & 7; sm.w3t[i] = j < A2 ? actor.w3[j * TC_HID + n] : 0.f; }
-  }
+  for (int i = tid; i < W1P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm.w1p)[i] = reinterpret_cast<const uint4*>(w1p_g)[i];
+  for (int i = tid; i < 8 * TC_HID; i += TC_THREADS) { const int n = i >> 3, j = i & 7; sm.w3t[i] = j < A2 ? actor.w3[j * TC_HID + n] : 0.f; }
   for (int i = tid; i < TC_HID; i += TC_THREADS) sm.b2[i] = actor.b2[i];
   if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
   if (tid == 0) {
     TcBars& b = sm.bars;
     for (int s = 0; s < NS; ++s) { tc::mbar_init(&b.xfull[s], TCM); tc::mbar_init(&b.logits[s], TCM); }
-    tc::mbar_init(&b.h1full, 1); tc::mbar_init(&b.h1free, TCM); tc::mbar_init(&b.h2full, 1); tc::mbar_init(&b.h2free, TCM);
-    tc::mbar_init(&b.l3full, 1);
-    for (int i = 0; i < NA2; ++i) { tc::mbar_init(&b.a2full[i], TCM); tc::mbar_init(&b.a2free[i], 1); }
-    for (int i = 0; i < NA; ++i) { tc::mbar_init(&b.afull[i], TCM); tc::mbar_init(&b.afree[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&b.h1full[i], 1); tc::mbar_init(&b.h1free[i], TCM);
+      tc::mbar_init(&b.h2full[i], 1); tc::mbar_init(&b.h2free[i], TCM);
+    }
+    for (int i = 0; i < NCH; ++i) { tc::mbar_init(&b.afull[i], TCM); tc::mbar_init(&b.afree[i], 1); }
     for (int i = 0; i < NB; ++i) { tc::mbar_init(&b.bfull[i], 1); tc::mbar_init(&b.bfree[i], 1); }
     tc::mbar_fence_init();
   }
@@ -226,8 +201,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem = sm.bars.tmem_slot;
-  const uint32_t tmem_h1 = tmem, tmem_h2 = tmem + 256;
+  const uint32_t tmem = sm.bars.tmem_slot;     // buffer b of tile-step t (b = t & 1) = columns [256 b, 256 b + 256)
 
   const int64_t num_tiles = (st.n + TCM - 1) / TCM;
   const int64_t num_pairs = (num_tiles + NS - 1) / NS;      // "pair" = group of NS tiles in flight
@@ -271,6 +245,13 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
 #endif
         TC_WAIT(&sm.bars.logits[s], lcount & 1, 1, lcount);
         ++lcount;
+        // the logits of this slot were written into its X-operand region (free between layer 1 and the next
+        // write_xop): take them into registers, then a slot-wide barrier so that no thread of the slot can overwrite
+        // them with its next observation before every thread has read its own
+        float lg[A2];
+#pragma unroll
+        for (int j = 0; j < A2; ++j) lg[j] = logits_of(s)[j * TCM + r];
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory");
 #ifdef MSACL_TC_TIMING
         const long long t_w1 = clock64();
 #endif
@@ -293,8 +274,8 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           float lp_gauss = 0.f, lp_tanh = 0.f, lp_scale = 0.f;
 #pragma unroll
           for (int j = 0; j < A; ++j) {
-            const float mean = sm.logits[s][j * TCM + r];
-            const float ls = sm.logits[s][(A + j) * TCM + r];
+            const float mean = lg[j];
+            const float ls = lg[A + j];
             const float sd = expf(fminf(fmaxf(ls, actor.min_log_std), actor.max_log_std));
             const float half = (E::act_high(j) - E::act_low(j)) / 2.0f;
             const float mid = (E::act_high(j) + E::act_low(j)) / 2.0f;
@@ -382,21 +363,21 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       const int nt = tiles_in_pair(pair);
       for (int k = 0; k < K; ++k)
         for (int s = 0; s < nt; ++s, ++ts) {
+          const uint32_t buf = ts & 1u, tmem_b = tmem + buf * 256u;
           TC_T0(t_a);
-          TC_WAIT(&sm.bars.h1full, ts & 1, 2, ts);
+          TC_WAIT(&sm.bars.h1full[buf], (ts >> 1) & 1, 2, ts);
           tc::tc_fence_after();
           if (r == 0) TC_ACC(8, t_a);                 // epi1: wait for H1
           TC_T0(t_b);
           for (int c = 0; c < NCH; ++c) {
-            const uint32_t ai = ts * NCH + c, stg = ai % NA;
             TC_T0(t_c);
-            if (ai >= NA) TC_WAIT(&sm.bars.afree[stg], ((ai / NA) - 1) & 1, 3, ai);
+            if (ts > 0) TC_WAIT(&sm.bars.afree[c], (ts - 1) & 1, 3, ts);    // layer 2 of the previous tile-step is done with stage c
             if (r == 0) TC_ACC(10, t_c);              // epi1: wait for a free A stage
             uint32_t v[32];
-            tc::tmem_ld32(tmem_h1 + lane_addr + (uint32_t)(c * 32), v);
+            tc::tmem_ld32(tmem_b + lane_addr + (uint32_t)(c * 32), v);
             tc::tmem_ld_wait();
-            if (c == NCH - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h1free); }
-            unsigned char* base = sm.astage[stg] + r * 16;
+            if (c == NCH - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h1free[buf]); }   // layer 2 may now overwrite the buffer
+            unsigned char* base = sm.astage[c] + r * 16;
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) {
               float w[8];
@@ -408,7 +389,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
               *reinterpret_cast<uint4*>(base + A_HALF + kb * A_LBO) = lo;
             }
             tc::fence_async_smem();
-            tc::mbar_arrive(&sm.bars.afull[stg]);
+            tc::mbar_arrive(&sm.bars.afull[c]);
           }
           if (r == 0) TC_ACC(9, t_b);                 // epi1: chunk loop total
         }
@@ -423,60 +404,21 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       const int nt = tiles_in_pair(pair);
       for (int k = 0; k < K; ++k)
         for (int s = 0; s < nt; ++s, ++ts) {
+          const uint32_t buf = ts & 1u, tmem_b = tmem + buf * 256u;
           TC_T0(t_a);
-          TC_WAIT(&sm.bars.h2full, ts & 1, 4, ts);
+          TC_WAIT(&sm.bars.h2full[buf], (ts >> 1) & 1, 4, ts);
           tc::tc_fence_after();
           if (r == 0) TC_ACC(11, t_a);                // epi2: wait for H2
           TC_T0(t_b);
-          if constexpr (L3TC) {
-            // H2 -> +b2, ReLU -> bf16 hi/lo -> layer-3 A stages; the logits come back through TMEM
-            for (int c = 0; c < NCH; ++c) {
-              const uint32_t ai = ts * NCH + c, stg = ai % NA2;
-              TC_T0(t_c);
-              if (ai >= NA2) TC_WAIT(&sm.bars.a2free[stg], ((ai / NA2) - 1) & 1, 5, ai);
-              if (r == 0) TC_ACC(20, t_c);            // epi2: wait for a free layer-3 A stage
-              uint32_t v[32];
-              tc::tmem_ld32(tmem_h2 + lane_addr + (uint32_t)(c * 32), v);
-              tc::tmem_ld_wait();
-              unsigned char* base = sm.a2stage[stg] + r * 16;
-#pragma unroll
-              for (int kb = 0; kb < 4; ++kb) {
-                const float4 b0 = *reinterpret_cast<const float4*>(&sm.b2[c * 32 + kb * 8]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&sm.b2[c * 32 + kb * 8 + 4]);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                float w[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = fmaxf(__uint_as_float(v[kb * 8 + j]) + bb[j], 0.f);
-                uint4 hi, lo;
-                split8(w, hi, lo);
-                *reinterpret_cast<uint4*>(base + kb * A_LBO) = hi;
-                *reinterpret_cast<uint4*>(base + A_HALF + kb * A_LBO) = lo;
-              }
-              tc::fence_async_smem();
-              tc::tc_fence_before();     // chunk 0: the layer-3 accumulator overwrites H2 columns 0-15 after this arrive
-              tc::mbar_arrive(&sm.bars.a2full[stg]);
-            }
-            TC_T0(t_l);
-            TC_WAIT(&sm.bars.l3full, ts & 1, 6, ts);
-            tc::tc_fence_after();
-            if (r == 0) TC_ACC(21, t_l);              // epi2: wait for the layer-3 UMMAs
-            uint32_t lg[8];
-            tc::tmem_ld8(tmem_h2 + lane_addr, lg);
-            tc::tmem_ld_wait();
-            tc::tc_fence_before();
-            tc::mbar_arrive(&sm.bars.h2free);
-#pragma unroll
-            for (int j = 0; j < A2; ++j) sm.logits[s][j * TCM + r] = __uint_as_float(lg[j]) + sm.b3[j];
-          } else {
           constexpr int NP = (A2 + 1) / 2;          // logit pairs (j, j+1) accumulated with packed FFMA2
           u64 acc[NP];
 #pragma unroll
           for (int q = 0; q < NP; ++q) acc[q] = pack2(sm.b3[2 * q], sm.b3[2 * q + 1]);
           for (int cb = 0; cb < TC_HID / 16; ++cb) {      // 16 columns per TMEM load: leaves registers to prefetch W3 rows
             uint32_t v[16];
-            tc::tmem_ld16(tmem_h2 + lane_addr + (uint32_t)(cb * 16), v);
+            tc::tmem_ld16(tmem_b + lane_addr + (uint32_t)(cb * 16), v);
             tc::tmem_ld_wait();
-            if (cb == TC_HID / 16 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h2free); }
+            if (cb == TC_HID / 16 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h2free[buf]); }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cb * 16 + 4 * q]);
@@ -503,9 +445,8 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           for (int q = 0; q < NP; ++q) {
             float lo, hi;
             unpack2(acc[q], lo, hi);
-            sm.logits[s][(2 * q) * TCM + r] = lo;
-            if (2 * q + 1 < A2) sm.logits[s][(2 * q + 1) * TCM + r] = hi;
-          }
+            logits_of(s)[(2 * q) * TCM + r] = lo;
+            if (2 * q + 1 < A2) logits_of(s)[(2 * q + 1) * TCM + r] = hi;
           }
           tc::mbar_arrive(&sm.bars.logits[s]);
           if (r == 0) TC_ACC(12, t_b);                // epi2: compute
@@ -518,26 +459,26 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(TCM, TC_HID);
-      const uint32_t idesc3 = tc::make_idesc_bf16(TCM, N3);
-      const uint32_t w1base = tc::smem_u32(sm.w1p), w3base = w1base + 2 * W1_HALF;
-      // layer 1 of tile-step `t1` (slot s, xn = number of X operands that slot has produced before):
+      const uint32_t w1base = tc::smem_u32(sm.w1p);
+      // layer 1 of tile-step t1 (slot s; xn = number of X operands that slot has produced before) into buffer t1 & 1:
       // H1 = [obs | 1 | 0] . [W1 | b1 | 0]^T  (K = 16, three products)
       auto issue_l1 = [&](int s, uint32_t xn, uint32_t t1) {
+        TC_T0(t_h);
+        if (t1 >= 2) TC_WAIT(&sm.bars.h2free[t1 & 1], ((t1 >> 1) - 1) & 1, 10, t1);   // epilogue 2 of tile-step t1-2 has drained the buffer
+        TC_ACC(17, t_h);                              // MMA: wait for a free TMEM buffer
         TC_T0(t_x);
         TC_WAIT(&sm.bars.xfull[s], xn & 1, 7, t1);
         TC_ACC(13, t_x);                              // MMA: wait for X
-        TC_T0(t_h);
-        if (t1 > 0) TC_WAIT(&sm.bars.h1free, (t1 - 1) & 1, 8, t1);
-        TC_ACC(14, t_h);                              // MMA: wait for H1 free
         tc::tc_fence_after();
+        const uint32_t tmem_b = tmem + (t1 & 1u) * 256u;
         const uint64_t dw1 = tc::make_smem_desc(w1base, B_LBO, SBO);
         const uint64_t dw2 = tc::make_smem_desc(w1base + W1_HALF, B_LBO, SBO);
         const uint64_t dx1 = tc::make_smem_desc(tc::smem_u32(sm.xop[s]), A_LBO, SBO);
         const uint64_t dx2 = tc::make_smem_desc(tc::smem_u32(sm.xop[s] + X_HALF), A_LBO, SBO);
-        tc::umma_bf16(tmem_h1, dx1, dw1, idesc, 0u);
-        tc::umma_bf16(tmem_h1, dx1, dw2, idesc, 1u);
-        tc::umma_bf16(tmem_h1, dx2, dw1, idesc, 1u);
-        tc::umma_commit(&sm.bars.h1full);
+        tc::umma_bf16(tmem_b, dx1, dw1, idesc, 0u);
+        tc::umma_bf16(tmem_b, dx1, dw2, idesc, 1u);
+        tc::umma_bf16(tmem_b, dx2, dw1, idesc, 1u);
+        tc::umma_commit(&sm.bars.h1full[t1 & 1]);
       };
       uint32_t ts = 0, pi = 0;                        // tile-step counter, local group counter
       for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++pi) {
@@ -545,20 +486,37 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         for (int k = 0; k < K; ++k)
           for (int s = 0; s < nt; ++s, ++ts) {
             if (ts == 0) issue_l1(0, 0u, 0u);
-            // ---- layer 2: H2 = relu(H1) . W2^T over 8 A chunks x 2 k-steps
+            const uint32_t buf = ts & 1u, tmem_b = tmem + buf * 256u;
+            // ---- successor tile-step: its layer 1 goes into the other buffer as early as that buffer is drained and
+            //      its X operand is there (probed without blocking before and between the layer-2 chunks), so that
+            //      epilogue 1 of the successor trails this tile's layer 2 stage by stage; at the latest after layer 2
+            int s2 = s + 1, k2 = k;
+            int64_t pair2 = pair;
+            uint32_t pi2 = pi;
+            if (s2 == nt) { s2 = 0; if (++k2 == K) { k2 = 0; pair2 += gridDim.x; ++pi2; } }
+            const uint32_t xn2 = pi2 * (uint32_t)K + (uint32_t)k2, t2 = ts + 1;
+            bool next_pending = pair2 < num_pairs;
+            auto try_next = [&]() {
+              if (next_pending && (t2 < 2 || tc::mbar_test(&sm.bars.h2free[t2 & 1], ((t2 >> 1) - 1) & 1)) &&
+                  tc::mbar_test(&sm.bars.xfull[s2], xn2 & 1)) {
+                issue_l1(s2, xn2, t2);
+                next_pending = false;
+              }
+            };
+            try_next();
+            // ---- layer 2: H2 = relu(H1) . W2^T, accumulated over H1's own buffer once epilogue 1 has drained it
+            TC_T0(t_h);
+            TC_WAIT(&sm.bars.h1free[buf], (ts >> 1) & 1, 8, ts);
+            TC_ACC(14, t_h);                          // MMA: wait for epilogue 1 to finish reading H1
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
-              const uint32_t ai = ts * NCH + c, as = ai % NA;
               TC_T0(t_1);
-              TC_WAIT(&sm.bars.afull[as], (ai / NA) & 1, 9, ai);
-              TC_ACC(15, t_1);                        // MMA: wait for A chunk
-              TC_T0(t_3);
-              if (c == 0 && ts > 0) TC_WAIT(&sm.bars.h2free, (ts - 1) & 1, 10, ts);
-              TC_ACC(17, t_3);                        // MMA: wait for H2 free
-              const uint32_t abase = tc::smem_u32(sm.astage[as]);
+              TC_WAIT(&sm.bars.afull[c], ts & 1, 9, ts);
+              TC_ACC(15, t_1);                        // MMA: wait for A stage
+              const uint32_t abase = tc::smem_u32(sm.astage[c]);
 #pragma unroll
               for (int j = 0; j < KC2 / KCB; ++j) {
-                const uint32_t bi = ai * (KC2 / KCB) + j, bs = bi % NB;
+                const uint32_t bi = (ts * NCH + c) * (KC2 / KCB) + j, bs = bi % NB;
                 TC_T0(t_2);
                 TC_WAIT(&sm.bars.bfull[bs], (bi / NB) & 1, 11, bi);
                 TC_ACC(16, t_2);                      // MMA: wait for B stage
@@ -568,51 +526,16 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
                 const uint64_t da2 = tc::make_smem_desc(abase + A_HALF + j * 2 * A_LBO, A_LBO, SBO);
                 const uint64_t db1 = tc::make_smem_desc(bbase, B_LBO, SBO);
                 const uint64_t db2 = tc::make_smem_desc(bbase + B_HALF, B_LBO, SBO);
-                tc::umma_bf16(tmem_h2, da1, db1, idesc, (c > 0 || j > 0) ? 1u : 0u);
-                tc::umma_bf16(tmem_h2, da1, db2, idesc, 1u);
-                tc::umma_bf16(tmem_h2, da2, db1, idesc, 1u);
+                tc::umma_bf16(tmem_b, da1, db1, idesc, (c > 0 || j > 0) ? 1u : 0u);
+                tc::umma_bf16(tmem_b, da1, db2, idesc, 1u);
+                tc::umma_bf16(tmem_b, da2, db1, idesc, 1u);
                 tc::umma_commit(&sm.bars.bfree[bs]);
               }
-              tc::umma_commit(&sm.bars.afree[as]);
+              tc::umma_commit(&sm.bars.afree[c]);
+              try_next();
             }
-            tc::umma_commit(&sm.bars.h2full);
-            // ---- successor tile-step: its layer 1 goes ahead of this tile's layer 3 whenever it belongs to another
-            //      slot (its X operand then cannot depend on logits that are still to be produced)
-            int s2 = s + 1, k2 = k;
-            int64_t pair2 = pair;
-            uint32_t pi2 = pi;
-            if (s2 == nt) { s2 = 0; if (++k2 == K) { k2 = 0; pair2 += gridDim.x; ++pi2; } }
-            const bool has_next = pair2 < num_pairs;
-            const uint32_t xn2 = pi2 * (uint32_t)K + (uint32_t)k2;
-            // (only if that X operand is already there: never stall this tile's logits behind another slot's env phase)
-            const bool early = has_next && (!L3TC || (nt > 1 && tc::mbar_test(&sm.bars.xfull[s2], xn2 & 1)));
-            if (early) issue_l1(s2, xn2, ts + 1);
-            if constexpr (L3TC) {
-              // ---- layer 3: logits = relu(H2 + b2) . W3^T, N = 16, accumulator in H2 columns 0-15
-#pragma unroll 1
-              for (int c = 0; c < NCH; ++c) {
-                const uint32_t ai = ts * NCH + c, as = ai % NA2;
-                TC_T0(t_4);
-                TC_WAIT(&sm.bars.a2full[as], (ai / NA2) & 1, 12, ai);
-                TC_ACC(19, t_4);                      // MMA: wait for a layer-3 A chunk
-                tc::tc_fence_after();
-                const uint32_t abase = tc::smem_u32(sm.a2stage[as]);
-#pragma unroll
-                for (int j = 0; j < KC2 / 16; ++j) {
-                  const uint32_t wb = w3base + (uint32_t)(c * (KC2 / 16) + j) * 2 * W3_LBO;
-                  const uint64_t da1 = tc::make_smem_desc(abase + j * 2 * A_LBO, A_LBO, SBO);
-                  const uint64_t da2 = tc::make_smem_desc(abase + A_HALF + j * 2 * A_LBO, A_LBO, SBO);
-                  const uint64_t dw31 = tc::make_smem_desc(wb, W3_LBO, SBO);
-                  const uint64_t dw32 = tc::make_smem_desc(wb + W3_HALF, W3_LBO, SBO);
-                  tc::umma_bf16(tmem_h2, da1, dw31, idesc3, (c > 0 || j > 0) ? 1u : 0u);
-                  tc::umma_bf16(tmem_h2, da1, dw32, idesc3, 1u);
-                  tc::umma_bf16(tmem_h2, da2, dw31, idesc3, 1u);
-                }
-                tc::umma_commit(&sm.bars.a2free[as]);
-              }
-              tc::umma_commit(&sm.bars.l3full);
-            }
-            if (has_next && !early) issue_l1(s2, xn2, ts + 1);
+            tc::umma_commit(&sm.bars.h2full[buf]);
+            if (next_pending) issue_l1(s2, xn2, t2);
 #ifdef MSACL_TC_TIMING
             if (stats) atomicAdd(&stats[18], 1.0);
 #endif
@@ -620,7 +543,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       }
     }
     } else if (warp == W_TMA) {
-    // =========================== TMA producer: W2 chunk images ===========================
+    // =========================== TMA producer: W2 k-step images ===========================
     if (lane == 0) {
       int64_t tile_steps = 0;
       for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) tile_steps += (int64_t)tiles_in_pair(pair) * K;
@@ -650,9 +573,9 @@ extern "C" int msacl_tc_pack_bytes(int64_t* w1p_bytes, int64_t* w2p_bytes) {
   return MSACL_OK;
 }
 
-extern "C" int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, int32_t act_dim, void* w1p, void* w2p, void* stream) {
-  if (!actor || !w1p || !w2p || obs_dim < 1 || obs_dim > 15 || act_dim < 1 || act_dim > 4) { set_error("tc_pack_actor: bad argument"); return MSACL_ERR_BAD_ARG; }
-  tc_pack_actor_kernel<<<(NCHB * 2 * TC_HID + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*actor, obs_dim, 2 * act_dim, (unsigned char*)w1p, (unsigned char*)w2p);
+extern "C" int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, void* w1p, void* w2p, void* stream) {
+  if (!actor || !w1p || !w2p || obs_dim < 1 || obs_dim > 15) { set_error("tc_pack_actor: bad argument"); return MSACL_ERR_BAD_ARG; }
+  tc_pack_actor_kernel<<<(NCHB * 2 * TC_HID + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*actor, obs_dim, (unsigned char*)w1p, (unsigned char*)w2p);
   return check_launch("tc_pack_actor");
 }
 
@@ -664,14 +587,12 @@ extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_a
   if ((reinterpret_cast<uintptr_t>(w2p) & 15) || (reinterpret_cast<uintptr_t>(w1p) & 15)) { set_error("rollout_fused_tc: packed weights must be 16-byte aligned"); return MSACL_ERR_BAD_ARG; }
   const int64_t tiles = (st->n + TCM - 1) / TCM;
   MSACL_DISPATCH_ENV(st->env_id, {
-    // QuadTracking keeps ~50 state registers per env -> 3 slots; the box envs run 4 slots
-    constexpr int NS = (ID == kQuadTracking) ? 3 : 4;
+    constexpr int NS = 3;      // tile slots in flight (shared memory holds the resident A operand + 3 X/logits slots)
+    static_assert(sizeof(TcSmem<ID, NS>) + 128 <= 232448, "shared-memory layout exceeds the 227 KB per-CTA limit");
     const int64_t groups = (tiles + NS - 1) / NS;
     const unsigned grid = (unsigned)(groups < kNumSMs ? groups : kNumSMs);
-    constexpr bool L3TC = MSACL_TC_L3TC;
-    static_assert(sizeof(TcSmem<ID, NS, L3TC>) + 128 <= 232448, "shared-memory layout exceeds the 227 KB per-CTA limit");
-    const size_t smem = sizeof(TcSmem<ID, NS, L3TC>) + 128;
-    auto kern = rollout_tc_kernel<ID, NS, L3TC>;
+    const size_t smem = sizeof(TcSmem<ID, NS>) + 128;
+    auto kern = rollout_tc_kernel<ID, NS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("rollout_fused_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
     kern<<<grid, TcCfg<NS>::THREADS, smem, (cudaStream_t)stream>>>(*st, *actor, (const unsigned char*)w1p, (const unsigned char*)w2p, K,

@@ -83,9 +83,69 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// UMMA issue-rate probe: one CTA per SM; thread 0 issues `iters` groups of three 128x256x16 UMMAs (the layer-2 inner
+// step of the rollout kernel: A stage = 8 x 16 KB ring, B stage = 3 x 16 KB ring, no-swizzle K-major operands) and
+// measures cycles from the first issue to the completion of the last.  mode 1 adds the other three warps storing
+// 16-byte vectors to shared memory the whole time (the epilogue / TMA write traffic of the real kernel).
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(int mode, int iters, double* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* a = smem;                 // 8 stages x 16 KB
+  unsigned char* b = smem + 131072;        // 3 stages x 16 KB
+  unsigned char* scratch = smem + 180224;  // 24 KB store target for the interfering warps
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + 204800);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 204800 + 64);
+  volatile int* stop = reinterpret_cast<volatile int*>(smem + 204800 + 128);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 180224 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); *stop = 0; }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::make_idesc_bf16(128, 256);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t ab = tc::smem_u32(a + ((i >> 1) & 7) * 16384 + (i & 1) * 4096), bb = tc::smem_u32(b + (i % 3) * 16384);
+      const uint64_t da1 = tc::make_smem_desc(ab, 2048, 128), da2 = tc::make_smem_desc(ab + 8192, 2048, 128);
+      const uint64_t db1 = tc::make_smem_desc(bb, 4096, 128), db2 = tc::make_smem_desc(bb + 8192, 4096, 128);
+      tc::umma_bf16(tmem, da1, db1, idesc, i > 0 ? 1u : 0u);
+      tc::umma_bf16(tmem, da1, db2, idesc, 1u);
+      tc::umma_bf16(tmem, da2, db1, idesc, 1u);
+    }
+    tc::umma_commit(bar);
+    tc::mbar_wait(bar, 0u);
+    const long long t1 = clock64();
+    *stop = 1;
+    if (blockIdx.x == 0) out[0] = (double)(t1 - t0) / (3.0 * iters);
+  } else if (warp > 0 && mode == 1) {
+    uint4 v = make_uint4(tid, tid, tid, tid);
+    int off = (tid - 32) * 16;
+    while (!*stop) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(scratch + ((off + q * 1536) % 24576)) = v;
+      off = (off + 12288) % 24576;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
 }  // namespace msacl
 
 using namespace msacl;
+
+extern "C" int msacl_umma_probe(int32_t mode, int32_t iters, double* cycles_per_umma, void* stream) {
+  if (!cycles_per_umma || iters <= 0 || mode < 0 || mode > 1) { set_error("umma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
+  const int smem = 204800 + 256;
+  cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("umma_probe: %s", cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
+  umma_probe_kernel<<<kNumSMs, 128, smem, (cudaStream_t)stream>>>(mode, iters, cycles_per_umma);
+  return check_launch("umma_probe");
+}
 
 extern "C" int msacl_selftest_tc_gemm(const float* A, const float* W, float* D, int32_t splits, void* stream) {
   if (!A || !W || !D || (splits != 1 && splits != 3)) { set_error("selftest_tc_gemm: bad argument"); return MSACL_ERR_BAD_ARG; }

@@ -59,7 +59,7 @@ class ActorWeights:
             _lib.check(lib.msacl_tc_pack_bytes(C.byref(n1), C.byref(n2)))
             w1p = torch.empty(n1.value, dtype=torch.uint8, device=self.w1.device)
             w2p = torch.empty(n2.value, dtype=torch.uint8, device=self.w1.device)
-            _lib.check(lib.msacl_tc_pack_actor(C.byref(self.desc), self.obs_dim, self.act_dim, w1p.data_ptr(), w2p.data_ptr(), _lib.current_stream()))
+            _lib.check(lib.msacl_tc_pack_actor(C.byref(self.desc), self.obs_dim, w1p.data_ptr(), w2p.data_ptr(), _lib.current_stream()))
             self._tc = (w1p, w2p)
         return self._tc
 

@@ -20,6 +20,6 @@ for env in sys.argv[1:]:
     s = ro.stats.cpu().numpy()
     n = max(s[18], 1)
     print(env, 'ms %.2f' % a.elapsed_time(b), 'env %.0f wait %.0f |' % (s[5] / max(s[7], 1), s[6] / max(s[7], 1)),
-          'per tile-step: epi1 waitH1 %.0f loop %.0f (waitAfree %.0f) | epi2 waitH2 %.0f compute %.0f (waitA2free %.0f waitL3 %.0f) | '
-          'MMA waitX %.0f waitH1free %.0f waitA %.0f waitB %.0f waitH2free %.0f waitA2 %.0f'
-          % (s[8] / n, s[9] / n, s[10] / n, s[11] / n, s[12] / n, s[20] / n, s[21] / n, s[13] / n, s[14] / n, s[15] / n, s[16] / n, s[17] / n, s[19] / n))
+          'per tile-step: epi1 waitH1 %.0f loop %.0f (waitAfree %.0f) | epi2 waitH2 %.0f compute %.0f | '
+          'MMA waitX %.0f waitEpi1 %.0f waitA %.0f waitB %.0f waitTmemBuf %.0f'
+          % (s[8] / n, s[9] / n, s[10] / n, s[11] / n, s[12] / n, s[13] / n, s[14] / n, s[15] / n, s[16] / n, s[17] / n))
