@@ -208,7 +208,9 @@ int msacl_selftest_tc_gemm(const float* A, const float* W, float* D, int32_t spl
 
 /* Diagnostic: average cycles per 128x256x16 bf16 UMMA when one thread per SM issues `iters` groups of three
  * back to back from no-swizzle K-major shared-memory operands (mode 0), or while the CTA's other warps
- * stream 16-byte shared-memory stores (mode 1).  cycles_per_umma: device double[1]. */
+ * stream 16-byte shared-memory stores (mode 1) or tcgen05.ld reads of other TMEM columns (mode 2; the aggregate
+ * read rate in bytes/cycle is returned in cycles_per_umma[1]); mode 3: a tcgen05.commit per group; mode 4: plus an
+ * mbarrier wait per group.  cycles_per_umma: device double[4]. */
 int msacl_umma_probe(int32_t mode, int32_t iters, double* cycles_per_umma, void* stream);
 
 const char* msacl_last_error(void);

@@ -15,10 +15,12 @@
 //                     16 k-steps x 3 UMMAs of 128x256x16, FP32 accumulators in TMEM.  TMEM is used as TWO 256-column
 //                     buffers; tile-step t keeps both its H1 and its H2 in buffer t&1 (H2 overwrites H1 once
 //                     epilogue 1 has drained it), so the MLP of tile-step t+1 runs while epilogue 2 of t reads.
-//   epilogue 1 (4)    TMEM(H1) -> ReLU -> split to bf16 hi/lo -> the shared-memory A operand of layer 2 (the whole
-//                     128x256 tile is resident: 8 stages of 16 KB in the UMMA canonical K-major layout, thread = row).
+//   epilogue warps (8) both epilogues, split by column halves (two warps per TMEM lane quadrant):
+//                     epilogue 1: TMEM(H1) -> ReLU -> split to bf16 hi/lo -> the shared-memory A operand of layer 2
+//                     (the whole 128x256 tile is resident: 8 stages of 16 KB, UMMA canonical K-major layout, thread = row);
+//                     epilogue 2: TMEM(H2) -> +b2, ReLU -> layer 3 (256 -> 2A) in packed FP32 FMAs, the two column
+//                     halves combined through shared memory -> logits in shared memory.
 //   TMA warp          pre-split W2 k-step images (16 KB) global/L2 -> shared ring (cp.async.bulk).
-//   epilogue 2 (4)    TMEM(H2) -> +b2, ReLU -> layer 3 (256 -> 2A) in packed FP32 FMAs -> logits in shared memory.
 // All hand-offs are mbarriers (per-stage full/free for A and B, per-buffer full/free for H2, H1 full/free, X full,
 // logits); tcgen05.commit signals the ones the tensor pipe produces.
 #include "common.cuh"
@@ -174,11 +176,12 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   constexpr int TC_THREADS = CFG::THREADS;
   constexpr int W_EPI1 = 4 * NS, W_EPI2 = 4 * NS + 4, W_MMA = 4 * NS + 8, W_TMA = 4 * NS + 9;
   static_assert(D < 16, "layer-1 K block holds obs + bias column");
-  static_assert(A2 * TCM * 4 <= 2 * X_HALF, "logits alias the X-operand region");
+  static_assert(A2 * TCM * 4 <= X_HALF && 8 * TCM * 4 <= X_HALF, "logits and partial sums alias the two halves of the X-operand region");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  auto logits_of = [&](int s) { return reinterpret_cast<float*>(sm.xop[s]); };
+  auto logits_of = [&](int s) { return reinterpret_cast<float*>(sm.xop[s]); };              // [2A][128] f32, first half of the region
+  auto partial_of = [&](int s) { return reinterpret_cast<float*>(sm.xop[s] + X_HALF); };   // epilogue-2 partial sums, second half
 
   // ---- one-time setup
   for (int i = tid; i < W1P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm.w1p)[i] = reinterpret_cast<const uint4*>(w1p_g)[i];
@@ -189,8 +192,8 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
     TcBars& b = sm.bars;
     for (int s = 0; s < NS; ++s) { tc::mbar_init(&b.xfull[s], TCM); tc::mbar_init(&b.logits[s], TCM); }
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&b.h1full[i], 1); tc::mbar_init(&b.h1free[i], TCM);
-      tc::mbar_init(&b.h2full[i], 1); tc::mbar_init(&b.h2free[i], TCM);
+      tc::mbar_init(&b.h1full[i], 1); tc::mbar_init(&b.h1free[i], 2 * TCM);     // drained by all 8 epilogue warps
+      tc::mbar_init(&b.h2full[i], 1); tc::mbar_init(&b.h2free[i], 2 * TCM);
     }
     for (int i = 0; i < NCH; ++i) { tc::mbar_init(&b.afull[i], TCM); tc::mbar_init(&b.afree[i], 1); }
     for (int i = 0; i < NB; ++i) { tc::mbar_init(&b.bfull[i], 1); tc::mbar_init(&b.bfree[i], 1); }
@@ -353,103 +356,132 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         if (lane == 0 && v[q] != 0.f) atomicAdd(&stats[q], (double)v[q]);
       }
     }
-  } else if (warp < W_EPI2) {
-    // =========================== epilogue 1: H1 -> ReLU -> bf16 hi/lo -> A stages ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CFG::EPI_REGS));
-    const int r = tid - W_EPI1 * 32;
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t ts = 0;
-    for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-      const int nt = tiles_in_pair(pair);
-      for (int k = 0; k < K; ++k)
-        for (int s = 0; s < nt; ++s, ++ts) {
-          const uint32_t buf = ts & 1u, tmem_b = tmem + buf * 256u;
-          TC_T0(t_a);
-          TC_WAIT(&sm.bars.h1full[buf], (ts >> 1) & 1, 2, ts);
-          tc::tc_fence_after();
-          if (r == 0) TC_ACC(8, t_a);                 // epi1: wait for H1
-          TC_T0(t_b);
-          for (int c = 0; c < NCH; ++c) {
-            TC_T0(t_c);
-            if (ts > 0) TC_WAIT(&sm.bars.afree[c], (ts - 1) & 1, 3, ts);    // layer 2 of the previous tile-step is done with stage c
-            if (r == 0) TC_ACC(10, t_c);              // epi1: wait for a free A stage
-            uint32_t v[32];
-            tc::tmem_ld32(tmem_b + lane_addr + (uint32_t)(c * 32), v);
-            tc::tmem_ld_wait();
-            if (c == NCH - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h1free[buf]); }   // layer 2 may now overwrite the buffer
-            unsigned char* base = sm.astage[c] + r * 16;
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb) {
-              float w[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) w[j] = fmaxf(__uint_as_float(v[kb * 8 + j]), 0.f);
-              uint4 hi, lo;
-              split8(w, hi, lo);
-              *reinterpret_cast<uint4*>(base + kb * A_LBO) = hi;
-              *reinterpret_cast<uint4*>(base + A_HALF + kb * A_LBO) = lo;
-            }
-            tc::fence_async_smem();
-            tc::mbar_arrive(&sm.bars.afull[c]);
-          }
-          if (r == 0) TC_ACC(9, t_b);                 // epi1: chunk loop total
-        }
-    }
   } else if (warp < W_MMA) {
-    // =========================== epilogue 2: H2 -> +b2, ReLU -> layer 3 -> logits ===========================
+    // =========================== epilogue warps (8): both epilogues, column-split ===========================
+    // Warp e = warp - W_EPI1: TMEM lane quadrant q = e & 3 (rows 32q..32q+31, thread = row), column half h = e >> 2.
+    //   epilogue 1 of a tile-step: H1[:, 128h..128h+127] -> ReLU -> bf16 hi/lo -> A stages 4h..4h+3
+    //   epilogue 2 of a tile-step: H2[:, 128h..128h+127] -> +b2, ReLU -> partial layer 3 (packed FP32 FMAs); half 1
+    //                              parks its partial sums in the slot's shared-memory region, half 0 adds them,
+    //                              writes the logits and signals the slot's env warps.
+    // Job order per tile-step t (groups of >= 2 slots): epilogue 1 of t+1 (it trails layer 2 of t stage by stage), then
+    // epilogue 2 of t (while layer 2 of t+1 runs).  With a single slot the X operand of t+1 needs the logits of t, so
+    // the order is swapped.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CFG::EPI_REGS));
-    const int r = tid - W_EPI2 * 32;
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const int q = warp & 3, h = (warp - W_EPI1) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const bool timer = (warp == W_EPI1 && lane == 0);
+    auto epi1 = [&](uint32_t t1) {
+      const uint32_t buf = t1 & 1u, tmem_b = tmem + buf * 256u;
+      TC_T0(t_a);
+      TC_WAIT(&sm.bars.h1full[buf], (t1 >> 1) & 1, 2, t1);
+      tc::tc_fence_after();
+      if (timer) TC_ACC(8, t_a);                      // epi1: wait for H1
+      TC_T0(t_b);
+#pragma unroll 1
+      for (int cc = 0; cc < NCH / 2; ++cc) {
+        const int c = h * (NCH / 2) + cc;
+        TC_T0(t_c);
+        if (t1 > 0) TC_WAIT(&sm.bars.afree[c], (t1 - 1) & 1, 3, t1);   // layer 2 of the previous tile-step is done with stage c
+        if (timer) TC_ACC(10, t_c);                   // epi1: wait for a free A stage
+        uint32_t v[32];
+        tc::tmem_ld32(tmem_b + lane_addr + (uint32_t)(c * 32), v);
+        tc::tmem_ld_wait();
+        if (cc == NCH / 2 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h1free[buf]); }   // layer 2 may overwrite the buffer
+        unsigned char* base = sm.astage[c] + r * 16;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          float w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = fmaxf(__uint_as_float(v[kb * 8 + j]), 0.f);
+          uint4 hi, lo;
+          split8(w, hi, lo);
+          *reinterpret_cast<uint4*>(base + kb * A_LBO) = hi;
+          *reinterpret_cast<uint4*>(base + A_HALF + kb * A_LBO) = lo;
+        }
+        tc::fence_async_smem();
+        tc::mbar_arrive(&sm.bars.afull[c]);
+      }
+      if (timer) TC_ACC(9, t_b);                      // epi1: chunk loop total
+    };
+    auto epi2 = [&](uint32_t t0, int s) {
+      const uint32_t buf = t0 & 1u, tmem_b = tmem + buf * 256u;
+      TC_T0(t_a);
+      TC_WAIT(&sm.bars.h2full[buf], (t0 >> 1) & 1, 4, t0);
+      tc::tc_fence_after();
+      if (timer) TC_ACC(11, t_a);                     // epi2: wait for H2
+      TC_T0(t_b);
+      constexpr int NP = (A2 + 1) / 2;                // logit pairs (j, j+1) accumulated with packed FFMA2
+      u64 acc[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) acc[p] = h == 0 ? pack2(sm.b3[2 * p], sm.b3[2 * p + 1]) : pack2(0.f, 0.f);
+#pragma unroll 1
+      for (int cc = 0; cc < TC_HID / 32; ++cc) {        // 16 columns per TMEM load: leaves registers to prefetch W3 rows
+        const int cb = h * (TC_HID / 32) + cc;
+        uint32_t v[16];
+        tc::tmem_ld16(tmem_b + lane_addr + (uint32_t)(cb * 16), v);
+        tc::tmem_ld_wait();
+        if (cc == TC_HID / 32 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h2free[buf]); }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cb * 16 + 4 * g]);
+          const float hv[4] = {fmaxf(__uint_as_float(v[4 * g + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * g + 1]) + bb.y, 0.f),
+                               fmaxf(__uint_as_float(v[4 * g + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * g + 3]) + bb.w, 0.f)};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float* wrow = &sm.w3t[(cb * 16 + 4 * g + c) * 8];      // all lanes read the same address: broadcast
+            const u64 hh = pack2(hv[c], hv[c]);
+            if constexpr (NP >= 1) {
+              const float4 w0 = *reinterpret_cast<const float4*>(wrow);
+              acc[0] = fma2(hh, pack2(w0.x, w0.y), acc[0]);
+              if constexpr (NP >= 2) acc[1] = fma2(hh, pack2(w0.z, w0.w), acc[1]);
+            }
+            if constexpr (NP >= 3) {
+              const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
+              acc[2] = fma2(hh, pack2(w1.x, w1.y), acc[2]);
+              if constexpr (NP >= 4) acc[3] = fma2(hh, pack2(w1.z, w1.w), acc[3]);
+            }
+          }
+        }
+      }
+      // combine the two column halves: rows of quadrant q are shared by warps (q, half 0) and (q, half 1)
+      float* part = partial_of(s);
+      if (h == 1) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          float lo, hi;
+          unpack2(acc[p], lo, hi);
+          part[(2 * p) * TCM + r] = lo;
+          part[(2 * p + 1) * TCM + r] = hi;
+        }
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(4 + q) : "memory");
+      if (h == 0) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          float lo, hi;
+          unpack2(acc[p], lo, hi);
+          logits_of(s)[(2 * p) * TCM + r] = lo + part[(2 * p) * TCM + r];
+          if (2 * p + 1 < A2) logits_of(s)[(2 * p + 1) * TCM + r] = hi + part[(2 * p + 1) * TCM + r];
+        }
+        tc::mbar_arrive(&sm.bars.logits[s]);
+      }
+      if (timer) TC_ACC(12, t_b);                     // epi2: compute
+    };
     uint32_t ts = 0;
     for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
       const int nt = tiles_in_pair(pair);
       for (int k = 0; k < K; ++k)
         for (int s = 0; s < nt; ++s, ++ts) {
-          const uint32_t buf = ts & 1u, tmem_b = tmem + buf * 256u;
-          TC_T0(t_a);
-          TC_WAIT(&sm.bars.h2full[buf], (ts >> 1) & 1, 4, ts);
-          tc::tc_fence_after();
-          if (r == 0) TC_ACC(11, t_a);                // epi2: wait for H2
-          TC_T0(t_b);
-          constexpr int NP = (A2 + 1) / 2;          // logit pairs (j, j+1) accumulated with packed FFMA2
-          u64 acc[NP];
-#pragma unroll
-          for (int q = 0; q < NP; ++q) acc[q] = pack2(sm.b3[2 * q], sm.b3[2 * q + 1]);
-          for (int cb = 0; cb < TC_HID / 16; ++cb) {      // 16 columns per TMEM load: leaves registers to prefetch W3 rows
-            uint32_t v[16];
-            tc::tmem_ld16(tmem_b + lane_addr + (uint32_t)(cb * 16), v);
-            tc::tmem_ld_wait();
-            if (cb == TC_HID / 16 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h2free[buf]); }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cb * 16 + 4 * q]);
-              const float hv[4] = {fmaxf(__uint_as_float(v[4 * q + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f),
-                                   fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f)};
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float* wrow = &sm.w3t[(cb * 16 + 4 * q + c) * 8];      // all lanes read the same address: broadcast
-                const u64 hh = pack2(hv[c], hv[c]);
-                if constexpr (NP >= 1) {
-                  const float4 w0 = *reinterpret_cast<const float4*>(wrow);
-                  acc[0] = fma2(hh, pack2(w0.x, w0.y), acc[0]);
-                  if constexpr (NP >= 2) acc[1] = fma2(hh, pack2(w0.z, w0.w), acc[1]);
-                }
-                if constexpr (NP >= 3) {
-                  const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
-                  acc[2] = fma2(hh, pack2(w1.x, w1.y), acc[2]);
-                  if constexpr (NP >= 4) acc[3] = fma2(hh, pack2(w1.z, w1.w), acc[3]);
-                }
-              }
-            }
+          if (ts == 0) epi1(0u);
+          const bool has_next = !(s + 1 == nt && k + 1 == K && pair + (int64_t)gridDim.x >= num_pairs);
+          if (nt > 1) {
+            if (has_next) epi1(ts + 1);
+            epi2(ts, s);
+          } else {
+            epi2(ts, s);
+            if (has_next) epi1(ts + 1);
           }
-#pragma unroll
-          for (int q = 0; q < NP; ++q) {
-            float lo, hi;
-            unpack2(acc[q], lo, hi);
-            logits_of(s)[(2 * q) * TCM + r] = lo;
-            if (2 * q + 1 < A2) logits_of(s)[(2 * q + 1) * TCM + r] = hi;
-          }
-          tc::mbar_arrive(&sm.bars.logits[s]);
-          if (r == 0) TC_ACC(12, t_b);                // epi2: compute
         }
     }
   } else {
@@ -460,6 +492,14 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(TCM, TC_HID);
       const uint32_t w1base = tc::smem_u32(sm.w1p);
+      // The issuing thread is the serial resource of the tensor pipeline, so its per-k-step instruction stream is kept
+      // short: descriptors are (constant high word, low word = base + (byte offset >> 4)) -- the 14-bit address field
+      // cannot carry because shared memory is < 256 KB -- and the W2 ring position is tracked incrementally.
+      const uint32_t a_lo0 = (uint32_t)tc::make_smem_desc(tc::smem_u32(sm.astage[0]), A_LBO, SBO);
+      const uint32_t b_lo0 = (uint32_t)tc::make_smem_desc(tc::smem_u32(sm.bstage[0]), B_LBO, SBO);
+      const uint32_t d_hi = (uint32_t)(tc::make_smem_desc(0u, 0u, SBO) >> 32);
+      auto mk = [&](uint32_t lo) { return ((uint64_t)d_hi << 32) | (uint64_t)lo; };
+      uint32_t bs = 0, bph = 0;                       // W2 ring stage / phase parity of the next k-step
       // layer 1 of tile-step t1 (slot s; xn = number of X operands that slot has produced before) into buffer t1 & 1:
       // H1 = [obs | 1 | 0] . [W1 | b1 | 0]^T  (K = 16, three products)
       auto issue_l1 = [&](int s, uint32_t xn, uint32_t t1) {
@@ -513,23 +553,21 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
               TC_T0(t_1);
               TC_WAIT(&sm.bars.afull[c], ts & 1, 9, ts);
               TC_ACC(15, t_1);                        // MMA: wait for A stage
-              const uint32_t abase = tc::smem_u32(sm.astage[c]);
+              const uint32_t a_lo = a_lo0 + (uint32_t)c * (2 * A_HALF / 16);
 #pragma unroll
               for (int j = 0; j < KC2 / KCB; ++j) {
-                const uint32_t bi = (ts * NCH + c) * (KC2 / KCB) + j, bs = bi % NB;
                 TC_T0(t_2);
-                TC_WAIT(&sm.bars.bfull[bs], (bi / NB) & 1, 11, bi);
+                TC_WAIT(&sm.bars.bfull[bs], bph, 11, ts);
                 TC_ACC(16, t_2);                      // MMA: wait for B stage
                 tc::tc_fence_after();
-                const uint32_t bbase = tc::smem_u32(sm.bstage[bs]);
-                const uint64_t da1 = tc::make_smem_desc(abase + j * 2 * A_LBO, A_LBO, SBO);
-                const uint64_t da2 = tc::make_smem_desc(abase + A_HALF + j * 2 * A_LBO, A_LBO, SBO);
-                const uint64_t db1 = tc::make_smem_desc(bbase, B_LBO, SBO);
-                const uint64_t db2 = tc::make_smem_desc(bbase + B_HALF, B_LBO, SBO);
+                const uint32_t b_lo = b_lo0 + bs * (2 * B_HALF / 16);
+                const uint64_t da1 = mk(a_lo + j * (2 * A_LBO / 16)), da2 = mk(a_lo + j * (2 * A_LBO / 16) + A_HALF / 16);
+                const uint64_t db1 = mk(b_lo), db2 = mk(b_lo + B_HALF / 16);
                 tc::umma_bf16(tmem_b, da1, db1, idesc, (c > 0 || j > 0) ? 1u : 0u);
                 tc::umma_bf16(tmem_b, da1, db2, idesc, 1u);
                 tc::umma_bf16(tmem_b, da2, db1, idesc, 1u);
                 tc::umma_commit(&sm.bars.bfree[bs]);
+                if (++bs == NB) { bs = 0; bph ^= 1u; }
               }
               tc::umma_commit(&sm.bars.afree[c]);
               try_next();
@@ -548,11 +586,13 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       int64_t tile_steps = 0;
       for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) tile_steps += (int64_t)tiles_in_pair(pair) * K;
       const int64_t total = tile_steps * NCHB;
+      uint32_t bs = 0, bph = 1, kk = 0;            // ring stage, parity of the "free" phase to wait for, k-step within the tile
       for (int64_t i = 0; i < total; ++i) {
-        const uint32_t bs = (uint32_t)(i % NB);
-        if (i >= NB) TC_WAIT(&sm.bars.bfree[bs], (uint32_t)(((i / NB) - 1) & 1), 13, i);
+        if (i >= NB) TC_WAIT(&sm.bars.bfree[bs], bph, 13, i);
         tc::mbar_expect_tx(&sm.bars.bfull[bs], 2 * B_HALF);
-        tc::tma_bulk_g2s(sm.bstage[bs], w2p_g + (size_t)(i % NCHB) * 2 * B_HALF, 2 * B_HALF, &sm.bars.bfull[bs]);
+        tc::tma_bulk_g2s(sm.bstage[bs], w2p_g + (size_t)kk * 2 * B_HALF, 2 * B_HALF, &sm.bars.bfull[bs]);
+        if (++bs == NB) { bs = 0; bph ^= 1u; }
+        if (++kk == NCHB) kk = 0;
       }
     }
     }

@@ -86,8 +86,11 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W
 // UMMA issue-rate probe: one CTA per SM; thread 0 issues `iters` groups of three 128x256x16 UMMAs (the layer-2 inner
 // step of the rollout kernel: A stage = 8 x 16 KB ring, B stage = 3 x 16 KB ring, no-swizzle K-major operands) and
 // measures cycles from the first issue to the completion of the last.  mode 1 adds the other three warps storing
-// 16-byte vectors to shared memory the whole time (the epilogue / TMA write traffic of the real kernel).
-__global__ void __launch_bounds__(128, 1) umma_probe_kernel(int mode, int iters, double* __restrict__ out) {
+// 16-byte vectors to shared memory the whole time (the epilogue / TMA write traffic of the real kernel); mode 2 has
+// warps 1-7 read the other 256 TMEM columns with tcgen05.ld the whole time (the epilogues' accumulator reads) and
+// reports their aggregate rate in out[1] (bytes per cycle); mode 3 adds a tcgen05.commit after every group of three,
+// mode 4 additionally an (already satisfied) mbarrier wait per group -- the rollout kernel's per-k-step protocol.
+__global__ void __launch_bounds__(256, 1) umma_probe_kernel(int mode, int iters, double* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* a = smem;                 // 8 stages x 16 KB
   unsigned char* b = smem + 131072;        // 3 stages x 16 KB
@@ -96,9 +99,10 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int mode, int iters,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 204800 + 64);
   volatile int* stop = reinterpret_cast<volatile int*>(smem + 204800 + 128);
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < 180224 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); *stop = 0; }
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  unsigned long long* ldcount = reinterpret_cast<unsigned long long*>(smem + 204800 + 192);
+  for (int i = tid; i < 180224 / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_init(bar + 1, 1); tc::mbar_init(bar + 2, 1); tc::mbar_fence_init(); tc::mbar_arrive(bar + 2); *stop = 0; *ldcount = 0ull; }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -114,13 +118,15 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int mode, int iters,
       tc::umma_bf16(tmem, da1, db1, idesc, i > 0 ? 1u : 0u);
       tc::umma_bf16(tmem, da1, db2, idesc, 1u);
       tc::umma_bf16(tmem, da2, db1, idesc, 1u);
+      if (mode >= 3) tc::umma_commit(bar + 1);               // per-k-step commit, as the rollout kernel's stage release
+      if (mode >= 4) { tc::mbar_wait(bar + 2, 0u); tc::tc_fence_after(); }   // + an (already satisfied) mbarrier wait per k-step
     }
     tc::umma_commit(bar);
     tc::mbar_wait(bar, 0u);
     const long long t1 = clock64();
     *stop = 1;
-    if (blockIdx.x == 0) out[0] = (double)(t1 - t0) / (3.0 * iters);
-  } else if (warp > 0 && mode == 1) {
+    if (blockIdx.x == 0) { out[0] = (double)(t1 - t0) / (3.0 * iters); out[2] = (double)(t1 - t0); }
+  } else if (warp > 0 && warp < 4 && mode == 1) {
     uint4 v = make_uint4(tid, tid, tid, tid);
     int off = (tid - 32) * 16;
     while (!*stop) {
@@ -128,10 +134,27 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int mode, int iters,
       for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(scratch + ((off + q * 1536) % 24576)) = v;
       off = (off + 12288) % 24576;
     }
+  } else if (warp > 0 && mode == 2) {
+    unsigned long long n = 0;
+    uint32_t acc = 0;
+    while (!*stop) {
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256u + (uint32_t)(cb * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc ^= v[j];
+      }
+      n += 8;
+    }
+    if (acc == 0x12345678u) out[3] = 1.0;     // keep the loads alive
+    if ((tid & 31) == 0) atomicAdd(ldcount, n);
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+  if (tid == 0 && blockIdx.x == 0 && mode == 2) out[1] = (double)(*ldcount) * 4096.0 / out[2];   // 32 lanes x 32 columns x 4 B per load
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace msacl
@@ -139,11 +162,11 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int mode, int iters,
 using namespace msacl;
 
 extern "C" int msacl_umma_probe(int32_t mode, int32_t iters, double* cycles_per_umma, void* stream) {
-  if (!cycles_per_umma || iters <= 0 || mode < 0 || mode > 1) { set_error("umma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
+  if (!cycles_per_umma || iters <= 0 || mode < 0 || mode > 4) { set_error("umma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
   const int smem = 204800 + 256;
   cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("umma_probe: %s", cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
-  umma_probe_kernel<<<kNumSMs, 128, smem, (cudaStream_t)stream>>>(mode, iters, cycles_per_umma);
+  umma_probe_kernel<<<kNumSMs, 256, smem, (cudaStream_t)stream>>>(mode, iters, cycles_per_umma);
   return check_launch("umma_probe");
 }
 

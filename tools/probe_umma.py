@@ -5,9 +5,11 @@ import torch
 import msacl_b200
 from msacl_b200 import _lib
 lib = _lib.load()
-out = torch.zeros(1, dtype=torch.float64, device="cuda")
-for mode in (0, 1):
+out = torch.zeros(4, dtype=torch.float64, device="cuda")
+for mode in (0, 1, 2, 3, 4):
     for iters in (64, 512):
+        out.zero_()
         _lib.check(lib.msacl_umma_probe(mode, iters, out.data_ptr(), _lib.current_stream()))
         torch.cuda.synchronize()
-        print("mode", mode, "iters", iters, "cycles/UMMA %.1f" % out.item(), flush=True)
+        o = out.cpu().numpy()
+        print("mode", mode, "iters", iters, "cycles/UMMA %.1f" % o[0], ("tcgen05.ld rate %.1f B/cycle" % o[1]) if mode == 2 else "", flush=True)
