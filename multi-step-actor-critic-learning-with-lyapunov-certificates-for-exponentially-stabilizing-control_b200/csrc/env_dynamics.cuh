@@ -340,12 +340,15 @@ __device__ __forceinline__ void quad_desired(const float* x, const float* v, dou
     const double mg = (j == 2) ? m * gz : m * 0.0;
     fd[j] = -(((double)p - mg) + (double)(mf * ad[j]));
   }
-  const double fn = sqrt((fd[0] * fd[0] + fd[1] * fd[1]) + fd[2] * fd[2]);
-  const double b3[3] = {fd[0] / fn, fd[1] / fn, fd[2] / fn};
+  // normalisations as x * rsqrt(|x|^2): differs from x / sqrt(|x|^2) by a few float64 ulps, far below the float32
+  // resolution every consumer of the desired frame is rounded to (one reciprocal square root instead of a square
+  // root and three divisions on the float64 pipe)
+  const double ifn = rsqrt((fd[0] * fd[0] + fd[1] * fd[1]) + fd[2] * fd[2]);
+  const double b3[3] = {fd[0] * ifn, fd[1] * ifn, fd[2] * ifn};
   const double b1[3] = {ct, st, 0.0};
   double c[3] = {b3[1] * b1[2] - b3[2] * b1[1], b3[2] * b1[0] - b3[0] * b1[2], b3[0] * b1[1] - b3[1] * b1[0]};
-  const double cn = sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
-  const double b2[3] = {c[0] / cn, c[1] / cn, c[2] / cn};
+  const double icn = rsqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+  const double b2[3] = {c[0] * icn, c[1] * icn, c[2] * icn};
   const double bn[3] = {b2[1] * b3[2] - b2[2] * b3[1], b2[2] * b3[0] - b2[0] * b3[2], b2[0] * b3[1] - b2[1] * b3[0]};
 #pragma unroll
   for (int i = 0; i < 3; ++i) { Rd[3 * i + 0] = bn[i]; Rd[3 * i + 1] = b2[i]; Rd[3 * i + 2] = b3[i]; }
@@ -360,19 +363,20 @@ __device__ __forceinline__ void quad_errors(const float* x, const float* v, cons
     obs[j] = (float)((double)x[j] - xd[j]);
     obs[3 + j] = v[j] - vd[j];
   }
-  // E = Rd^T R - R^T Rd ; eR = 0.5 * vee(E) with vee = (E[2][1], E[0][2], E[1][0])
-  auto RdTR = [&](int i, int j) {
-    return (Rd[0 + i] * (double)R[0 + j] + Rd[3 + i] * (double)R[3 + j]) + Rd[6 + i] * (double)R[6 + j];
-  };
-  auto RTRd = [&](int i, int j) {
-    return ((double)R[0 + i] * Rd[0 + j] + (double)R[3 + i] * Rd[3 + j]) + (double)R[6 + i] * Rd[6 + j];
-  };
-  obs[6] = (float)(RdTR(2, 1) - RTRd(2, 1)) * 0.5f;
-  obs[7] = (float)(RdTR(0, 2) - RTRd(0, 2)) * 0.5f;
-  obs[8] = (float)(RdTR(1, 0) - RTRd(1, 0)) * 0.5f;
+  // E = Rd^T R - R^T Rd ; eR = 0.5 * vee(E) with vee = (E[2][1], E[0][2], E[1][0]).  M = Rd^T R is formed once:
+  // (R^T Rd)[i][j] = M[j][i] term by term (same products, same association), so nothing changes numerically.
+  double M[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      M[3 * i + j] = (Rd[0 + i] * (double)R[0 + j] + Rd[3 + i] * (double)R[3 + j]) + Rd[6 + i] * (double)R[6 + j];
+  obs[6] = (float)(M[3 * 2 + 1] - M[3 * 1 + 2]) * 0.5f;
+  obs[7] = (float)(M[3 * 0 + 2] - M[3 * 2 + 0]) * 0.5f;
+  obs[8] = (float)(M[3 * 1 + 0] - M[3 * 0 + 1]) * 0.5f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const double w = (RTRd(i, 0) * Omd[0] + RTRd(i, 1) * Omd[1]) + RTRd(i, 2) * Omd[2];
+    const double w = (M[3 * 0 + i] * Omd[0] + M[3 * 1 + i] * Omd[1]) + M[3 * 2 + i] * Omd[2];
     obs[9 + i] = (float)((double)Om[i] - w);
   }
 }
@@ -436,9 +440,10 @@ template <> struct Env<kQuadTracking> {
     quad_desired(x, v, t, xd, vd, Rd);
     double dtt = t - t_last;
     if (dtt < 1e-6) dtt = 1e-6;
+    const double inv_dtt = 1.0 / dtt;                  // one float64 division instead of nine (same argument as above)
     float Rdd[9];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) Rdd[j] = (float)((Rd[j] - sd[1 + j]) / dtt);
+    for (int j = 0; j < 9; ++j) Rdd[j] = (float)((Rd[j] - sd[1 + j]) * inv_dtt);
     auto RdT_Rdd = [&](int i, int j) {
       return (Rd[0 + i] * (double)Rdd[0 + j] + Rd[3 + i] * (double)Rdd[3 + j]) + Rd[6 + i] * (double)Rdd[6 + j];
     };
