@@ -25,9 +25,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <int WPB>
+// DT = compile-time obs_dim (0: run-time D).  The kernel is instruction-issue bound before it is HBM bound (a warp
+// per 20-step window moves only 1.4 KB), so the per-window instruction stream is kept lean: no run-time loops over D,
+// one running 64-bit element index, all loads of a window issued before the first use.
+template <int WPB, int DT>
 __global__ void __launch_bounds__(WPB * 32)
-lyapunov_risk_kernel(int64_t B, int n, int D, const float* __restrict__ obs, const float* __restrict__ obs2,
+lyapunov_risk_kernel(int64_t B, int n, int D_rt, const float* __restrict__ obs, const float* __restrict__ obs2,
                      const float* __restrict__ logp_new, const float* __restrict__ logp_old,
                      const float* __restrict__ lya_obs, const float* __restrict__ lya_obs2,
                      const float* __restrict__ coef_son, const float* __restrict__ coef_diff,
@@ -37,33 +40,45 @@ lyapunov_risk_kernel(int64_t B, int n, int D, const float* __restrict__ obs, con
   __shared__ float s_part[3][WPB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool act = lane < n;
+  const int D = DT > 0 ? DT : D_rt;
   const float son = act ? coef_son[lane] : 0.f, dif = act ? coef_diff[lane] : 0.f, sl = act ? coef_sl[lane] : 0.f;
   const float inv_bn = pos_scale / (float)((double)B * n);
   const float w_scale = diff_scale / (float)B;
   float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-  for (int64_t b = (int64_t)blockIdx.x * WPB + warp; b < B; b += (int64_t)gridDim.x * WPB) {
-    const int64_t e = b * n + lane;
+  const int64_t wstride = (int64_t)gridDim.x * WPB;
+  const int64_t estep = wstride * n;
+  int64_t b = (int64_t)blockIdx.x * WPB + warp;
+  for (int64_t e = b * n + lane; b < B; b += wstride, e += estep) {
     float ratio = 1.f, v1 = 0.f, v2 = 0.f, op = 0.f, op2 = 0.f;
     if (act) {
-      // issue every load of this lane before the first use (memory-level parallelism)
       const float ln = logp_new[e], lo_ = logp_old[e];
       v1 = lya_obs[e]; v2 = lya_obs2[e];
       const float* o = obs + e * D;
       const float* q = obs2 + e * D;
-      if ((D & 3) == 0) {            // rows are 16-byte aligned: vector loads
-        for (int d = 0; d < D; d += 4) {
-          const float4 a = *reinterpret_cast<const float4*>(o + d);
-          const float4 c = *reinterpret_cast<const float4*>(q + d);
-          op = __fmaf_rn(a.x, a.x, op); op = __fmaf_rn(a.y, a.y, op); op = __fmaf_rn(a.z, a.z, op); op = __fmaf_rn(a.w, a.w, op);
-          op2 = __fmaf_rn(c.x, c.x, op2); op2 = __fmaf_rn(c.y, c.y, op2); op2 = __fmaf_rn(c.z, c.z, op2); op2 = __fmaf_rn(c.w, c.w, op2);
+      if constexpr (DT > 0 && DT % 4 == 0) {            // rows are 16-byte aligned: vector loads
+        float4 a[DT / 4], c[DT / 4];
+#pragma unroll
+        for (int d = 0; d < DT / 4; ++d) { a[d] = reinterpret_cast<const float4*>(o)[d]; c[d] = reinterpret_cast<const float4*>(q)[d]; }
+#pragma unroll
+        for (int d = 0; d < DT / 4; ++d) {
+          op = __fmaf_rn(a[d].x, a[d].x, op); op = __fmaf_rn(a[d].y, a[d].y, op); op = __fmaf_rn(a[d].z, a[d].z, op); op = __fmaf_rn(a[d].w, a[d].w, op);
+          op2 = __fmaf_rn(c[d].x, c[d].x, op2); op2 = __fmaf_rn(c[d].y, c[d].y, op2); op2 = __fmaf_rn(c[d].z, c[d].z, op2); op2 = __fmaf_rn(c[d].w, c[d].w, op2);
         }
-      } else if ((D & 1) == 0) {
-        for (int d = 0; d < D; d += 2) {
-          const float2 a = *reinterpret_cast<const float2*>(o + d);
-          const float2 c = *reinterpret_cast<const float2*>(q + d);
-          op = __fmaf_rn(a.x, a.x, op); op = __fmaf_rn(a.y, a.y, op);
-          op2 = __fmaf_rn(c.x, c.x, op2); op2 = __fmaf_rn(c.y, c.y, op2);
+      } else if constexpr (DT > 0 && DT % 2 == 0) {
+        float2 a[DT / 2], c[DT / 2];
+#pragma unroll
+        for (int d = 0; d < DT / 2; ++d) { a[d] = reinterpret_cast<const float2*>(o)[d]; c[d] = reinterpret_cast<const float2*>(q)[d]; }
+#pragma unroll
+        for (int d = 0; d < DT / 2; ++d) {
+          op = __fmaf_rn(a[d].x, a[d].x, op); op = __fmaf_rn(a[d].y, a[d].y, op);
+          op2 = __fmaf_rn(c[d].x, c[d].x, op2); op2 = __fmaf_rn(c[d].y, c[d].y, op2);
         }
+      } else if constexpr (DT > 0) {
+        float a[DT], c[DT];
+#pragma unroll
+        for (int d = 0; d < DT; ++d) { a[d] = o[d]; c[d] = q[d]; }
+#pragma unroll
+        for (int d = 0; d < DT; ++d) { op = __fmaf_rn(a[d], a[d], op); op2 = __fmaf_rn(c[d], c[d], op2); }
       } else {
         for (int d = 0; d < D; ++d) { op = __fmaf_rn(o[d], o[d], op); op2 = __fmaf_rn(q[d], q[d], op2); }
       }
@@ -277,9 +292,20 @@ extern "C" int msacl_lyapunov_risk(int64_t B, int32_t n, int32_t D, const float*
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(loss_parts, 0, 3 * sizeof(double), s);
   constexpr int WPB = 8;
-  lyapunov_risk_kernel<WPB><<<grid_for(B, WPB), WPB * 32, 0, s>>>(B, n, D, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2,
-                                                               coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale,
-                                                               pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);
+#define MSACL_LYA_LAUNCH(DT)                                                                                              \
+  lyapunov_risk_kernel<WPB, DT><<<grid_for(B, WPB), WPB * 32, 0, s>>>(B, n, D, obs, obs2, logp_new, logp_old, lya_obs,    \
+                                                                      lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, \
+                                                                      diff_scale, pos_scale, loss_parts, grad_lya_obs,       \
+                                                                      grad_lya_obs2, is_clip, esl)
+  switch (D) {           // obs_dim of the six reference envs; anything else takes the run-time-D instantiation
+    case 2: MSACL_LYA_LAUNCH(2); break;
+    case 4: MSACL_LYA_LAUNCH(4); break;
+    case 6: MSACL_LYA_LAUNCH(6); break;
+    case 7: MSACL_LYA_LAUNCH(7); break;
+    case 12: MSACL_LYA_LAUNCH(12); break;
+    default: MSACL_LYA_LAUNCH(0); break;
+  }
+#undef MSACL_LYA_LAUNCH
   return check_launch("lyapunov_risk");
 }
 

@@ -130,34 +130,72 @@ window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_fl
   }
 }
 
-// One warp per sampled window; every field of a window is a contiguous run of floats.  With
-// n_step % 4 == 0 (reference default 20) all runs are multiples of 16 bytes and 16-byte aligned,
-// so the copy is done with float4 (else scalar).
-__device__ __forceinline__ void copy_run(float* __restrict__ dst, const float* __restrict__ src, int count, int lane, bool vec) {
-  if (vec) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int e = lane; e < count / 4; e += 32) d4[e] = s4[e];
-  } else {
-    for (int e = lane; e < count; e += 32) dst[e] = src[e];
-  }
+// One warp per sampled window (grid-stride).  Every field of a window is a contiguous run of floats; with
+// n_step % 4 == 0 (reference default 20) all runs are whole, 16-byte aligned float4 vectors, and the window is copied as
+// ONE flat list of vectors (obs | obs2 | act | rew | cost | done | logp).  The vector -> (field, offset) map is the same
+// for every window, so each lane resolves its (up to GATHER_MAX_VEC) vectors once, and per window only adds the slot
+// offset: all loads of a window are in flight together, then the stores.  Other n_step: scalar run-by-run copy.
+constexpr int GATHER_MAX_VEC = 6;     // covers n_step * (2D + A + 4) / 4 <= 192 vectors (e.g. n_step 24, D 12, A 4)
+
+__device__ __forceinline__ void gather_vec_map(const msacl_ring_t& R, int i, int Lo, int La, int Ls, float*& base, int& stride) {
+  const int ns = R.n_step;
+  if (i < Lo) { base = R.obs + 4 * i; stride = ns * R.obs_dim; return; }
+  i -= Lo;
+  if (i < Lo) { base = R.obs2 + 4 * i; stride = ns * R.obs_dim; return; }
+  i -= Lo;
+  if (i < La) { base = R.act + 4 * i; stride = ns * R.act_dim; return; }
+  i -= La;
+  const int f = i / Ls, o = i - f * Ls;
+  base = (f == 0 ? R.rew : (f == 1 ? R.cost : (f == 2 ? R.done : R.logp))) + 4 * o;
+  stride = ns;
 }
 
+__device__ __forceinline__ void copy_run(float* __restrict__ dst, const float* __restrict__ src, int count, int lane) {
+  for (int e = lane; e < count; e += 32) dst[e] = src[e];
+}
+
+// NV = float4 vectors per lane (ceil(vectors per window / 32)); 0 = scalar fallback
+template <int NV>
 __global__ void __launch_bounds__(256)
 ring_gather_kernel(msacl_ring_t ring, const int64_t* __restrict__ idx, int64_t B, msacl_ring_t batch) {
   const int lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  if (b >= B) return;
-  const int64_t s = idx[b];
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x / 32);
+  int64_t b = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int ns = ring.n_step, D = ring.obs_dim, A = ring.act_dim;
-  const bool vec = (ns & 3) == 0;
-  copy_run(batch.obs + b * ns * D, ring.obs + s * ns * D, ns * D, lane, vec);
-  copy_run(batch.obs2 + b * ns * D, ring.obs2 + s * ns * D, ns * D, lane, vec);
-  copy_run(batch.act + b * ns * A, ring.act + s * ns * A, ns * A, lane, vec);
-  copy_run(batch.rew + b * ns, ring.rew + s * ns, ns, lane, vec);
-  copy_run(batch.cost + b * ns, ring.cost + s * ns, ns, lane, vec);
-  copy_run(batch.done + b * ns, ring.done + s * ns, ns, lane, vec);
-  copy_run(batch.logp + b * ns, ring.logp + s * ns, ns, lane, vec);
+  const int Lo = ns * D / 4, La = ns * A / 4, Ls = ns / 4;
+  const int total = 2 * Lo + La + 4 * Ls;
+  if constexpr (NV > 0) {
+    float* sbase[NV];
+    float* dbase[NV];
+    int stride[NV];
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int i = it * 32 + lane;
+      sbase[it] = nullptr; dbase[it] = nullptr; stride[it] = 0;
+      if (i < total) { gather_vec_map(ring, i, Lo, La, Ls, sbase[it], stride[it]); gather_vec_map(batch, i, Lo, La, Ls, dbase[it], stride[it]); }
+    }
+    for (; b < B; b += wstride) {
+      const int64_t s = idx[b];
+      float4 v[NV];
+#pragma unroll
+      for (int it = 0; it < NV; ++it)
+        if (it * 32 + lane < total) v[it] = *reinterpret_cast<const float4*>(sbase[it] + s * stride[it]);
+#pragma unroll
+      for (int it = 0; it < NV; ++it)
+        if (it * 32 + lane < total) *reinterpret_cast<float4*>(dbase[it] + b * stride[it]) = v[it];
+    }
+  } else {
+    for (; b < B; b += wstride) {
+      const int64_t s = idx[b];
+      copy_run(batch.obs + b * ns * D, ring.obs + s * ns * D, ns * D, lane);
+      copy_run(batch.obs2 + b * ns * D, ring.obs2 + s * ns * D, ns * D, lane);
+      copy_run(batch.act + b * ns * A, ring.act + s * ns * A, ns * A, lane);
+      copy_run(batch.rew + b * ns, ring.rew + s * ns, ns, lane);
+      copy_run(batch.cost + b * ns, ring.cost + s * ns, ns, lane);
+      copy_run(batch.done + b * ns, ring.done + s * ns, ns, lane);
+      copy_run(batch.logp + b * ns, ring.logp + s * ns, ns, lane);
+    }
+  }
 }
 
 }  // namespace msacl
@@ -197,6 +235,20 @@ extern "C" int msacl_ring_gather(const msacl_ring_t* ring, const int64_t* idx, i
   if (int rc = validate_ring(batch)) return rc;
   if (!idx || B <= 0) { set_error("ring_gather: bad argument"); return MSACL_ERR_BAD_ARG; }
   const int wpb = 8;
-  ring_gather_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(*ring, idx, B, *batch);
+  const int64_t want = (B + wpb - 1) / wpb, cap = (int64_t)kNumSMs * 8;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  const int ns = ring->n_step;
+  const int total = ns * (2 * ring->obs_dim + ring->act_dim + 4) / 4;      // float4 vectors per window
+  const int nv = ((ns & 3) == 0 && total <= 32 * GATHER_MAX_VEC) ? (total + 31) / 32 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nv) {
+    case 1: ring_gather_kernel<1><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 2: ring_gather_kernel<2><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 3: ring_gather_kernel<3><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 4: ring_gather_kernel<4><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 5: ring_gather_kernel<5><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 6: ring_gather_kernel<6><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    default: ring_gather_kernel<0><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+  }
   return check_launch("ring_gather");
 }

@@ -41,14 +41,51 @@ def line(name, ms, nbytes, units):
                       "achieved_gbs": round(gbs, 1), "hbm_peak_gbs": HBM, "frac": round(gbs / HBM, 3)}))
 
 
+# Each kernel is timed twice: "op" = the Python-level operator a user calls (allocations, the small torch epilogue ops
+# and ctypes overhead included), "kernel" = the C-ABI call alone on preallocated outputs (what the HBM roofline bounds).
+import ctypes as C
+from msacl_b200 import _lib
+lib = _lib.load()
+st = _lib.current_stream()
+
 ms = timeit(lambda: tg.lyapunov_risk_raw(obs, obs2, lpn, lpo, v1, v2, coef, want_labels=False))
-line("lyapunov_risk (fwd + analytic bwd)", ms, B * n * 4 * (2 * D + 4 + 2), B)
+line("lyapunov_risk (fwd + analytic bwd), op", ms, B * n * 4 * (2 * D + 4 + 2), B)
+parts = torch.empty(3, dtype=torch.float64, device=dev)
+g1, g2 = torch.empty_like(v1), torch.empty_like(v2)
+ms = timeit(lambda: _lib.check(lib.msacl_lyapunov_risk(
+    B, n, D, obs.data_ptr(), obs2.data_ptr(), lpn.data_ptr(), lpo.data_ptr(), v1.data_ptr(), v2.data_ptr(),
+    coef.son.data_ptr(), coef.diff.data_ptr(), coef.sl.data_ptr(), coef.alpha1, coef.alpha2, 10.0, 1.0,
+    parts.data_ptr(), g1.data_ptr(), g2.data_ptr(), None, None, st)))
+line("lyapunov_risk (fwd + analytic bwd), kernel", ms, B * n * 4 * (2 * D + 4 + 2), B)
+
 ms = timeit(lambda: tg.q_backup(rew, done, q1, q2, lpn, 0.99, 0.2))
-line("q_backup", ms, B * n * 4 * 6, B)
-ms = timeit(lambda: tg.stability_advantage(v1[:, 0].contiguous(), v2, coef))
-line("stability_advantage + normalize", ms, B * 4 * (n + 1 + 3), B)
+line("q_backup, op", ms, B * n * 4 * 6, B)
+bk = torch.empty_like(rew)
+ms = timeit(lambda: _lib.check(lib.msacl_q_backup(B * n, rew.data_ptr(), done.data_ptr(), q1.data_ptr(), q2.data_ptr(), lpn.data_ptr(),
+                                                  0.99, 0.2, bk.data_ptr(), st)))
+line("q_backup, kernel", ms, B * n * 4 * 6, B)
+
+v0 = v1[:, 0].contiguous()
+ms = timeit(lambda: tg.stability_advantage(v0, v2, coef))
+line("stability_advantage + normalize, op", ms, B * 4 * (n + 1 + 3), B)
+raw, adv, mom = torch.empty_like(v0), torch.empty_like(v0), torch.empty(2, dtype=torch.float64, device=dev)
+
+
+def _adv():
+    _lib.check(lib.msacl_stability_advantage(B, n, v0.data_ptr(), v2.data_ptr(), coef.diff.data_ptr(), coef.sl.data_ptr(),
+                                             raw.data_ptr(), mom.data_ptr(), st))
+    _lib.check(lib.msacl_advantage_normalize(B, raw.data_ptr(), mom.data_ptr(), adv.data_ptr(), st))
+
+
+ms = timeit(_adv)
+line("stability_advantage + normalize, kernels", ms, B * 4 * (n + 1 + 3), B)
+
 buf = B200NstepReplayBuffer(obs_dim=D, act_dim=A, buffer_max_size=B, n_step=n)
 buf._ptr_size[1] = B
 idx = torch.randint(0, B, (1 << 18,), device=dev, generator=g)
 ms = timeit(lambda: buf.gather(idx))
-line("ring_gather (2^18 windows)", ms, idx.numel() * n * 4 * (2 * D + A + 4) * 2, idx.numel())
+line("ring_gather (2^18 windows), op", ms, idx.numel() * n * 4 * (2 * D + A + 4) * 2, idx.numel())
+out = {k: torch.empty(idx.numel(), *v.shape[1:], dtype=torch.float32, device=dev) for k, v in buf.n_step_buf.items()}
+dst = buf._make_ring(out, idx.numel())
+ms = timeit(lambda: _lib.check(lib.msacl_ring_gather(C.byref(buf._ring), idx.data_ptr(), idx.numel(), C.byref(dst), st)))
+line("ring_gather (2^18 windows), kernel", ms, idx.numel() * n * 4 * (2 * D + A + 4) * 2, idx.numel())
