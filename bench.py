@@ -286,8 +286,9 @@ def main():
         def full_step():
             a = upload_actor()
             ro.run(a)
+            cur = tr.fields()                            # views of the chunk this launch wrote
             for k in host_fields:
-                host_fields[k].copy_(dev_fields[k], non_blocking=True)
+                host_fields[k].copy_(cur[k][tr.H:], non_blocking=True)
             stream.synchronize()
 
         for _ in range(2):

@@ -64,13 +64,16 @@ __device__ __forceinline__ void wd_wait(void* bar, uint32_t parity, int site, ui
 #define TC_WAIT(bar, par, site, aux) tc::mbar_wait(bar, par)
 #endif
 
+#ifndef MSACL_TC_NS
+#define MSACL_TC_NS(ID) 3
+#endif
 constexpr int TCM = 128;            // envs per tile
 constexpr int TC_HID = 256;
 constexpr int KC2 = 32;             // K per A stage
 constexpr int NCH = TC_HID / KC2;   // 8 A stages = the whole layer-2 A operand of a tile
 constexpr int KCB = 16;             // K per W2 stage (one UMMA k-step)
 constexpr int NCHB = TC_HID / KCB;  // 16 W2 stages per tile-step
-constexpr int NB = 3;               // W2 ring depth
+constexpr int NB_MAX = 3;           // W2 ring depth (TcCfg<NS>::NB stages are used)
 constexpr int A_HALF = TCM * KC2 * 2;       // 8 KB  (a1 or a2 image of a stage)
 constexpr int B_HALF = TC_HID * KCB * 2;    // 8 KB  (b1 or b2 image of a stage)
 constexpr int A_LBO = TCM * 16, B_LBO = TC_HID * 16, SBO = 128;
@@ -81,21 +84,22 @@ constexpr int W1_HALF = TC_HID * 16 * 2;    // 8 KB
 // launch regs * warps >= sum of the budgets below, or setmaxnreg.inc never returns; and all four warps of a
 // warpgroup must execute the same setmaxnreg (the {MMA, TMA, idle, idle} group shares MISC_REGS).
 template <int NS> struct TcCfg;
-template <> struct TcCfg<2> { static constexpr int THREADS = 640, ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40; };   // launch 96*20 = 1920 >= 8*152 + 8*64 + 4*40
-template <> struct TcCfg<3> { static constexpr int THREADS = 768, ENV_REGS = 112, EPI_REGS = 56, MISC_REGS = 32; };   // launch 80*24 = 1920 = 12*112 + 8*56 + 4*32
+template <> struct TcCfg<2> { static constexpr int THREADS = 640, ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40, NB = 3; };   // launch 96*20 = 1920 >= 8*152 + 8*64 + 4*40
+template <> struct TcCfg<3> { static constexpr int THREADS = 768, ENV_REGS = 112, EPI_REGS = 56, MISC_REGS = 32, NB = 3; };   // launch 80*24 = 1920 = 12*112 + 8*56 + 4*32
+template <> struct TcCfg<4> { static constexpr int THREADS = 896, ENV_REGS = 88, EPI_REGS = 56, MISC_REGS = 40, NB = 2; };    // launch 72*28 = 2016 = 16*88 + 8*56 + 4*40; the 4th slot's 8 KB come out of the W2 ring
 constexpr int W2P_BYTES = NCHB * 2 * B_HALF;   // 256 KB packed W2 (hi/lo k-step images)
 constexpr int W1P_BYTES = 2 * W1_HALF;
 
 struct TcBars {
   unsigned long long xfull[4], logits[4];
   unsigned long long h1full[2], h1free[2], h2full[2], h2free[2];   // per TMEM buffer
-  unsigned long long afull[NCH], afree[NCH], bfull[NB], bfree[NB];
+  unsigned long long afull[NCH], afree[NCH], bfull[NB_MAX], bfree[NB_MAX];
   uint32_t tmem_slot;
 };
 
 template <int ID, int NS>
 struct TcSmem {
-  alignas(128) unsigned char bstage[NB][2 * B_HALF];     //  48 KB
+  alignas(128) unsigned char bstage[TcCfg<NS>::NB][2 * B_HALF];     //  48 KB (NS = 4: 32 KB)
   alignas(128) unsigned char astage[NCH][2 * A_HALF];    // 128 KB
   alignas(128) unsigned char w1p[W1P_BYTES];             //  16 KB
   alignas(128) unsigned char xop[NS][2 * X_HALF];        //   8 KB per slot; doubles as the slot's logits [2A][128] f32
@@ -173,7 +177,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   using S = TcSmem<ID, NS>;
   using CFG = TcCfg<NS>;
   constexpr int D = E::D, A = E::A, A2 = 2 * A;
-  constexpr int TC_THREADS = CFG::THREADS;
+  constexpr int TC_THREADS = CFG::THREADS, NB = CFG::NB;
   constexpr int W_EPI1 = 4 * NS, W_EPI2 = 4 * NS + 4, W_MMA = 4 * NS + 8, W_TMA = 4 * NS + 9;
   static_assert(D < 16, "layer-1 K block holds obs + bias column");
   static_assert(A2 * TCM * 4 <= X_HALF && 8 * TCM * 4 <= X_HALF, "logits and partial sums alias the two halves of the X-operand region");
@@ -627,7 +631,7 @@ extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_a
   if ((reinterpret_cast<uintptr_t>(w2p) & 15) || (reinterpret_cast<uintptr_t>(w1p) & 15)) { set_error("rollout_fused_tc: packed weights must be 16-byte aligned"); return MSACL_ERR_BAD_ARG; }
   const int64_t tiles = (st->n + TCM - 1) / TCM;
   MSACL_DISPATCH_ENV(st->env_id, {
-    constexpr int NS = 3;      // tile slots in flight (shared memory holds the resident A operand + 3 X/logits slots)
+    constexpr int NS = MSACL_TC_NS(ID);      // tile slots in flight
     static_assert(sizeof(TcSmem<ID, NS>) + 128 <= 232448, "shared-memory layout exceeds the 227 KB per-CTA limit");
     const int64_t groups = (tiles + NS - 1) / NS;
     const unsigned grid = (unsigned)(groups < kNumSMs ? groups : kNumSMs);

@@ -76,28 +76,64 @@ class ActorWeights:
 
 
 class TransitionBuffers:
-    """[(H + K), n, .] transition store: H = n_step - 1 history slices + K new slices."""
+    """Transition store of one rollout: for every field a `[H + M*K, n, .]` array, H = n_step - 1 history slices.
 
-    def __init__(self, spec, n, K, n_step, device):
+    Launch j writes the K slices of chunk j % M; the H slices in front of a chunk are the tail of the previous
+    chunk, so n-step windows that straddle two launches are contiguous in memory without copying.  Only when the
+    chunk index wraps (every M launches) the last H slices are carried back to the front.  `obs`, `act`, ... and
+    `fields()` are views of the *current* window `[H + K, n, .]` (history first, the K new slices at `[H:]`), so
+    consumers index them exactly as if the store were `[(H + K), n, .]` rolled after every launch (M = 1)."""
+
+    NAMES = ("obs", "act", "rew", "cost", "obs2", "done", "logp", "emit")
+
+    def __init__(self, spec, n, K, n_step, device, chunks=None):
         self.H, self.K, self.n = n_step - 1, K, n
-        T = self.H + K
+        slice_bytes = n * (4 * (2 * spec.obs_dim + spec.act_dim + 3) + 2)
+        if chunks is None:
+            chunks = 4
+            if torch.device(device).type == "cuda":      # keep the store below a fifth of the free device memory
+                free, _ = torch.cuda.mem_get_info(device)
+                while chunks > 1 and (self.H + chunks * K) * slice_bytes > 0.2 * free:
+                    chunks -= 1
+        self.M = max(1, int(chunks))
+        T = self.H + self.M * K
         f = lambda *s: torch.zeros(T, n, *s, dtype=torch.float32, device=device)
         b = lambda: torch.zeros(T, n, dtype=torch.uint8, device=device)
-        self.obs, self.act, self.rew, self.cost = f(spec.obs_dim), f(spec.act_dim), f(), f()
-        self.obs2, self.done, self.logp, self.emit = f(spec.obs_dim), b(), f(), b()
+        self._full = dict(obs=f(spec.obs_dim), act=f(spec.act_dim), rew=f(), cost=f(), obs2=f(spec.obs_dim), done=b(),
+                          logp=f(), emit=b())
+        self._j = self.M - 1          # the first roll_history() wraps to chunk 0
+
+    def _view(self, name):
+        base = self._j * self.K
+        return self._full[name][base:base + self.H + self.K]
+
+    obs = property(lambda self: self._view("obs"))
+    act = property(lambda self: self._view("act"))
+    rew = property(lambda self: self._view("rew"))
+    cost = property(lambda self: self._view("cost"))
+    obs2 = property(lambda self: self._view("obs2"))
+    done = property(lambda self: self._view("done"))
+    logp = property(lambda self: self._view("logp"))
+    emit = property(lambda self: self._view("emit"))
 
     def fields(self):
-        return dict(obs=self.obs, act=self.act, rew=self.rew, cost=self.cost, obs2=self.obs2, done=self.done,
-                    logp=self.logp, emit=self.emit)
+        return {k: self._view(k) for k in self.NAMES}
 
     def desc(self, t0=0):
         return _lib.Transitions(**{k: v[t0:].data_ptr() for k, v in self.fields().items()})
 
     def roll_history(self):
+        """Advance to the next chunk (called once before every launch)."""
+        self._j += 1
+        if self._j < self.M:
+            return
+        self._j = 0
         if self.H == 0:
             return
-        for v in self.fields().values():
-            v[:self.H].copy_(v[self.K:self.K + self.H].clone() if self.K < self.H else v[self.K:self.K + self.H])
+        src0 = self.M * self.K                          # tail of the last chunk -> history of chunk 0
+        for v in self._full.values():
+            src = v[src0:src0 + self.H]
+            v[:self.H].copy_(src.clone() if src0 < self.H else src)
 
 
 class DeviceWindowBatch:
