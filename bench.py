@@ -251,9 +251,8 @@ def main():
         buf.add_batch(batch)                             # n-step windows -> device replay ring
         sub = buf.sample_batch(Bq)                       # replay batch for the learner
         stats = ro.stats[:8].clone()
-        if world > 1:                                    # NCCL: replay-batch all-gather + episode statistics all-reduce
-            sub = mdist.all_gather_replay_batch(sub)
-            stats = mdist.all_reduce_stats(stats)
+        if world > 1:                                    # NCCL: replay-batch all-gather + episode statistics sum, one bucket
+            sub, stats = mdist.exchange_batch_and_stats(sub, stats)
         for k in host_batch:                             # D2H: the replay batch + statistics
             host_batch[k].copy_(sub[k], non_blocking=True)
         host_stats.copy_(stats, non_blocking=True)
@@ -382,7 +381,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps, "gpu_launches_per_step": 5,
                     "what": "per step: H2D actor weights (pinned) -> sampler rollout -> buffer.add_batch (device window scatter) -> "
-                            "buffer.sample_batch -> [NCCL all-gather/all-reduce if N>1] -> D2H replay batch + episode stats (pinned)"},
+                            "buffer.sample_batch -> [one packed NCCL all-gather of the sub-batches + statistics if N>1] -> D2H replay batch + episode stats (pinned)"},
             "roofline": roofline,
         }
         if cpu is not None:

@@ -39,6 +39,31 @@ def all_gather_replay_batch(sub_batch):
     return out
 
 
+def exchange_batch_and_stats(sub_batch, stats):
+    """One collective per chunk instead of eight: the per-rank replay sub-batch {field: [B/G, n, ...]} (float32) and
+    the [8] float64 statistics vector are packed into one buffer, all-gathered once, and unpacked into the global
+    batch {field: [B, n, ...]} (rank order, as `all_gather_replay_batch`) and the rank-summed statistics (as
+    `all_reduce_stats`; summed in rank order, so the result is identical on every rank).  NVSwitch makes the cost of
+    these small exchanges launch latency, not bandwidth, hence the single bucket."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return sub_batch, stats
+    world = dist.get_world_size()
+    keys = sorted(sub_batch)
+    parts = [sub_batch[k].contiguous().float().reshape(-1) for k in keys]
+    st32 = stats.detach().to(torch.float64).contiguous().view(torch.float32)         # 8 doubles -> 16 floats, bit-exact
+    packed = torch.cat(parts + [st32.to(parts[0].device)])
+    flat = torch.empty(world * packed.numel(), dtype=torch.float32, device=packed.device)
+    dist.all_gather_into_tensor(flat, packed)
+    full = flat.view(world, packed.numel())
+    out, off = {}, 0
+    for k, p in zip(keys, parts):
+        shape = tuple(sub_batch[k].shape)
+        out[k] = full[:, off:off + p.numel()].reshape((world * shape[0],) + shape[1:])
+        off += p.numel()
+    stats_all = full[:, off:off + st32.numel()].contiguous().view(torch.float64)      # [world, 8]
+    return out, stats_all.sum(dim=0)
+
+
 def episode_summary(stats):
     """Host dict from a (reduced) statistics vector."""
     s = stats.detach().cpu().tolist()

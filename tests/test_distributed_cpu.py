@@ -30,6 +30,10 @@ def _worker(rank, world, port, q):
     red = mdist.all_reduce_stats(stats)
     sub = {"obs": torch.full((3, 4, 2), float(rank)), "rew": torch.full((3, 4), float(rank) + 0.5)}
     full = mdist.all_gather_replay_batch(sub)
+    # the single-bucket exchange must give exactly what the two separate collectives give
+    full2, red2 = mdist.exchange_batch_and_stats(sub, stats)
+    assert sorted(full2) == sorted(full) and all(torch.equal(full2[k], full[k]) for k in full)
+    assert torch.equal(red2, red) and red2.dtype == torch.float64
     q.put((rank, red.tolist(), {k: v.tolist() for k, v in full.items()}, mdist.episode_summary(red)))
     dist.destroy_process_group()
 
