@@ -168,13 +168,13 @@ class FusedRollout:
     """Owns env state + transition buffers and launches msacl_rollout_fused."""
 
     def __init__(self, env_name, num_envs, horizon, n_step=20, reward_scale=100.0, cost_scale=100.0, seed=0, env_base=0,
-                 device="cuda", max_step=None, state=None, engine="ffma"):
+                 device="cuda", max_step=None, state=None, engine="ffma", history_chunks=None):
         self.engine = engine
         self.spec = get_spec(env_name)
         self.state = state or EnvStateBuffers(env_name, num_envs, seed=seed, env_base=env_base, device=device, max_step=max_step)
         self.n, self.K, self.n_step = self.state.n, int(horizon), int(n_step)
         self.reward_scale, self.cost_scale = float(reward_scale), float(cost_scale)
-        self.tr = TransitionBuffers(self.spec, self.n, self.K, self.n_step, self.state.device)
+        self.tr = TransitionBuffers(self.spec, self.n, self.K, self.n_step, self.state.device, chunks=history_chunks)
         self.stats = torch.zeros(32, dtype=torch.float64, device=self.state.device)   # [0:8) documented, rest diagnostic
         self.global_step = 0
 

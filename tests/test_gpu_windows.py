@@ -58,9 +58,12 @@ def test_window_store_matches_oracle_ring(name, ring_size):
     assert set(b) == set(FIELDS) and b["obs"].shape == (64, n_step, spec.obs_dim) and b["rew"].shape == (64, n_step)
 
 
-def test_ring_from_reference_golden_transitions():
+@pytest.mark.parametrize("chunks", [1, 2, None])
+def test_ring_from_reference_golden_transitions(chunks):
     """Feed the reference sampler's recorded per-step transitions through the device scatter and
-    compare the ring with the reference NstepReplayBuffer's arrays bit for bit."""
+    compare the ring with the reference NstepReplayBuffer's arrays bit for bit.  chunks = number of K-slice chunks
+    of the transition store (1: history copied before every launch; 2 / default 4: carried over only when the chunk
+    index wraps -- the run is long enough to wrap several times)."""
     from msacl_b200 import _lib
     from msacl_b200.buffer import B200NstepReplayBuffer
     from msacl_b200.sampler import DeviceWindowBatch, TransitionBuffers
@@ -71,8 +74,9 @@ def test_ring_from_reference_golden_transitions():
         T, N = g["step_eps"].shape[:2]
         n_step = int(g["n_step"])
         buf = B200NstepReplayBuffer(obs_dim=spec.obs_dim, act_dim=spec.act_dim, buffer_max_size=int(g["ring"]), n_step=n_step)
-        K = 8
-        tr = TransitionBuffers(spec, N, K, n_step, torch.device("cuda"))
+        K = 4
+        tr = TransitionBuffers(spec, N, K, n_step, torch.device("cuda"), chunks=chunks)
+        assert tr.M == (chunks or 4) and T // K > 2 * tr.M
         for c in range(T // K):
             tr.roll_history()
             sl = slice(c * K, (c + 1) * K)
@@ -97,3 +101,31 @@ def test_host_store_path_and_ram():
     assert buf.ptr == 2 and buf.size == 3
     assert buf.n_step_buf["rew"][:, 0].cpu().tolist() == [3.0, 4.0, 2.0]
     assert buf.__get_RAM__() == round(3 * 4 * (2 + 1 + 1 + 1 + 2 + 1 + 1) * 4 / 2 ** 20, 2)
+
+
+def test_chunked_transition_store_equals_rolled_store():
+    """Same rollout, history copied before every launch (1 chunk) vs carried over only on wrap (3 chunks): the new
+    transition slices, the stored windows and the ring bookkeeping must be bit-identical over several wraps."""
+    from msacl_b200.buffer import B200NstepReplayBuffer
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    from msacl_b200.specs import get_spec
+    name, n, K, n_step = "Pendulum", 300, 3, 5
+    spec = get_spec(name)
+    torch.manual_seed(3)
+    lin = [torch.nn.Linear(spec.obs_dim, 256), torch.nn.Linear(256, 256), torch.nn.Linear(256, 2 * spec.act_dim)]
+    aw = ActorWeights([(l.weight, l.bias) for l in lin])
+    ros = [FusedRollout(name, n, K, n_step=n_step, seed=11, engine="tc", history_chunks=m) for m in (1, 3)]
+    bufs = [B200NstepReplayBuffer(obs_dim=spec.obs_dim, act_dim=spec.act_dim, buffer_max_size=4096, n_step=n_step) for _ in ros]
+    for ro in ros:
+        ro.state.reset()
+    assert [ro.tr.M for ro in ros] == [1, 3]
+    for launch in range(8):
+        batches = [ro.run(aw) for ro in ros]
+        fa, fb = (ro.tr.fields() for ro in ros)
+        for k in fa:
+            assert torch.equal(fa[k], fb[k]), (launch, k)          # history + new slices of the current window
+        cnt = [int(b.add_batch(x).item()) for b, x in zip(bufs, batches)]
+        assert cnt[0] == cnt[1] and (bufs[0].ptr, bufs[0].size) == (bufs[1].ptr, bufs[1].size)
+    assert bufs[0].size > 0
+    for k in FIELDS:
+        assert torch.equal(bufs[0].n_step_buf[k], bufs[1].n_step_buf[k]), k
