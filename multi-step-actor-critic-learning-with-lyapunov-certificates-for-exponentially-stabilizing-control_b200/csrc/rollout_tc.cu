@@ -247,6 +247,16 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       if (owner) e.load(st, gi);
       write_xop(e.obs(), owner);
       for (int k = 0; k < K; ++k) {
+        // the action noise of this step does not depend on the logits: draw it while the tile's MLP is still running
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (owner && !deterministic) {
+          if (eps) {
+#pragma unroll
+            for (int j = 0; j < A; ++j) z[j] = eps[((int64_t)k * st.n + gi) * A + j];
+          } else {
+            action_noise4(st.seed, st.env_base + (uint64_t)gi, step_base + (uint32_t)k, z);
+          }
+        }
 #ifdef MSACL_TC_TIMING
         const long long t_w0 = clock64();
 #endif
@@ -267,15 +277,6 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           if (out.obs) {
 #pragma unroll
             for (int d = 0; d < D; ++d) out.obs[row * D + d] = e.obs()[d];
-          }
-          float z[4] = {0.f, 0.f, 0.f, 0.f};
-          if (!deterministic) {
-            if (eps) {
-#pragma unroll
-              for (int j = 0; j < A; ++j) z[j] = eps[row * A + j];
-            } else {
-              action_noise4(st.seed, st.env_base + (uint64_t)gi, step_base + (uint32_t)k, z);
-            }
           }
           float act[A];
           float lp_gauss = 0.f, lp_tanh = 0.f, lp_scale = 0.f;
