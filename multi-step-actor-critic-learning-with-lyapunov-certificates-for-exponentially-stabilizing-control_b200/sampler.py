@@ -231,7 +231,8 @@ class B200NstepOffSampler:
         self.total_sample_number = 0
         # actor engine: "tc" = tcgen05 split-bf16 tensor cores (default), "ffma" = FP32 FFMA (bit-closer to torch fp32)
         self.rollout = FusedRollout(self.env_id, self.num_envs, self.horizon, self.n_step, self.reward_scale, self.cost_scale,
-                                    device=self.device, state=self.envs.state, engine=kwargs.get("rollout_engine", "tc"))
+                                    device=self.device, state=self.envs.state, engine=kwargs.get("rollout_engine", "tc"),
+                                    history_chunks=kwargs.get("history_chunks"))
         self.envs.state.reset()        # base.py:98  envs.reset(seed=None)
         self._actor = None
 
