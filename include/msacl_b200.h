@@ -192,6 +192,13 @@ int msacl_stability_advantage(int64_t B, int32_t n, const float* lya_obs0, const
                               void* stream);
 int msacl_advantage_normalize(int64_t B, const float* adv_raw, const double* moments, float* adv, void* stream);
 
+/* Soft target update of a whole parameter list in one launch (RL/algorithm/msacl.py:445-460):
+ * dst[t][i] = dst[t][i] * polyak + one_minus * src[t][i] for t < count, i < numel[t], with the reference's three
+ * float32 roundings (bit-exact with `p_targ.mul_(polyak); p_targ.add_((1 - polyak) * p)`).
+ * src / dst / numel are DEVICE arrays (pointer tables of length count); max_numel = max_t numel[t] sizes the grid. */
+int msacl_polyak_update(int32_t count, const float* const* src, float* const* dst, const int64_t* numel,
+                        int64_t max_numel, float polyak, float one_minus, void* stream);
+
 /* Device FP32 FFMA peak probes used by bench.py for the roofline denominator.
  * mode 0: independent FFMA chains with immediate operands (pipe peak);
  * mode 1: register-resident 8x8 outer-product accumulation, i.e. a register-tiled SGEMM inner

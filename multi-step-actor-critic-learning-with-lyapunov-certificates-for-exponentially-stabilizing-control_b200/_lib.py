@@ -64,6 +64,7 @@ SIGNATURES = {
     "msacl_stability_advantage": (C.c_int, [C.c_int64, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
     "msacl_advantage_normalize": (C.c_int, [C.c_int64, vp, vp, vp, vp]),
     "msacl_selftest_tc_gemm": (C.c_int, [vp, vp, vp, C.c_int32, vp]),
+    "msacl_polyak_update": (C.c_int, [C.c_int32, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp]),
     "msacl_ffma_probe": (C.c_int, [C.c_int32, C.c_int32, vp, c_f64p, vp]),
     "msacl_umma_probe": (C.c_int, [C.c_int32, C.c_int32, vp, vp]),
 }

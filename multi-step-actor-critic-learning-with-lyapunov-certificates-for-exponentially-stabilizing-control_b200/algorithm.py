@@ -228,13 +228,14 @@ class B200MSACL:
                 net.log_alpha.clamp_(max=math.log(self.alpha_bound))
 
     def _target_update(self):
+        """msacl.py:445-460 as one multi-tensor kernel launch (bit-exact with the per-tensor mul_/add_ pair)."""
         net = self.networks
-        with torch.no_grad():
-            polyak = 1 - self.tau
-            for src, dst in ((net.q1, net.q1_target), (net.q2, net.q2_target)):
-                for p, pt in zip(src.parameters(), dst.parameters()):
-                    pt.data.mul_(polyak)
-                    pt.data.add_((1 - polyak) * p.data)
+        pairs = [(p.data, pt.data) for src, dst in ((net.q1, net.q1_target), (net.q2, net.q2_target))
+                 for p, pt in zip(src.parameters(), dst.parameters())]
+        key = tuple((p.data_ptr(), pt.data_ptr()) for p, pt in pairs)
+        if getattr(self, "_polyak_key", None) != key:          # first call, or a network was replaced / moved
+            self._polyak, self._polyak_key = tg.PolyakUpdater(pairs), key
+        self._polyak.step(self.tau)
 
 
 MSACL = B200MSACL

@@ -156,6 +156,21 @@ adv_normalize_kernel(int64_t B, const float* __restrict__ adv_raw, const double*
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) adv[i] = (adv_raw[i] - fmean) / denom;
 }
 
+// Soft (Polyak) target update over a whole parameter list in ONE launch (RL/algorithm/msacl.py:445-460 does
+// `p_targ.mul_(polyak); p_targ.add_((1 - polyak) * p)` per tensor: ~24 tiny launches per iteration).  blockIdx.y = tensor,
+// grid-stride over its elements; the three float32 roundings of the reference expression are kept (no FMA).
+__global__ void __launch_bounds__(256)
+polyak_update_kernel(const float* const* __restrict__ src, float* const* __restrict__ dst, const int64_t* __restrict__ numel,
+                     float polyak, float one_minus) {
+  const int t = blockIdx.y;
+  const float* __restrict__ s = src[t];
+  float* __restrict__ d = dst[t];
+  const int64_t n = numel[t];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    d[i] = __fadd_rn(__fmul_rn(d[i], polyak), __fmul_rn(one_minus, s[i]));
+}
+
 // FP32 FFMA peak probes (roofline denominators for the fused rollout kernel).
 //  mode 0: 8 independent accumulator chains per thread, multiplier/addend are compile-time
 //          constants (ptxas emits the immediate form) -- the best case the FMA pipe can do.
@@ -327,6 +342,15 @@ extern "C" int msacl_advantage_normalize(int64_t B, const float* adv_raw, const 
   if (B <= 1 || !adv_raw || !moments || !adv) { set_error("advantage_normalize: bad argument"); return MSACL_ERR_BAD_ARG; }
   adv_normalize_kernel<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, adv_raw, moments, adv);
   return check_launch("advantage_normalize");
+}
+
+extern "C" int msacl_polyak_update(int32_t count, const float* const* src, float* const* dst, const int64_t* numel,
+                                   int64_t max_numel, float polyak, float one_minus, void* stream) {
+  if (count <= 0 || count > 65535 || !src || !dst || !numel || max_numel <= 0) { set_error("polyak_update: bad argument"); return MSACL_ERR_BAD_ARG; }
+  const int64_t want = (max_numel + 255) / 256;
+  const dim3 grid((unsigned)(want < 64 ? want : 64), (unsigned)count);
+  polyak_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, numel, polyak, one_minus);
+  return check_launch("polyak_update");
 }
 
 extern "C" int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, void* stream) {

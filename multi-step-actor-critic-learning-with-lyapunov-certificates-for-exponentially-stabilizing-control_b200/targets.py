@@ -6,6 +6,7 @@ autograd Functions where the reference back-propagates through them.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -94,3 +95,33 @@ def clipped_surrogate(new_logp0, old_logp0, adv, clip_coef=0.1):
     surr1 = ratio * adv
     surr2 = torch.clamp(ratio, 1 - clip_coef, 1 + clip_coef) * adv
     return torch.min(surr1, surr2).mean()
+
+
+class PolyakUpdater:
+    """Soft target update `p_targ <- p_targ * polyak + (1 - polyak) * p` over whole parameter lists in one kernel
+    launch (msacl.py:445-460), bit-exact with the reference's per-tensor `mul_` / `add_` pair.  The device pointer
+    tables are built once; parameters must keep their storage (optimizers update in place)."""
+
+    def __init__(self, pairs):
+        pairs = [(p, pt) for p, pt in pairs]
+        if not pairs:
+            raise ValueError("no parameters")
+        for p, pt in pairs:
+            if not (p.is_cuda and pt.is_cuda and p.dtype == pt.dtype == torch.float32 and p.is_contiguous() and pt.is_contiguous()
+                    and p.numel() == pt.numel()):
+                raise ValueError("PolyakUpdater needs matching contiguous CUDA float32 parameter pairs")
+        self._pairs = pairs
+        dev = pairs[0][0].device
+        self._src = torch.tensor([p.data_ptr() for p, _ in pairs], dtype=torch.int64, device=dev)
+        self._dst = torch.tensor([pt.data_ptr() for _, pt in pairs], dtype=torch.int64, device=dev)
+        self._numel = torch.tensor([p.numel() for p, _ in pairs], dtype=torch.int64, device=dev)
+        self._max = max(p.numel() for p, _ in pairs)
+        self._ptrs = [(p.data_ptr(), pt.data_ptr()) for p, pt in pairs]
+
+    def step(self, tau):
+        if any((p.data_ptr(), pt.data_ptr()) != q for (p, pt), q in zip(self._pairs, self._ptrs)):
+            raise RuntimeError("a parameter changed its storage since the PolyakUpdater was built")
+        polyak = 1 - tau
+        _lib.check(_lib.load().msacl_polyak_update(len(self._pairs), self._src.data_ptr(), self._dst.data_ptr(), self._numel.data_ptr(),
+                                                  self._max, float(np.float32(polyak)), float(np.float32(1 - polyak)),
+                                                  _lib.current_stream()))

@@ -98,3 +98,24 @@ def test_policy_loss_reference_golden():
     _, oadv = otg.stability_advantage(g["pol_lya_obs0"], g["pol_lya_obs2"], coefs)
     _, ograd = otg.clipped_surrogate(g["pol_new_logp0"], g["logp"][:, 0], oadv, 0.1)
     np.testing.assert_allclose(new_logp0.grad.cpu().numpy(), ograd, rtol=1e-4, atol=1e-7)
+
+
+def test_polyak_update_multi_tensor_bit_exact():
+    """One-launch soft target update vs the reference's per-tensor `mul_` / `add_` pair (msacl.py:445-460)."""
+    from msacl_b200.targets import PolyakUpdater
+    g = torch.Generator(device="cuda").manual_seed(5)
+    shapes = [(256, 6), (256,), (256, 256), (1, 256), (1,), (257, 3), (65536 + 3,)]
+    src = [torch.randn(*s, device="cuda", generator=g) for s in shapes]
+    dst = [torch.randn(*s, device="cuda", generator=g) for s in shapes]
+    ref = [d.clone() for d in dst]
+    up = PolyakUpdater(list(zip(src, dst)))
+    for tau in (0.005, 0.005, 0.1):
+        polyak = 1 - tau
+        for p, pt in zip(src, ref):
+            pt.mul_(polyak)
+            pt.add_((1 - polyak) * p)
+        up.step(tau)
+        for a, b in zip(dst, ref):
+            assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        PolyakUpdater([(src[0], dst[1])])
