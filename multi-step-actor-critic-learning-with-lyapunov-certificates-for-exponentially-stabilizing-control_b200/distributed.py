@@ -64,6 +64,28 @@ def exchange_batch_and_stats(sub_batch, stats):
     return out, stats_all.sum(dim=0)
 
 
+def mean_std_over_ranks(*per_instance):
+    """Mean and population std of per-instance values whose instances are sharded over ranks (evaluator: one value per
+    evaluation episode).  One all-reduce of the float64 moments [N, sum x_j, sum x_j^2 ...]; single-process: two-pass
+    torch mean/std.  Returns [(mean, std), ...] as Python floats, identical on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [(float(x.mean()), float(x.std(unbiased=False))) for x in per_instance]
+    dev = per_instance[0].device
+    m = [torch.tensor(float(per_instance[0].numel()), dtype=torch.float64, device=dev)]
+    for x in per_instance:
+        x = x.double()
+        m += [x.sum(), (x * x).sum()]
+    m = torch.stack(m)
+    dist.all_reduce(m, op=dist.ReduceOp.SUM)
+    n = m[0]
+    out = []
+    for j in range(len(per_instance)):
+        mean = m[1 + 2 * j] / n
+        var = torch.clamp(m[2 + 2 * j] / n - mean * mean, min=0.0)
+        out.append((float(mean), float(var.sqrt())))
+    return out
+
+
 def episode_summary(stats):
     """Host dict from a (reduced) statistics vector."""
     s = stats.detach().cpu().tolist()

@@ -3,9 +3,14 @@
 distribution's mode() action (act_distribution_cls.py:90-95) until every instance has finished its FIRST
 episode; per instance the scaled reward / cost are averaged over the steps of that episode, and the mean
 and (population) std over instances are returned: (TRM, TRS, TCM, TCS).
+With torch.distributed initialised (one process per GPU) the `num_eval_episode` instances are sharded over the ranks
+(global instance ids key the resets, so the set of episodes does not depend on the number of GPUs) and the statistics
+are combined with one all-reduce of the float64 moments; every rank returns the same four numbers.
 """
 import torch
+import torch.distributed as dist
 
+from . import distributed as mdist
 from .sampler import ActorWeights, FusedRollout
 
 
@@ -20,6 +25,7 @@ class B200Evaluator:
         self.max_step = kwargs.get("max_step")
         self.networks = kwargs.get("networks")
         self.seed = int(kwargs.get("eval_env_seed") or 0)
+        self.distributed = bool(kwargs.get("distributed", True))     # shard the episodes over torch.distributed ranks
         self._resets = 0
 
     def load_state_dict(self, state_dict):
@@ -27,9 +33,13 @@ class B200Evaluator:
 
     def run_parallel_episodes(self, actor: ActorWeights = None, state_init=None):
         actor = actor or ActorWeights.from_policy(self.networks.policy, device=self.device)
-        n = self.num_eval_episode
+        lo, hi = 0, self.num_eval_episode
+        sharded = self.distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if sharded:
+            lo, hi = mdist.shard_env_range(self.num_eval_episode, dist.get_rank(), dist.get_world_size())
+        n = max(hi - lo, 1)       # (a rank without instances still takes part in the all-reduce with one dummy env)
         ro = FusedRollout(self.env_id, n, self.chunk, n_step=1, reward_scale=self.reward_scale, cost_scale=self.cost_scale,
-                          seed=self.seed, device=self.device, max_step=self.max_step, engine=self.engine)
+                          seed=self.seed, env_base=lo, device=self.device, max_step=self.max_step, engine=self.engine)
         ro.state.episode.fill_(self._resets)          # envs.reset(seed=None): a fresh set of initial states per call
         self._resets += 1
         ro.state.reset()
@@ -52,7 +62,12 @@ class B200Evaluator:
             finished |= cum[-1] > 0
             steps += self.chunk
         ep_ret, ep_cost = ret_sum / count, cost_sum / count
-        return (float(ep_ret.mean()), float(ep_ret.std(unbiased=False)), float(ep_cost.mean()), float(ep_cost.std(unbiased=False)))
+        if hi - lo == 0:                                     # dummy instance of an empty shard: contributes nothing
+            ep_ret, ep_cost = ep_ret[:0], ep_cost[:0]
+        if not sharded:
+            return (float(ep_ret.mean()), float(ep_ret.std(unbiased=False)), float(ep_cost.mean()), float(ep_cost.std(unbiased=False)))
+        (trm, trs), (tcm, tcs) = mdist.mean_std_over_ranks(ep_ret, ep_cost)
+        return (trm, trs, tcm, tcs)
 
     def run_evaluation(self, iteration=0):
         return self.run_parallel_episodes()

@@ -34,6 +34,12 @@ def _worker(rank, world, port, q):
     full2, red2 = mdist.exchange_batch_and_stats(sub, stats)
     assert sorted(full2) == sorted(full) and all(torch.equal(full2[k], full[k]) for k in full)
     assert torch.equal(red2, red) and red2.dtype == torch.float64
+    # evaluator statistics: instances sharded over ranks, moments combined with one all-reduce
+    allv = torch.arange(10, dtype=torch.float64) ** 1.5
+    lo, hi = mdist.shard_env_range(10, rank, world)
+    (m, sd), (m2, sd2) = mdist.mean_std_over_ranks(allv[lo:hi], -2.0 * allv[lo:hi])
+    assert abs(m - float(allv.mean())) < 1e-12 and abs(sd - float(allv.std(unbiased=False))) < 1e-12
+    assert abs(m2 + 2.0 * float(allv.mean())) < 1e-12 and abs(sd2 - 2.0 * float(allv.std(unbiased=False))) < 1e-12
     q.put((rank, red.tolist(), {k: v.tolist() for k, v in full.items()}, mdist.episode_summary(red)))
     dist.destroy_process_group()
 
