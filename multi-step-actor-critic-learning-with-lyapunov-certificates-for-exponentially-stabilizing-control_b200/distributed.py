@@ -64,6 +64,20 @@ def exchange_batch_and_stats(sub_batch, stats):
     return out, stats_all.sum(dim=0)
 
 
+def broadcast_parameters(module_or_tensors, src=0):
+    """Learner -> rollout ranks: broadcast a module's parameters (e.g. `networks.policy`, 285 KB) from rank `src`
+    in ONE collective (flattened bucket) and copy them back in place, so that every rank samples with the same actor."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    tensors = [p.data for p in module_or_tensors.parameters()] if hasattr(module_or_tensors, "parameters") else list(module_or_tensors)
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.broadcast(flat, src=src)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+
+
 def mean_std_over_ranks(*per_instance):
     """Mean and population std of per-instance values whose instances are sharded over ranks (evaluator: one value per
     evaluation episode).  One all-reduce of the float64 moments [N, sum x_j, sum x_j^2 ...]; single-process: two-pass

@@ -34,6 +34,13 @@ def _worker(rank, world, port, q):
     full2, red2 = mdist.exchange_batch_and_stats(sub, stats)
     assert sorted(full2) == sorted(full) and all(torch.equal(full2[k], full[k]) for k in full)
     assert torch.equal(red2, red) and red2.dtype == torch.float64
+    # learner -> rollout ranks weight broadcast (one bucket)
+    torch.manual_seed(100 + rank)
+    pol = torch.nn.Sequential(torch.nn.Linear(3, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2))
+    torch.manual_seed(100)
+    want = torch.nn.Sequential(torch.nn.Linear(3, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2))
+    mdist.broadcast_parameters(pol, src=0)
+    assert all(torch.equal(a, b) for a, b in zip(pol.parameters(), want.parameters()))
     # evaluator statistics: instances sharded over ranks, moments combined with one all-reduce
     allv = torch.arange(10, dtype=torch.float64) ** 1.5
     lo, hi = mdist.shard_env_range(10, rank, world)
