@@ -494,7 +494,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CFG::MISC_REGS));
     if (warp == W_MMA) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_bf16(TCM, TC_HID);
       const uint32_t w1base = tc::smem_u32(sm.w1p);
       // The issuing thread is the serial resource of the tensor pipeline, so its per-k-step instruction stream is kept
@@ -587,7 +587,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
     }
     } else if (warp == W_TMA) {
     // =========================== TMA producer: W2 k-step images ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int64_t tile_steps = 0;
       for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) tile_steps += (int64_t)tiles_in_pair(pair) * K;
       const int64_t total = tile_steps * NCHB;
