@@ -4,7 +4,6 @@ The network forwards stay in PyTorch/cuBLAS (plain library GEMMs); everything be
 network outputs and the scalar losses is done by the kernels in csrc/targets.cu, wrapped as
 autograd Functions where the reference back-propagates through them.
 """
-import ctypes as C
 
 import numpy as np
 import torch

@@ -1,7 +1,7 @@
 """Small end-to-end exercise of every kernel for `compute-sanitizer --tool memcheck`."""
 import sys
 sys.path.insert(0, '/root/repo')
-import numpy as np, torch
+import torch
 import msacl_b200
 from msacl_b200 import targets as tg
 from msacl_b200.buffer import B200NstepReplayBuffer

@@ -1,6 +1,6 @@
 import sys
 sys.path.insert(0, '/root/repo')
-import numpy as np, torch
+import torch
 import msacl_b200
 from msacl_b200.sampler import ActorWeights, FusedRollout
 from msacl_b200.specs import get_spec
