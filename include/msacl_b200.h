@@ -101,7 +101,9 @@ typedef struct {
 } msacl_actor_t;
 
 /* Transition outputs of a K-step rollout, each [K][n][...] row-major.  Any pointer may be NULL
- * to skip that field. */
+ * to skip that field.  obs / obs2 / act are written one row per thread with 16-byte (row length % 4 == 0 floats) or
+ * 8-byte (even) vector stores: the pointers must be aligned accordingly (any [t][n][dim] slice of a 16-byte aligned
+ * allocation is). */
 typedef struct {
   float* obs;     /* [K][n][obs_dim]  observation the action was computed from */
   float* act;     /* [K][n][act_dim]  clipped action */

@@ -27,6 +27,30 @@ int check_launch(const char* what);
   }
 
 // register-resident state of one env instance
+// Row-per-thread store of N floats at dst[row * N ..): 16-byte (N % 4 == 0) or 8-byte (N % 2 == 0) vectors when the row
+// stride keeps them aligned (base pointers are torch allocations, >= 256-byte aligned), scalar otherwise.
+template <int N>
+__device__ __forceinline__ void store_row(float* __restrict__ dst, int64_t row, const float* v) {
+  float* p = dst + row * N;
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < N / 4; ++j) reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) reinterpret_cast<float2*>(p)[j] = make_float2(v[2 * j], v[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = v[j];
+  }
+}
+
+// host-side check matching store_row's vector width
+template <int N>
+inline bool row_store_misaligned(const void* p) {
+  constexpr uintptr_t mask = (N % 4 == 0) ? 15 : ((N % 2 == 0) ? 7 : 3);
+  return p != nullptr && (reinterpret_cast<uintptr_t>(p) & mask) != 0;
+}
+
 template <int ID>
 struct EnvRegs {
   using E = Env<ID>;

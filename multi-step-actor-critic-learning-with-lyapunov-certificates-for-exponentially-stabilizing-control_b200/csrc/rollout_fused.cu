@@ -327,8 +327,7 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
         if (owner) {
           const int64_t row = (int64_t)k * st.n + gi;
           if (out.obs) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) out.obs[row * D + d] = r.obs()[d];
+            store_row<D>(out.obs, row, r.obs());
           }
           float z[4] = {0.f, 0.f, 0.f, 0.f};
           if (!deterministic) {
@@ -375,12 +374,10 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
           r.run = min(r.run + 1, n_step);
           const bool emit = r.run >= n_step;
           if (out.act) {
-#pragma unroll
-            for (int j = 0; j < A; ++j) out.act[row * A + j] = act[j];
+            store_row<A>(out.act, row, act);
           }
           if (out.obs2) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) out.obs2[row * D + d] = r.obs()[d];        // real_next_obs (pre-reset)
+            store_row<D>(out.obs2, row, r.obs());                                  // real_next_obs (pre-reset)
           }
           if (out.rew) out.rew[row] = rew_s;
           if (out.cost) out.cost[row] = cost;
@@ -432,6 +429,10 @@ extern "C" int msacl_rollout_fused(const msacl_env_state_t* st, const msacl_acto
   const int64_t pairs = ((st->n + TM - 1) / TM + NTILE - 1) / NTILE;
   const unsigned grid = (unsigned)(pairs < kNumSMs ? pairs : kNumSMs);
   MSACL_DISPATCH_ENV(st->env_id, {
+    if (row_store_misaligned<Env<ID>::D>(out->obs) || row_store_misaligned<Env<ID>::D>(out->obs2) || row_store_misaligned<Env<ID>::A>(out->act)) {
+      set_error("rollout_fused: transition obs/obs2/act rows must be aligned to their vector width (16 B if the row length is a multiple of 4 floats, 8 B if even)");
+      return MSACL_ERR_BAD_ARG;
+    }
     const size_t smem = sizeof(Smem<ID>);
     auto kern = rollout_fused_kernel<ID>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

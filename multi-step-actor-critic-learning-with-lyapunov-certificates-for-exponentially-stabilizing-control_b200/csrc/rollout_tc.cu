@@ -275,8 +275,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         if (owner) {
           const int64_t row = (int64_t)k * st.n + gi;
           if (out.obs) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) out.obs[row * D + d] = e.obs()[d];
+            store_row<D>(out.obs, row, e.obs());
           }
           float act[A];
           float lp_gauss = 0.f, lp_tanh = 0.f, lp_scale = 0.f;
@@ -326,12 +325,10 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           // stores are issued after it and drain while the MLP of this tile is already running
           if (k + 1 < K) write_xop(e.obs(), true);
           if (out.act) {
-#pragma unroll
-            for (int j = 0; j < A; ++j) out.act[row * A + j] = act[j];
+            store_row<A>(out.act, row, act);
           }
           if (out.obs2) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) out.obs2[row * D + d] = obs2[d];
+            store_row<D>(out.obs2, row, obs2);
           }
           if (out.rew) out.rew[row] = rew_s;
           if (out.cost) out.cost[row] = cost;
@@ -632,6 +629,10 @@ extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_a
   if ((reinterpret_cast<uintptr_t>(w2p) & 15) || (reinterpret_cast<uintptr_t>(w1p) & 15)) { set_error("rollout_fused_tc: packed weights must be 16-byte aligned"); return MSACL_ERR_BAD_ARG; }
   const int64_t tiles = (st->n + TCM - 1) / TCM;
   MSACL_DISPATCH_ENV(st->env_id, {
+    if (row_store_misaligned<Env<ID>::D>(out->obs) || row_store_misaligned<Env<ID>::D>(out->obs2) || row_store_misaligned<Env<ID>::A>(out->act)) {
+      set_error("rollout_fused_tc: transition obs/obs2/act rows must be aligned to their vector width (16 B if the row length is a multiple of 4 floats, 8 B if even)");
+      return MSACL_ERR_BAD_ARG;
+    }
     constexpr int NS = MSACL_TC_NS(ID);      // tile slots in flight
     static_assert(sizeof(TcSmem<ID, NS>) + 128 <= 232448, "shared-memory layout exceeds the 227 KB per-CTA limit");
     const int64_t groups = (tiles + NS - 1) / NS;
