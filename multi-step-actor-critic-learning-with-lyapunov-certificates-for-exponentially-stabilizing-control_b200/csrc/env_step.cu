@@ -72,17 +72,13 @@ env_step_kernel(msacl_env_state_t st, const float* __restrict__ action, float* _
   const bool trunc = r.step >= st.max_step;
   r.ep_return += rew;
   r.ep_len += 1;
-  if (final_obs) {
-#pragma unroll
-    for (int j = 0; j < E::D; ++j) final_obs[i * E::D + j] = r.obs()[j];
-  }
+  if (final_obs) store_row<E::D>(final_obs, i, r.obs());
   if (term || trunc) {   // gymnasium 0.28.1 SyncVectorEnv: reset in the same step
     r.episode += 1;
     r.run = 0;
     r.reset(st.seed, st.env_base + (uint64_t)i);
   }
-#pragma unroll
-  for (int j = 0; j < E::D; ++j) next_obs[i * E::D + j] = r.obs()[j];
+  store_row<E::D>(next_obs, i, r.obs());
   reward[i] = rew;
   terminated[i] = term ? 1 : 0;
   truncated[i] = trunc ? 1 : 0;
@@ -181,8 +177,13 @@ int msacl_env_step(const msacl_env_state_t* st, const float* action, float* next
   if (!action || !next_obs || !reward || !terminated || !truncated) { set_error("env_step: null buffer"); return MSACL_ERR_BAD_ARG; }
   const int threads = 128;
   const unsigned blocks = (unsigned)((st->n + threads - 1) / threads);
-  MSACL_DISPATCH_ENV(st->env_id, (env_step_kernel<ID><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                                     *st, action, next_obs, reward, terminated, truncated, final_obs)));
+  MSACL_DISPATCH_ENV(st->env_id, {
+    if (row_store_misaligned<Env<ID>::D>(next_obs) || row_store_misaligned<Env<ID>::D>(final_obs)) {
+      set_error("env_step: next_obs / final_obs rows must be aligned to their vector width (16 B if obs_dim %% 4 == 0, 8 B if even)");
+      return MSACL_ERR_BAD_ARG;
+    }
+    env_step_kernel<ID><<<blocks, threads, 0, (cudaStream_t)stream>>>(*st, action, next_obs, reward, terminated, truncated, final_obs);
+  });
   return check_launch("env_step");
 }
 
