@@ -73,7 +73,7 @@ constexpr int KC2 = 32;             // K per A stage
 constexpr int NCH = TC_HID / KC2;   // 8 A stages = the whole layer-2 A operand of a tile
 constexpr int KCB = 16;             // K per W2 stage (one UMMA k-step)
 constexpr int NCHB = TC_HID / KCB;  // 16 W2 stages per tile-step
-constexpr int NB_MAX = 3;           // W2 ring depth (TcCfg<NS>::NB stages are used)
+constexpr int NB_MAX = 4;           // W2 ring depth: see tc_ring_depth()
 constexpr int A_HALF = TCM * KC2 * 2;       // 8 KB  (a1 or a2 image of a stage)
 constexpr int B_HALF = TC_HID * KCB * 2;    // 8 KB  (b1 or b2 image of a stage)
 constexpr int A_LBO = TCM * 16, B_LBO = TC_HID * 16, SBO = 128;
@@ -97,13 +97,26 @@ struct TcBars {
   uint32_t tmem_slot;
 };
 
+// Layer-1 K block: obs (D) + bias column need 16 K columns only for the quadrotor (D + 1 = 13).  For the box envs
+// (D + 1 <= 8) the second 8-column K block of both layer-1 operands is all zero, so it is not stored per slot: the
+// operand descriptors' K-block stride (LBO) points at one shared zero block instead.  That and the narrower W3 (2A <= 4)
+// free the shared memory for a fourth W2 ring stage.
+template <int ID> __host__ __device__ constexpr bool tc_two_kblocks() { return Env<ID>::D + 1 > 8; }
+template <int ID, int NS> __host__ __device__ constexpr int tc_ring_depth() { return NS == 4 ? 2 : (tc_two_kblocks<ID>() ? 3 : 4); }
+template <int ID> __host__ __device__ constexpr int tc_w3_stride() { return 2 * Env<ID>::A > 4 ? 8 : 4; }
+
 template <int ID, int NS>
 struct TcSmem {
-  alignas(128) unsigned char bstage[TcCfg<NS>::NB][2 * B_HALF];     //  48 KB (NS = 4: 32 KB)
+  static constexpr bool X2 = tc_two_kblocks<ID>();
+  static constexpr int NB = tc_ring_depth<ID, NS>();
+  static constexpr int XH = X2 ? X_HALF : X_HALF / 2;          // bytes of the hi (or lo) image of a slot's X operand
+  static constexpr int W1H = X2 ? W1_HALF : W1_HALF / 2;       // bytes of the hi (or lo) image of the W1|b1 operand
+  alignas(128) unsigned char bstage[NB][2 * B_HALF];     //  48 KB (box envs: 64 KB)
   alignas(128) unsigned char astage[NCH][2 * A_HALF];    // 128 KB
-  alignas(128) unsigned char w1p[W1P_BYTES];             //  16 KB
-  alignas(128) unsigned char xop[NS][2 * X_HALF];        //   8 KB per slot; doubles as the slot's logits [2A][128] f32
-  alignas(16) float w3t[TC_HID * 8];       // layer-3 weights transposed: [unit n][output j] (zero padded to 8)
+  alignas(128) unsigned char w1p[2 * W1H];               //  16 KB (box envs: 8 KB)
+  alignas(128) unsigned char xop[NS][2 * XH];            //   8 KB (4 KB) per slot; doubles as the slot's logits / partial sums
+  alignas(128) unsigned char zeros[X2 ? 128 : W1_HALF / 2];   // shared all-zero second K block (box envs)
+  alignas(16) float w3t[TC_HID * tc_w3_stride<ID>()];   // layer-3 weights transposed: [unit n][output j] (zero padded)
   alignas(16) float b2[TC_HID];
   alignas(16) float b3[8];
   TcBars bars;
@@ -177,19 +190,25 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   using S = TcSmem<ID, NS>;
   using CFG = TcCfg<NS>;
   constexpr int D = E::D, A = E::A, A2 = 2 * A;
-  constexpr int TC_THREADS = CFG::THREADS, NB = CFG::NB;
-  constexpr int W_EPI1 = 4 * NS, W_EPI2 = 4 * NS + 4, W_MMA = 4 * NS + 8, W_TMA = 4 * NS + 9;
+  constexpr int TC_THREADS = CFG::THREADS, NB = S::NB, XH = S::XH, W1H = S::W1H, W3S = tc_w3_stride<ID>();
+  constexpr bool X2 = S::X2;
+  constexpr int W_EPI1 = 4 * NS, W_MMA = 4 * NS + 8, W_TMA = 4 * NS + 9;
   static_assert(D < 16, "layer-1 K block holds obs + bias column");
-  static_assert(A2 * TCM * 4 <= X_HALF && 8 * TCM * 4 <= X_HALF, "logits and partial sums alias the two halves of the X-operand region");
+  static_assert(A2 * TCM * 4 <= XH && ((A2 + 1) / 2) * 2 * TCM * 4 <= XH, "logits and partial sums alias the two halves of the X-operand region");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto logits_of = [&](int s) { return reinterpret_cast<float*>(sm.xop[s]); };              // [2A][128] f32, first half of the region
-  auto partial_of = [&](int s) { return reinterpret_cast<float*>(sm.xop[s] + X_HALF); };   // epilogue-2 partial sums, second half
+  auto partial_of = [&](int s) { return reinterpret_cast<float*>(sm.xop[s] + XH); };       // epilogue-2 partial sums, second half
 
   // ---- one-time setup
-  for (int i = tid; i < W1P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm.w1p)[i] = reinterpret_cast<const uint4*>(w1p_g)[i];
-  for (int i = tid; i < 8 * TC_HID; i += TC_THREADS) { const int n = i >> 3, j = i & 7; sm.w3t[i] = j < A2 ? actor.w3[j * TC_HID + n] : 0.f; }
+  // W1|b1 images: the packed global buffer always holds both K blocks per image; box envs keep only the first
+  for (int i = tid; i < 2 * W1H / 16; i += TC_THREADS) {
+    const int img = i / (W1H / 16), off = i % (W1H / 16);
+    reinterpret_cast<uint4*>(sm.w1p)[i] = reinterpret_cast<const uint4*>(w1p_g + (size_t)img * W1_HALF)[off];
+  }
+  for (int i = tid; i < (int)sizeof(sm.zeros) / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm.zeros)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < W3S * TC_HID; i += TC_THREADS) { const int n = i / W3S, j = i % W3S; sm.w3t[i] = j < A2 ? actor.w3[j * TC_HID + n] : 0.f; }
   for (int i = tid; i < TC_HID; i += TC_THREADS) sm.b2[i] = actor.b2[i];
   if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
   if (tid == 0) {
@@ -226,14 +245,14 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] = (k < D) ? (valid ? obs[k < D ? k : 0] : 0.f) : (k == D ? 1.f : 0.f);
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
+      for (int kb = 0; kb < (X2 ? 2 : 1); ++kb) {
         float w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j] = v[kb * 8 + j];
         uint4 hi, lo;
         split8(w, hi, lo);
         *reinterpret_cast<uint4*>(sm.xop[s] + kb * A_LBO + r * 16) = hi;
-        *reinterpret_cast<uint4*>(sm.xop[s] + X_HALF + kb * A_LBO + r * 16) = lo;
+        *reinterpret_cast<uint4*>(sm.xop[s] + XH + kb * A_LBO + r * 16) = lo;
       }
       tc::fence_async_smem();
       tc::mbar_arrive(&sm.bars.xfull[s]);
@@ -431,7 +450,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
                                fmaxf(__uint_as_float(v[4 * g + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * g + 3]) + bb.w, 0.f)};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float* wrow = &sm.w3t[(cb * 16 + 4 * g + c) * 8];      // all lanes read the same address: broadcast
+            const float* wrow = &sm.w3t[(cb * 16 + 4 * g + c) * W3S];    // all lanes read the same address: broadcast
             const u64 hh = pack2(hv[c], hv[c]);
             if constexpr (NP >= 1) {
               const float4 w0 = *reinterpret_cast<const float4*>(wrow);
@@ -513,10 +532,12 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         TC_ACC(13, t_x);                              // MMA: wait for X
         tc::tc_fence_after();
         const uint32_t tmem_b = tmem + (t1 & 1u) * 256u;
-        const uint64_t dw1 = tc::make_smem_desc(w1base, B_LBO, SBO);
-        const uint64_t dw2 = tc::make_smem_desc(w1base + W1_HALF, B_LBO, SBO);
-        const uint64_t dx1 = tc::make_smem_desc(tc::smem_u32(sm.xop[s]), A_LBO, SBO);
-        const uint64_t dx2 = tc::make_smem_desc(tc::smem_u32(sm.xop[s] + X_HALF), A_LBO, SBO);
+        // K-block stride: the next 8 K columns follow in place (quadrotor) or are the shared zero block (box envs)
+        const uint32_t xbase = tc::smem_u32(sm.xop[s]), zbase = tc::smem_u32(sm.zeros);
+        const uint64_t dw1 = tc::make_smem_desc(w1base, X2 ? B_LBO : zbase - w1base, SBO);
+        const uint64_t dw2 = tc::make_smem_desc(w1base + W1H, X2 ? B_LBO : zbase - (w1base + W1H), SBO);
+        const uint64_t dx1 = tc::make_smem_desc(xbase, X2 ? A_LBO : zbase - xbase, SBO);
+        const uint64_t dx2 = tc::make_smem_desc(xbase + XH, X2 ? A_LBO : zbase - (xbase + XH), SBO);
         tc::umma_bf16(tmem_b, dx1, dw1, idesc, 0u);
         tc::umma_bf16(tmem_b, dx1, dw2, idesc, 1u);
         tc::umma_bf16(tmem_b, dx2, dw1, idesc, 1u);
