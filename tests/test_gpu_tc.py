@@ -137,3 +137,30 @@ def test_tc_statistics_and_determinism():
     st = outs[0][1].cpu().numpy()
     done = outs[0][0]["done"].cpu().numpy().astype(bool)
     assert st[0] == done.sum() and st[3] + st[4] == st[0] and st[0] > 0
+
+
+def test_rollout_rejects_misaligned_transition_rows():
+    """obs / obs2 / act rows are written with 16- or 8-byte vector stores: a misaligned pointer must be refused by
+    the C ABI (both engines) instead of faulting on the device."""
+    import ctypes as C
+    from msacl_b200 import _lib
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    from msacl_b200.specs import get_spec
+    name = "TwoLink"                       # obs_dim 4 -> float4 rows, act_dim 2 -> float2 rows
+    spec = get_spec(name)
+    lin = [torch.nn.Linear(spec.obs_dim, 256), torch.nn.Linear(256, 256), torch.nn.Linear(256, 2 * spec.act_dim)]
+    aw = ActorWeights([(l.weight, l.bias) for l in lin])
+    ro = FusedRollout(name, 256, 2, n_step=3, engine="tc")
+    ro.state.reset()
+    ro.tr.roll_history()
+    lib = _lib.load()
+    w1p, w2p = aw.tc_images()
+    for field, shift in (("obs", 4), ("obs2", 8), ("act", 4)):
+        out = ro.tr.desc(ro.tr.H)
+        setattr(out, field, getattr(out, field) + shift)
+        common = (2, 0, 3, 100.0, 100.0, None, 0, C.byref(out), ro.stats.data_ptr(), _lib.current_stream())
+        rc_tc = lib.msacl_rollout_fused_tc(C.byref(ro.state.desc), C.byref(aw.desc), w1p.data_ptr(), w2p.data_ptr(), *common)
+        rc_ff = lib.msacl_rollout_fused(C.byref(ro.state.desc), C.byref(aw.desc), *common)
+        assert rc_tc != 0 and rc_ff != 0, field
+        assert b"aligned" in lib.msacl_last_error()
+    torch.cuda.synchronize()
