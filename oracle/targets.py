@@ -89,3 +89,13 @@ def clipped_surrogate(new_logp0, old_logp0, adv, clip_coef=0.1):
     use1 = surr1 <= surr2
     g = np.where(use1, adv * ratio, np.where(inside, adv * ratio, f32(0))) / f32(B)
     return f32(loss), g.astype(f32)
+
+
+def polyak_update(target_params, params, tau):
+    """Soft target update (msacl.py:445-460): `p_targ.mul_(polyak); p_targ.add_((1 - polyak) * p)` with polyak = 1 - tau.
+    float32 arrays in, new float32 target arrays out; the Python scalars are applied as float32 (torch casts a Python
+    scalar to the tensor dtype) and every operation rounds to float32 separately."""
+    polyak = 1 - tau
+    pk, om = np.float32(polyak), np.float32(1 - polyak)
+    return [(np.asarray(t, np.float32) * pk + om * np.asarray(p, np.float32)).astype(np.float32)
+            for t, p in zip(target_params, params)]

@@ -114,8 +114,10 @@ def test_polyak_update_multi_tensor_bit_exact():
         for p, pt in zip(src, ref):
             pt.mul_(polyak)
             pt.add_((1 - polyak) * p)
+        want = otg.polyak_update([d.cpu().numpy() for d in dst], [p.cpu().numpy() for p in src], tau)   # oracle, before the step
         up.step(tau)
-        for a, b in zip(dst, ref):
+        for a, b, w in zip(dst, ref, want):
             assert torch.equal(a, b)
+            assert np.array_equal(a.cpu().numpy(), w)
     with pytest.raises(ValueError):
         PolyakUpdater([(src[0], dst[1])])

@@ -192,3 +192,21 @@ def test_msacl_policy_loss_matches_reference():
     loss = -g["policy_q_term"] - loss_lya
     np.testing.assert_allclose(loss, g["loss_policy"], rtol=1e-5, atol=1e-5)
     assert np.isfinite(grad).all()
+
+
+def test_oracle_polyak_matches_torch_ops():
+    """oracle.targets.polyak_update vs the reference's literal torch statements (msacl.py:445-460) on CPU tensors."""
+    import torch
+    from oracle import targets as otg
+    g = torch.Generator().manual_seed(1)
+    ps = [torch.randn(33, 7, generator=g), torch.randn(5, generator=g)]
+    ts = [torch.randn(33, 7, generator=g), torch.randn(5, generator=g)]
+    for tau in (0.005, 0.3):
+        want = [t.clone() for t in ts]
+        polyak = 1 - tau
+        for p, pt in zip(ps, want):
+            pt.data.mul_(polyak)
+            pt.data.add_((1 - polyak) * p.data)
+        got = otg.polyak_update([t.numpy() for t in ts], [p.numpy() for p in ps], tau)
+        for w, gq in zip(want, got):
+            assert np.array_equal(w.numpy(), gq)
