@@ -303,15 +303,16 @@ template <> struct Env<kSingleTrackCar> {
 // QuadTracking: float32 state x[0:3] v[3:6] R[6:15] (row-major) Omega[15:18] obs[18:30];
 //               float64 state t[0], Rd_last[1:10] (row-major; t_last == previous t)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void quad_polar_f32(float (&R)[9]) {
+__device__ __forceinline__ void quad_polar_f32(float (&R)[9], float theta2) {
   // Orthogonal polar factor of a near-rotation 3x3 (reference: U @ Vh of np.linalg.svd,
-  // QuadTracking.py:308-315).  Newton iteration X <- (X + X^-T)/2 converges quadratically;
-  // the input is within h^2|w|^2/2 of a rotation so three sweeps reach float32 round-off.
+  // QuadTracking.py:308-315).  Newton iteration X <- (X + X^-T)/2: every singular value 1 + e goes to 1 + e^2/2.
+  // The input is (rotation) x (I + h hat(w)), singular values sqrt(1 + theta^2), theta = h |w|, i.e. e0 = theta^2/2:
+  // two sweeps leave e0^4/8 (< 1e-9 for theta^2 < 0.02, below float32 round-off); a third sweep only runs for
+  // theta^2 >= 0.02 (|w| > 14 rad/s, at the edge of the observation box).
   // The det<0 branch of the reference cannot trigger for such inputs (det ~ +1).
   // (The sweep is not a restatement of a NumPy expression, so it uses explicit fused multiply-adds: fewer
   // instructions and fewer roundings; everything that mirrors reference arithmetic stays unfused.)
-#pragma unroll
-  for (int it = 0; it < 3; ++it) {
+  auto sweep = [&]() {
     auto cof = [](float a, float b, float c, float d) { return __fmaf_rn(a, b, -(c * d)); };   // a*b - c*d
     const float c00 = cof(R[4], R[8], R[5], R[7]), c01 = cof(R[5], R[6], R[3], R[8]), c02 = cof(R[3], R[7], R[4], R[6]);
     const float c10 = cof(R[2], R[7], R[1], R[8]), c11 = cof(R[0], R[8], R[2], R[6]), c12 = cof(R[1], R[6], R[0], R[7]);
@@ -321,7 +322,10 @@ __device__ __forceinline__ void quad_polar_f32(float (&R)[9]) {
     R[0] = __fmaf_rn(c00, hid, 0.5f * R[0]); R[1] = __fmaf_rn(c01, hid, 0.5f * R[1]); R[2] = __fmaf_rn(c02, hid, 0.5f * R[2]);
     R[3] = __fmaf_rn(c10, hid, 0.5f * R[3]); R[4] = __fmaf_rn(c11, hid, 0.5f * R[4]); R[5] = __fmaf_rn(c12, hid, 0.5f * R[5]);
     R[6] = __fmaf_rn(c20, hid, 0.5f * R[6]); R[7] = __fmaf_rn(c21, hid, 0.5f * R[7]); R[8] = __fmaf_rn(c22, hid, 0.5f * R[8]);
-  }
+  };
+  sweep();
+  sweep();
+  if (theta2 >= 0.02f) sweep();
 }
 
 // desired frame at time t for position x / velocity v (QuadTracking.py:122-139, trajectory :29-36)
@@ -431,7 +435,7 @@ template <> struct Env<kQuadTracking> {
       Om[0] = (float)((double)w0 + dO0 * kDtD);
       Om[1] = (float)((double)w1 + dO1 * kDtD);
       Om[2] = (float)((double)w2 + dO2 * kDtD);
-      quad_polar_f32(R);
+      quad_polar_f32(R, (kDt * kDt) * ((w0 * w0 + w1 * w1) + w2 * w2));
     }
 #pragma unroll
     for (int j = 0; j < 9; ++j) sf[6 + j] = R[j];
