@@ -70,6 +70,14 @@ __global__ void __launch_bounds__(1024) window_scan_kernel(int64_t* __restrict__
   }
 }
 
+constexpr int SC_IT = 3;   // register-resident path of the scatter: up to 96 obs vectors and 96 act scalars per window
+template <int N> struct ObsVec;
+template <> struct ObsVec<4> { using type = float4; };
+template <> struct ObsVec<2> { using type = float2; };
+template <> struct ObsVec<1> { using type = float; };
+
+// W = obs vector width in floats (4 if obs_dim % 4 == 0, 2 if even, else 1)
+template <int W>
 __global__ void __launch_bounds__(WB)
 window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_flags, msacl_ring_t ring,
                       const int64_t* __restrict__ block_offsets, const int64_t* __restrict__ header) {
@@ -104,24 +112,97 @@ window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_fl
   __syncthreads();
   const int num = s_num;
   const int ns = ring.n_step, D = ring.obs_dim, A = ring.act_dim;
+  // A window's rows come from ns transition slices (stride n rows), its ring entry is contiguous per field.  Work items
+  // are OW-float vectors of the obs / obs2 rows (OW = 4, 2 or 1: the widest that divides obs_dim), scalars of the act
+  // rows, and one lane per row for the four per-step scalars.  The item -> (row, offset) map is the same for every
+  // window: each lane derives it once and then walks it with additions only (no division in the window loop).
+  constexpr int OW = W;
+  const int vpr = D / OW;                         // obs vectors per row
+  const int nv = ns * vpr, na = ns * A;
+  const int r0 = lane / vpr, q0 = lane - r0 * vpr, dr = 32 / vpr, dq = 32 - dr * vpr;
+  const int ar0 = lane / A, aj0 = lane - ar0 * A, adr = 32 / A, adj = 32 - adr * A;
+  const int64_t row_stride = n * (int64_t)D, arow_stride = n * (int64_t)A;
+  using VecT = typename ObsVec<OW>::type;
   for (int w = warp; w < num; w += WB / 32) {
     const int64_t slot = s_slot[w];
     if (slot < 0) continue;
     const int64_t newest = s_src[w];
-    const int64_t t_new = newest / n, i = newest % n;
-    const int64_t t0 = t_new - (ns - 1);
-    for (int e = lane; e < ns * D; e += 32) {
-      const int r = e / D, d = e % D;
-      const int64_t src = ((t0 + r) * n + i) * D + d;
-      ring.obs[(slot * ns + r) * D + d] = tr.obs[src];
-      ring.obs2[(slot * ns + r) * D + d] = tr.obs2[src];
+    const int64_t t_new = newest / n, i = newest - t_new * n;
+    const int64_t first = (t_new - (ns - 1)) * n + i;              // flat (t, i) row index of the window's oldest transition
+    const float* so = tr.obs + first * D;
+    const float* so2 = tr.obs2 + first * D;
+    const float* sa = tr.act + first * A;
+    float* dob = ring.obs + slot * ns * D;
+    float* dob2 = ring.obs2 + slot * ns * D;
+    float* da = ring.act + slot * ns * A;
+#ifndef MSACL_SCATTER_REGPATH
+#define MSACL_SCATTER_REGPATH 1
+#endif
+    if (MSACL_SCATTER_REGPATH && nv <= 32 * SC_IT && na <= 32 * SC_IT) {
+      // every load of the window is issued before the first store (one memory round trip per window)
+      VecT vo[SC_IT], vo2[SC_IT];
+      float va[SC_IT], vr = 0.f, vc = 0.f, vl = 0.f;
+      uint8_t vd = 0;
+      int r = r0, q = q0;
+#pragma unroll
+      for (int it = 0; it < SC_IT; ++it) {
+        if (it * 32 + lane < nv) {
+          const int64_t src = r * row_stride + q * OW;
+          vo[it] = *reinterpret_cast<const VecT*>(so + src);
+          vo2[it] = *reinterpret_cast<const VecT*>(so2 + src);
+        }
+        r += dr; q += dq;
+        if (q >= vpr) { q -= vpr; ++r; }
+      }
+      r = ar0;
+      int j = aj0;
+#pragma unroll
+      for (int it = 0; it < SC_IT; ++it) {
+        if (it * 32 + lane < na) va[it] = sa[r * arow_stride + j];
+        r += adr; j += adj;
+        if (j >= A) { j -= A; ++r; }
+      }
+      if (lane < ns) {
+        const int64_t src = first + lane * n;
+        vr = tr.rew[src]; vc = tr.cost[src]; vl = tr.logp[src]; vd = tr.done[src];
+      }
+#pragma unroll
+      for (int it = 0; it < SC_IT; ++it) {
+        const int v = it * 32 + lane;
+        if (v < nv) {
+          *reinterpret_cast<VecT*>(dob + (int64_t)v * OW) = vo[it];
+          *reinterpret_cast<VecT*>(dob2 + (int64_t)v * OW) = vo2[it];
+        }
+        if (v < na) da[v] = va[it];
+      }
+      if (lane < ns) {
+        ring.rew[slot * ns + lane] = vr;
+        ring.cost[slot * ns + lane] = vc;
+        ring.done[slot * ns + lane] = vd ? 1.0f : 0.0f;
+        ring.logp[slot * ns + lane] = vl;
+      }
+      continue;
     }
-    for (int e = lane; e < ns * A; e += 32) {
-      const int r = e / A, d = e % A;
-      ring.act[(slot * ns + r) * A + d] = tr.act[((t0 + r) * n + i) * A + d];
+    {
+      int r = r0, q = q0;
+      for (int v = lane; v < nv; v += 32) {
+        const int64_t src = r * row_stride + q * OW;
+        *reinterpret_cast<VecT*>(dob + (int64_t)v * OW) = *reinterpret_cast<const VecT*>(so + src);
+        *reinterpret_cast<VecT*>(dob2 + (int64_t)v * OW) = *reinterpret_cast<const VecT*>(so2 + src);
+        r += dr; q += dq;
+        if (q >= vpr) { q -= vpr; ++r; }
+      }
+    }
+    {
+      int r = ar0, j = aj0;
+      for (int e = lane; e < na; e += 32) {
+        da[e] = sa[r * arow_stride + j];
+        r += adr; j += adj;
+        if (j >= A) { j -= A; ++r; }
+      }
     }
     for (int r = lane; r < ns; r += 32) {
-      const int64_t src = (t0 + r) * n + i;
+      const int64_t src = first + r * n;
       ring.rew[slot * ns + r] = tr.rew[src];
       ring.cost[slot * ns + r] = tr.cost[src];
       ring.done[slot * ns + r] = tr.done[src] ? 1.0f : 0.0f;
@@ -225,7 +306,13 @@ extern "C" int msacl_window_store(const msacl_transitions_t* tr, int32_t H, int3
   cudaStream_t s = (cudaStream_t)stream;
   window_count_kernel<<<(unsigned)nb, WB, 0, s>>>(tr->emit + (int64_t)H * n, total, scratch + 2);
   window_scan_kernel<<<1, 1024, 0, s>>>(scratch + 2, nb, scratch, ptr_size, count_out, ring->max_size);
-  window_scatter_kernel<<<(unsigned)nb, WB, 0, s>>>(*tr, H, n, total, *ring, scratch + 2, scratch);
+  const int D = ring->obs_dim;
+  auto misaligned = [&](const void* p, int w) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(4 * w - 1)) != 0; };
+  int W = (D % 4 == 0) ? 4 : ((D % 2 == 0) ? 2 : 1);
+  while (W > 1 && (misaligned(tr->obs, W) || misaligned(tr->obs2, W) || misaligned(ring->obs, W) || misaligned(ring->obs2, W))) W >>= 1;
+  if (W == 4) window_scatter_kernel<4><<<(unsigned)nb, WB, 0, s>>>(*tr, H, n, total, *ring, scratch + 2, scratch);
+  else if (W == 2) window_scatter_kernel<2><<<(unsigned)nb, WB, 0, s>>>(*tr, H, n, total, *ring, scratch + 2, scratch);
+  else window_scatter_kernel<1><<<(unsigned)nb, WB, 0, s>>>(*tr, H, n, total, *ring, scratch + 2, scratch);
   return check_launch("window_store");
 }
 

@@ -89,3 +89,26 @@ out = {k: torch.empty(idx.numel(), *v.shape[1:], dtype=torch.float32, device=dev
 dst = buf._make_ring(out, idx.numel())
 ms = timeit(lambda: _lib.check(lib.msacl_ring_gather(C.byref(buf._ring), idx.data_ptr(), idx.numel(), C.byref(dst), st)))
 line("ring_gather (2^18 windows), kernel", ms, idx.numel() * n * 4 * (2 * D + A + 4) * 2, idx.numel())
+
+# n-step window store (deque windows + add_batch): every env emits a window at every step of a K-step chunk; the ring
+# keeps the last `max_size` of them.  Algorithmic bytes = live windows x (read the n_step rows + write the ring entry).
+from msacl_b200.sampler import DeviceWindowBatch, TransitionBuffers
+from msacl_b200.specs import get_spec
+for env_name in ("TwoLink", "QuadTracking"):
+    spec = get_spec(env_name)
+    N, K = 1 << 18, 8
+    Dw, Aw = spec.obs_dim, spec.act_dim
+    tr = TransitionBuffers(spec, N, K, n, torch.device(dev), chunks=1)
+    tr.roll_history()
+    for k, v in tr.fields().items():
+        if v.dtype == torch.float32:
+            v.copy_(torch.randn(v.shape, device=dev, generator=g))
+    tr.emit.fill_(1)
+    ring_size = 1 << 20
+    buf2 = B200NstepReplayBuffer(obs_dim=Dw, act_dim=Aw, buffer_max_size=ring_size, n_step=n)
+    batch = DeviceWindowBatch(tr, n)
+    ms = timeit(lambda: buf2.add_batch(batch))
+    live = min(N * K, ring_size)
+    line(f"window_store {env_name} (count + scan + scatter, 2^20 live windows)", ms, live * n * 4 * (2 * Dw + Aw + 4) * 2 + N * K, live)
+    del tr, buf2, batch
+    torch.cuda.empty_cache()
