@@ -121,27 +121,55 @@ lyapunov_risk_kernel(int64_t B, int n, int D_rt, const float* __restrict__ obs, 
   }
 }
 
-template <int WPB>
-__global__ void __launch_bounds__(WPB * 32)
+// One THREAD per window (a window is only n floats: a warp per window spends an instruction per 80 bytes and is
+// issue-bound at a fifth of the HBM peak).  A warp covers 32 consecutive windows = 32*n contiguous floats; each lane
+// reads its own n floats as float4 vectors when n % 4 == 0 (every sector fetched is fully used by the warp).  The
+// lambda-weighted sum runs in step order, the batch moments are reduced per warp and per block in float64.
+template <int TPB>
+__global__ void __launch_bounds__(TPB)
 stability_adv_kernel(int64_t B, int n, const float* __restrict__ lya_obs0, const float* __restrict__ lya_obs2,
                      const float* __restrict__ coef_diff, const float* __restrict__ coef_sl, float* __restrict__ adv_raw,
                      double* __restrict__ moments) {
-  __shared__ double s_m[2][WPB];
+  __shared__ float s_dif[32], s_sl[32];
+  __shared__ double s_m[2][TPB / 32];
+  if (threadIdx.x < 32) {
+    s_dif[threadIdx.x] = threadIdx.x < n ? coef_diff[threadIdx.x] : 0.f;
+    s_sl[threadIdx.x] = threadIdx.x < n ? coef_sl[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool act = lane < n;
-  const float dif = act ? coef_diff[lane] : 0.f, sl = act ? coef_sl[lane] : 0.f;
+  const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(lya_obs2) & 15) == 0;
   double m1 = 0.0, m2 = 0.0;
-  for (int64_t b = (int64_t)blockIdx.x * WPB + warp; b < B; b += (int64_t)gridDim.x * WPB) {
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  for (int64_t b = (int64_t)blockIdx.x * TPB + threadIdx.x; b < B; b += stride) {
     const float v0 = lya_obs0[b];
-    const float v2 = act ? lya_obs2[b * n + lane] : 0.f;
-    const float a = warp_sum(dif * (v0 * sl - v2));       // msacl.py:395-399
-    if (lane == 0) { adv_raw[b] = a; m1 += (double)a; m2 += (double)a * (double)a; }
+    const float* row = lya_obs2 + b * n;
+    float a = 0.f;
+    if (vec) {
+      for (int k = 0; k < n; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(row + k);
+        a += s_dif[k] * (v0 * s_sl[k] - v.x);                 // msacl.py:395-399
+        a += s_dif[k + 1] * (v0 * s_sl[k + 1] - v.y);
+        a += s_dif[k + 2] * (v0 * s_sl[k + 2] - v.z);
+        a += s_dif[k + 3] * (v0 * s_sl[k + 3] - v.w);
+      }
+    } else {
+      for (int k = 0; k < n; ++k) a += s_dif[k] * (v0 * s_sl[k] - row[k]);
+    }
+    adv_raw[b] = a;
+    m1 += (double)a;
+    m2 += (double)a * (double)a;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, o);
   }
   if (lane == 0) { s_m[0][warp] = m1; s_m[1][warp] = m2; }
   __syncthreads();
   if (threadIdx.x < 2) {
     double s = 0.0;
-    for (int w = 0; w < WPB; ++w) s += s_m[threadIdx.x][w];
+    for (int w = 0; w < TPB / 32; ++w) s += s_m[threadIdx.x][w];
     atomicAdd(&moments[threadIdx.x], s);
   }
 }
@@ -333,8 +361,8 @@ extern "C" int msacl_stability_advantage(int64_t B, int32_t n, const float* lya_
   }
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(moments, 0, 2 * sizeof(double), s);
-  constexpr int WPB = 8;
-  stability_adv_kernel<WPB><<<grid_for(B, WPB), WPB * 32, 0, s>>>(B, n, lya_obs0, lya_obs2, coef_diff, coef_sl, adv_raw, moments);
+  constexpr int TPB = 128;
+  stability_adv_kernel<TPB><<<grid_for(B, TPB), TPB, 0, s>>>(B, n, lya_obs0, lya_obs2, coef_diff, coef_sl, adv_raw, moments);
   return check_launch("stability_advantage");
 }
 
