@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MSACL_ABI_VERSION 1
+#define MSACL_ABI_VERSION 2
 
 /* env ids: the fixed table of RL/env/make_env.py:19-32 */
 enum {
@@ -46,7 +46,8 @@ enum {
  * Row counts / layout per env come from msacl_env_dims(). */
 typedef struct {
   int32_t env_id;
-  int32_t max_step;      /* time limit (reference: 1000, e.g. RL/env/VanderPol.py:67) */
+  int32_t max_step;      /* time limit (reference: 1000, e.g. RL/env/VanderPol.py:67); <= 0 (msacl_env_step only): bare
+                            env semantics -- no time limit, no autoreset, stepping continues from a terminal state */
   int64_t n;             /* env instances on this GPU */
   int64_t stride;        /* row pitch in elements, >= n */
   float* sf;
@@ -113,6 +114,9 @@ typedef struct {
   uint8_t* done;  /* [K][n]  terminated | truncated */
   float* logp;    /* [K][n]  log-prob of the sampled action */
   uint8_t* emit;  /* [K][n]  1 iff the env's n-step deque is full after this transition */
+  float* logits;  /* [K][n][2*act_dim]  optional diagnostic: the policy MLP output the action was sampled from
+                     (mean || log_std BEFORE clamp/exp, i.e. the pre-tanh Gaussian parameters); parity tests assert
+                     the tensor-core engine's stated tolerance on it.  Ignored by msacl_window_store. */
 } msacl_transitions_t;
 
 /* Fused K-step rollout: actor forward + TanhGauss sample + clip + env step + reward/cost
@@ -122,8 +126,9 @@ typedef struct {
  * (act_distribution_cls.py:45-57) and rew_plus_cost (RL/utils/rew_plus_cost.py:18-21).
  *   eps        optional [K][n][act_dim] explicit N(0,1) draws (tests); NULL -> Philox(seed,
  *              env_base+i, step_base+k)
- *   stats      optional double[8]: episodes, sum return, sum length, terminated, truncated,
- *              sum scaled reward, sum cost, steps   (atomically accumulated)
+ *   stats      optional double[8], atomically accumulated: [0] finished episodes, [1] sum of their returns,
+ *              [2] sum of their lengths, [3] terminated, [4] truncated; [5..7] reserved (not written by release
+ *              builds; the MSACL_TC_TIMING debug build uses [5..18] for role timers)
  *   deterministic != 0 -> action = mode() (act_distribution_cls.py:90-95; evaluator path) */
 int msacl_rollout_fused(const msacl_env_state_t* st, const msacl_actor_t* actor, int32_t K, uint32_t step_base,
                         int32_t n_step, float reward_scale, float cost_scale, const float* eps,
@@ -140,6 +145,11 @@ int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_actor_t* act
                            int32_t K, uint32_t step_base, int32_t n_step, float reward_scale, float cost_scale,
                            const float* eps, int32_t deterministic, const msacl_transitions_t* out, double* stats,
                            void* stream);
+
+/* Diagnostic: out[i] = NormalizeOrientMatrix(in[i]) for n row-major 3x3 float32 matrices through the device polar
+ * routine of the QuadTracking step (RL/env/QuadTracking.py:308-315), including its det < 0 branch (:312-314), which the
+ * dynamics cannot reach.  theta2 = (h |Omega|)^2 hint (>= 0.02 -> a third Newton sweep). */
+int msacl_selftest_quad_polar(const float* in, float* out, int64_t n, float theta2, void* stream);
 
 /* Fill out[n][act_dim] with the N(0,1) draws the rollout uses at global step `step`. */
 int msacl_action_noise(uint64_t seed, uint64_t env_base, int64_t n, int32_t act_dim, uint32_t step, float* out,
@@ -158,9 +168,11 @@ typedef struct {
  * (nstep_replay_buffer.py:91-125).
  *   tr        transitions of H + K steps: the first H = n_step-1 slices are the tail of the
  *             previous chunk (history), the last K are new; emit flags of history are ignored
- *   scratch   int64[2 + ceil(K*n/1024)] device scratch
+ *   scratch   int64[msacl_window_store_scratch_elems(K, n)] device scratch (= 2 + ceil(K*n/256): a two-word
+ *             header and one count per block of 256 emit flags)
  *   ptr_size  device int64[2] = {ptr, size}, updated in place
  *   count_out device int64[1]: number of windows stored by this call */
+int64_t msacl_window_store_scratch_elems(int32_t K, int64_t n);
 int msacl_window_store(const msacl_transitions_t* tr, int32_t H, int32_t K, int64_t n, const msacl_ring_t* ring,
                        int64_t* ptr_size, int64_t* count_out, int64_t* scratch, void* stream);
 

@@ -1,7 +1,7 @@
-"""ctypes binding of csrc/libmsacl_b200.so (the C ABI declared in include/msacl_b200.h).
+"""ctypes binding of lib/libmsacl_b200.so (the C ABI declared in include/msacl_b200.h).
 
-There is no CPU fallback: if the library is missing it is built with nvcc (build.py); if it
-cannot be built or loaded, importing the kernels raises.
+There is no CPU fallback: the library is (re)built with nvcc whenever its source digest does not match
+the tree (build.py); if it cannot be built or loaded, importing the kernels raises.
 """
 import ctypes as C
 import os
@@ -9,6 +9,7 @@ import os
 from . import build as _build
 
 _LIB = None
+ABI_VERSION = 2      # MSACL_ABI_VERSION of include/msacl_b200.h this binding was written against
 
 c_f32p = C.POINTER(C.c_float)
 c_f64p = C.POINTER(C.c_double)
@@ -31,7 +32,7 @@ class Actor(C.Structure):
 
 class Transitions(C.Structure):
     _fields_ = [("obs", vp), ("act", vp), ("rew", vp), ("cost", vp), ("obs2", vp), ("done", vp), ("logp", vp),
-                ("emit", vp)]
+                ("emit", vp), ("logits", vp)]
 
 
 class Ring(C.Structure):
@@ -55,6 +56,8 @@ SIGNATURES = {
     "msacl_rollout_fused_tc": (C.c_int, [C.POINTER(EnvState), C.POINTER(Actor), vp, vp, C.c_int32, C.c_uint32, C.c_int32,
                                          C.c_float, C.c_float, vp, C.c_int32, C.POINTER(Transitions), vp, vp]),
     "msacl_action_noise": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32, vp, vp]),
+    "msacl_window_store_scratch_elems": (C.c_int64, [C.c_int32, C.c_int64]),
+    "msacl_selftest_quad_polar": (C.c_int, [vp, vp, C.c_int64, C.c_float, vp]),
     "msacl_window_store": (C.c_int, [C.POINTER(Transitions), C.c_int32, C.c_int32, C.c_int64, C.POINTER(Ring), vp, vp,
                                      vp, vp]),
     "msacl_ring_gather": (C.c_int, [C.POINTER(Ring), vp, C.c_int64, C.POINTER(Ring), vp]),
@@ -80,14 +83,21 @@ def load():
     if _LIB is not None:
         return _LIB
     path = _build.LIB
-    if not os.path.exists(path):
-        _build.build()
+    try:
+        _build.build()                  # sha256 of the sources vs the stamp: returns at once when the library is current
+    except (OSError, RuntimeError) as e:
+        # no usable nvcc on this host: an existing library may still be loaded, but never silently when it is stale
+        if not os.path.exists(path):
+            raise
+        if not _build.is_current():
+            import warnings
+            warnings.warn(f"libmsacl_b200.so is older than its sources and could not be rebuilt ({e}); loading the stale binary")
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.msacl_abi_version() != 1:
+    if lib.msacl_abi_version() != ABI_VERSION:
         raise RuntimeError("libmsacl_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -28,6 +28,7 @@ class B200NstepReplayBuffer:
         self._ptr_size = torch.zeros(2, dtype=torch.int64, device=self.device)
         self._count = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._scratch = None
+        self._host_ps = (0, 0)
         self._ring = self._make_ring(self.n_step_buf, self.max_size)
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(kwargs.get("seed") or 0))
@@ -36,14 +37,20 @@ class B200NstepReplayBuffer:
         return _lib.Ring(max_size=max_size, n_step=self.n_step, obs_dim=self.obsv_dim, act_dim=self.act_dim,
                          **{k: bufs[k].data_ptr() for k in FIELDS})
 
-    # ---- bookkeeping (device counters; reading them synchronises)
+    # ---- bookkeeping: the counters live on the device (the window scan updates them); the host copy is refreshed
+    #      lazily, i.e. reading .ptr / .size synchronises only after a device append, and sample_batch never reads them
+    def _host_counters(self):
+        if self._host_ps is None:
+            self._host_ps = tuple(int(x) for x in self._ptr_size.tolist())
+        return self._host_ps
+
     @property
     def ptr(self):
-        return int(self._ptr_size[0].item())
+        return self._host_counters()[0]
 
     @property
     def size(self):
-        return int(self._ptr_size[1].item())
+        return self._host_counters()[1]
 
     def __len__(self):
         return self.size
@@ -62,8 +69,9 @@ class B200NstepReplayBuffer:
         vals = dict(obs=obs, act=act, rew=rew, cost=cost, obs2=next_obs, done=done, logp=logp)
         for k, v in vals.items():
             self.n_step_buf[k][p] = torch.as_tensor(np.asarray(v, dtype=np.float32), device=self.device)
-        self._ptr_size[0] = (p + 1) % self.max_size
-        self._ptr_size[1] = min(self.size + 1, self.max_size)
+        new = ((p + 1) % self.max_size, min(self.size + 1, self.max_size))
+        self._ptr_size.copy_(torch.tensor(new, dtype=torch.int64))
+        self._host_ps = new
 
     def add_batch(self, samples):
         if isinstance(samples, DeviceWindowBatch):
@@ -72,10 +80,12 @@ class B200NstepReplayBuffer:
             self.store(*s)
 
     def add_device_batch(self, batch: DeviceWindowBatch):
+        batch.check_current()
         tr = batch.tr
-        nb = (tr.K * tr.n + 255) // 256
-        if self._scratch is None or self._scratch.numel() < nb + 2:
-            self._scratch = torch.zeros(nb + 2, dtype=torch.int64, device=self.device)
+        self._host_ps = None
+        need = int(_lib.load().msacl_window_store_scratch_elems(tr.K, tr.n))      # exactly the size the header documents
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.zeros(need, dtype=torch.int64, device=self.device)
         desc = tr.desc(0)
         _lib.check(_lib.load().msacl_window_store(C.byref(desc), tr.H, tr.K, tr.n, C.byref(self._ring), self._ptr_size.data_ptr(),
                                                  self._count.data_ptr(), self._scratch.data_ptr(), _lib.current_stream()))
@@ -92,5 +102,8 @@ class B200NstepReplayBuffer:
 
     def sample_batch(self, batch_size: int) -> dict:
         """Uniform sampling with replacement over the valid range (nstep_replay_buffer.py:138)."""
-        idx = torch.randint(0, self.size, (int(batch_size),), device=self.device, generator=self._gen)
+        # idx ~ U{0..size-1} drawn on the device from the device-resident size (no host synchronisation)
+        u = torch.rand(int(batch_size), device=self.device, generator=self._gen, dtype=torch.float64)
+        size = self._ptr_size[1]
+        idx = torch.minimum((u * size).to(torch.int64), torch.clamp(size - 1, min=0))
         return self.gather(idx)

@@ -303,29 +303,82 @@ template <> struct Env<kSingleTrackCar> {
 // QuadTracking: float32 state x[0:3] v[3:6] R[6:15] (row-major) Omega[15:18] obs[18:30];
 //               float64 state t[0], Rd_last[1:10] (row-major; t_last == previous t)
 // ------------------------------------------------------------------------------------------
+// Cold path of NormalizeOrientMatrix (QuadTracking.py:312-314): det(U Vh) < 0.  The reference flips the last column of
+// U (the singular vector of the SMALLEST singular value) and recomputes U Vh, i.e. R' = Q (I - 2 v3 v3^T) with Q the
+// orthogonal polar factor of M (det -1) and v3 the right-singular vector of the smallest singular value = the eigenvector
+// of the smallest eigenvalue of P = Q^T M (symmetric positive definite).  v3 is the dominant eigenvector of adj(P)
+// (= det(P) P^-1), found by repeated squaring.  Unreachable from the dynamics (the input there is a rotation times
+// I + h hat(w), det ~ +1), so it lives out of line, in float64, and costs the hot path one predicate.
+static __device__ __noinline__ void quad_polar_reflected(float* Rm) {
+  double M[9], Q[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { M[i] = (double)Rm[i]; Q[i] = M[i]; }
+  auto cofactors = [](const double* X, double* C) {
+    C[0] = X[4] * X[8] - X[5] * X[7]; C[1] = X[5] * X[6] - X[3] * X[8]; C[2] = X[3] * X[7] - X[4] * X[6];
+    C[3] = X[2] * X[7] - X[1] * X[8]; C[4] = X[0] * X[8] - X[2] * X[6]; C[5] = X[1] * X[6] - X[0] * X[7];
+    C[6] = X[1] * X[5] - X[2] * X[4]; C[7] = X[2] * X[3] - X[0] * X[5]; C[8] = X[0] * X[4] - X[1] * X[3];
+  };
+  for (int it = 0; it < 40; ++it) {            // Newton: Q <- (Q + Q^-T)/2, converges to the orthogonal factor (det -1)
+    double C[9];
+    cofactors(Q, C);
+    const double det = Q[0] * C[0] + Q[1] * C[1] + Q[2] * C[2];
+    double delta = 0.0;
+    for (int i = 0; i < 9; ++i) { const double q = 0.5 * (Q[i] + C[i] / det); delta += fabs(q - Q[i]); Q[i] = q; }
+    if (delta < 1e-15) break;
+  }
+  double P[9], B[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) P[3 * i + j] = Q[i] * M[j] + Q[3 + i] * M[3 + j] + Q[6 + i] * M[6 + j];      // Q^T M
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 3; ++j) { const double a = 0.5 * (P[3 * i + j] + P[3 * j + i]); P[3 * i + j] = a; P[3 * j + i] = a; }
+  cofactors(P, B);                              // symmetric P: adj(P) = cofactor matrix
+  for (int it = 0; it < 12; ++it) {             // B <- B^2 / trace: rank-1 projector on the smallest eigenvector of P
+    double S[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) S[3 * i + j] = B[3 * i] * B[j] + B[3 * i + 1] * B[3 + j] + B[3 * i + 2] * B[6 + j];
+    const double tr = S[0] + S[4] + S[8];
+    for (int i = 0; i < 9; ++i) B[i] = S[i] / tr;
+  }
+  int best = 0;
+  double bn = -1.0;
+  for (int j = 0; j < 3; ++j) {
+    const double nn = B[j] * B[j] + B[3 + j] * B[3 + j] + B[6 + j] * B[6 + j];
+    if (nn > bn) { bn = nn; best = j; }
+  }
+  const double inv = rsqrt(bn);
+  const double v[3] = {B[best] * inv, B[3 + best] * inv, B[6 + best] * inv};
+  for (int i = 0; i < 3; ++i) {                 // R' = Q - 2 (Q v) v^T
+    const double qv = Q[3 * i] * v[0] + Q[3 * i + 1] * v[1] + Q[3 * i + 2] * v[2];
+    for (int j = 0; j < 3; ++j) Rm[3 * i + j] = (float)(Q[3 * i + j] - 2.0 * qv * v[j]);
+  }
+}
+
 __device__ __forceinline__ void quad_polar_f32(float (&R)[9], float theta2) {
   // Orthogonal polar factor of a near-rotation 3x3 (reference: U @ Vh of np.linalg.svd,
   // QuadTracking.py:308-315).  Newton iteration X <- (X + X^-T)/2: every singular value 1 + e goes to 1 + e^2/2.
   // The input is (rotation) x (I + h hat(w)), singular values sqrt(1 + theta^2), theta = h |w|, i.e. e0 = theta^2/2:
   // two sweeps leave e0^4/8 (< 1e-9 for theta^2 < 0.02, below float32 round-off); a third sweep only runs for
   // theta^2 >= 0.02 (|w| > 14 rad/s, at the edge of the observation box).
-  // The det<0 branch of the reference cannot trigger for such inputs (det ~ +1).
+  // The det<0 branch of the reference (:312-314) cannot trigger for such inputs (det ~ +1); it is honoured by the
+  // out-of-line quad_polar_reflected() behind the predicate on the first sweep's determinant.
   // (The sweep is not a restatement of a NumPy expression, so it uses explicit fused multiply-adds: fewer
   // instructions and fewer roundings; everything that mirrors reference arithmetic stays unfused.)
-  auto sweep = [&]() {
+  auto sweep = [&](bool first) -> bool {
     auto cof = [](float a, float b, float c, float d) { return __fmaf_rn(a, b, -(c * d)); };   // a*b - c*d
     const float c00 = cof(R[4], R[8], R[5], R[7]), c01 = cof(R[5], R[6], R[3], R[8]), c02 = cof(R[3], R[7], R[4], R[6]);
     const float c10 = cof(R[2], R[7], R[1], R[8]), c11 = cof(R[0], R[8], R[2], R[6]), c12 = cof(R[1], R[6], R[0], R[7]);
     const float c20 = cof(R[1], R[5], R[2], R[4]), c21 = cof(R[2], R[3], R[0], R[5]), c22 = cof(R[0], R[4], R[1], R[3]);
     const float det = __fmaf_rn(R[2], c02, __fmaf_rn(R[1], c01, R[0] * c00));
+    if (first && det < 0.0f) return false;
     const float hid = 0.5f / det;                 // (an approximate reciprocal here measured 1.5 % slower end to end)
     R[0] = __fmaf_rn(c00, hid, 0.5f * R[0]); R[1] = __fmaf_rn(c01, hid, 0.5f * R[1]); R[2] = __fmaf_rn(c02, hid, 0.5f * R[2]);
     R[3] = __fmaf_rn(c10, hid, 0.5f * R[3]); R[4] = __fmaf_rn(c11, hid, 0.5f * R[4]); R[5] = __fmaf_rn(c12, hid, 0.5f * R[5]);
     R[6] = __fmaf_rn(c20, hid, 0.5f * R[6]); R[7] = __fmaf_rn(c21, hid, 0.5f * R[7]); R[8] = __fmaf_rn(c22, hid, 0.5f * R[8]);
+    return true;
   };
-  sweep();
-  sweep();
-  if (theta2 >= 0.02f) sweep();
+  if (!sweep(true)) { quad_polar_reflected(R); return; }
+  sweep(false);
+  if (theta2 >= 0.02f) sweep(false);
 }
 
 // desired frame at time t for position x / velocity v (QuadTracking.py:122-139, trajectory :29-36)

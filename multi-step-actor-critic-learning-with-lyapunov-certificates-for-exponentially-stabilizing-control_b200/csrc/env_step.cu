@@ -69,11 +69,14 @@ env_step_kernel(msacl_env_state_t st, const float* __restrict__ action, float* _
   const float rew = E::step(r.sf, r.sd, a);
   const bool term = r.out_of_bounds();
   r.step += 1;
-  const bool trunc = r.step >= st.max_step;
+  // max_step <= 0: a bare env instance as the reference classes are outside a vector env -- no time limit and no
+  // autoreset; the state keeps evolving from the terminal state exactly as <env>.step would (e.g. VanderPol.py:100-130)
+  const bool vec = st.max_step > 0;
+  const bool trunc = vec && r.step >= st.max_step;
   r.ep_return += rew;
   r.ep_len += 1;
   if (final_obs) store_row<E::D>(final_obs, i, r.obs());
-  if (term || trunc) {   // gymnasium 0.28.1 SyncVectorEnv: reset in the same step
+  if (vec && (term || trunc)) {   // gymnasium 0.28.1 SyncVectorEnv: reset in the same step
     r.episode += 1;
     r.run = 0;
     r.reset(st.seed, st.env_base + (uint64_t)i);
@@ -96,6 +99,17 @@ __global__ void action_noise_kernel(uint64_t seed, uint64_t env_base, int64_t n,
 }  // namespace msacl
 
 using namespace msacl;
+
+__global__ void quad_polar_selftest_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, float theta2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float R[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) R[j] = in[i * 9 + j];
+  quad_polar_f32(R, theta2);
+#pragma unroll
+  for (int j = 0; j < 9; ++j) out[i * 9 + j] = R[j];
+}
 
 extern "C" {
 
@@ -185,6 +199,12 @@ int msacl_env_step(const msacl_env_state_t* st, const float* action, float* next
     env_step_kernel<ID><<<blocks, threads, 0, (cudaStream_t)stream>>>(*st, action, next_obs, reward, terminated, truncated, final_obs);
   });
   return check_launch("env_step");
+}
+
+int msacl_selftest_quad_polar(const float* in, float* out, int64_t n, float theta2, void* stream) {
+  if (!in || !out || n <= 0) { set_error("selftest_quad_polar: bad argument"); return MSACL_ERR_BAD_ARG; }
+  quad_polar_selftest_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(in, out, n, theta2);
+  return check_launch("selftest_quad_polar");
 }
 
 int msacl_action_noise(uint64_t seed, uint64_t env_base, int64_t n, int32_t act_dim, uint32_t step, float* out,

@@ -384,6 +384,10 @@ rollout_fused_kernel(msacl_env_state_t st, msacl_actor_t actor, int K, uint32_t 
           if (out.done) out.done[row] = done ? 1 : 0;
           if (out.logp) out.logp[row] = logp;
           if (out.emit) out.emit[row] = emit ? 1 : 0;
+          if (out.logits) {
+#pragma unroll
+            for (int j = 0; j < 2 * A; ++j) out.logits[row * (2 * A) + j] = sm.out[T][j * TM + et];
+          }
           if (done) {      // episode statistics: per-thread partials, reduced once per launch (no hot atomics)
             st_ep += 1.f; st_ret += r.ep_return; st_len += (float)r.ep_len;
             if (term) st_term += 1.f; else st_trunc += 1.f;
@@ -424,6 +428,7 @@ extern "C" int msacl_rollout_fused(const msacl_env_state_t* st, const msacl_acto
                                    const float* eps, int32_t deterministic, const msacl_transitions_t* out,
                                    double* stats, void* stream) {
   if (!st || !actor || !out || st->n <= 0 || K <= 0 || n_step <= 0) { set_error("rollout_fused: bad argument"); return MSACL_ERR_BAD_ARG; }
+  if (st->max_step <= 0) { set_error("rollout_fused: the sampler path needs max_step > 0 (bare-env mode is msacl_env_step only)"); return MSACL_ERR_BAD_ARG; }
   if (!actor->w1 || !actor->b1 || !actor->w2t || !actor->b2 || !actor->w3 || !actor->b3) { set_error("rollout_fused: null actor weights"); return MSACL_ERR_BAD_ARG; }
   if ((reinterpret_cast<uintptr_t>(actor->w2t) & 15) != 0) { set_error("rollout_fused: w2t must be 16-byte aligned"); return MSACL_ERR_BAD_ARG; }
   const int64_t pairs = ((st->n + TM - 1) / TM + NTILE - 1) / NTILE;

@@ -296,6 +296,10 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           if (out.obs) {
             store_row<D>(out.obs, row, e.obs());
           }
+          if (out.logits) {      // diagnostic output, written here so that the logits do not stay live across the env step
+#pragma unroll
+            for (int j = 0; j < A2; ++j) out.logits[row * A2 + j] = lg[j];
+          }
           float act[A];
           float lp_gauss = 0.f, lp_tanh = 0.f, lp_scale = 0.f;
 #pragma unroll
@@ -647,6 +651,7 @@ extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_a
                                       float cost_scale, const float* eps, int32_t deterministic,
                                       const msacl_transitions_t* out, double* stats, void* stream) {
   if (!st || !actor || !out || !w1p || !w2p || st->n <= 0 || K <= 0 || n_step <= 0) { set_error("rollout_fused_tc: bad argument"); return MSACL_ERR_BAD_ARG; }
+  if (st->max_step <= 0) { set_error("rollout_fused_tc: the sampler path needs max_step > 0 (bare-env mode is msacl_env_step only)"); return MSACL_ERR_BAD_ARG; }
   if ((reinterpret_cast<uintptr_t>(w2p) & 15) || (reinterpret_cast<uintptr_t>(w1p) & 15)) { set_error("rollout_fused_tc: packed weights must be 16-byte aligned"); return MSACL_ERR_BAD_ARG; }
   const int64_t tiles = (st->n + TCM - 1) / TCM;
   MSACL_DISPATCH_ENV(st->env_id, {

@@ -292,6 +292,11 @@ static int validate_ring(const msacl_ring_t* r) {
   return MSACL_OK;
 }
 
+extern "C" int64_t msacl_window_store_scratch_elems(int32_t K, int64_t n) {
+  if (K <= 0 || n <= 0) return 0;
+  return 2 + ((int64_t)K * n + WB - 1) / WB;
+}
+
 extern "C" int msacl_window_store(const msacl_transitions_t* tr, int32_t H, int32_t K, int64_t n,
                                   const msacl_ring_t* ring, int64_t* ptr_size, int64_t* count_out, int64_t* scratch,
                                   void* stream) {

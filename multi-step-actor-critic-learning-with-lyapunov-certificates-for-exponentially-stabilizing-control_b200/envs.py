@@ -50,7 +50,7 @@ class EnvStateBuffers:
         self.ep_len = torch.zeros(self.n, dtype=torch.int32, device=self.device)
         self.run = torch.zeros(self.n, dtype=torch.int32, device=self.device)
         self.desc = _lib.EnvState(
-            env_id=s.env_id, max_step=int(max_step or s.max_step), n=self.n, stride=self.n,
+            env_id=s.env_id, max_step=int(s.max_step if max_step is None else max_step), n=self.n, stride=self.n,
             sf=self.sf.data_ptr(), sd=self.sd.data_ptr() if s.sd_rows else None, step=self.step.data_ptr(),
             episode=self.episode.data_ptr(), ep_return=self.ep_return.data_ptr(), ep_len=self.ep_len.data_ptr(),
             run=self.run.data_ptr(), seed=int(seed) & (2 ** 64 - 1), env_base=int(env_base))
@@ -165,7 +165,9 @@ class B200VectorEnv:
 class B200Env:
     """Single-instance env with the gym.Env surface of the reference classes
     (`reset(seed, options) -> (obs, {})`, `step(a) -> (obs, reward, terminated, truncated, {})`;
-    e.g. RL/env/VanderPol.py:69-130).  No autoreset, like the reference classes."""
+    e.g. RL/env/VanderPol.py:69-130).  No autoreset, like the reference classes: the device state is stepped with
+    max_step = -1 (bare-env mode of msacl_env_step), so a step() after terminated=True continues from the terminal
+    state; the time limit is applied on the host from `current_step`, as the reference classes do."""
 
     def __init__(self, env_name, device="cuda"):
         self.spec = get_spec(env_name)
@@ -174,8 +176,7 @@ class B200Env:
         self.action_space = Box(s.act_low, s.act_high)
         self.obs_dim, self.act_dim = s.obs_dim, s.act_dim
         self.dt, self.control_step, self.max_step = s.dt, s.control_step, s.max_step
-        # max_step is enforced on the host here so that the device never autoresets this env
-        self._v = B200VectorEnv(env_name, 1, device=device, max_step=2 ** 31 - 1)
+        self._v = B200VectorEnv(env_name, 1, device=device, max_step=-1)
         self.current_step = 0
 
     def reset(self, seed=None, options=None):

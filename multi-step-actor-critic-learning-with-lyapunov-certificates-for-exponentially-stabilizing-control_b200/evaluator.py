@@ -62,6 +62,7 @@ class B200Evaluator:
             finished |= cum[-1] > 0
             steps += self.chunk
         ep_ret, ep_cost = ret_sum / count, cost_sum / count
+        self.last_first_episode_len = count.to(torch.int32)      # steps of each instance's first episode (this rank's shard)
         if hi - lo == 0:                                     # dummy instance of an empty shard: contributes nothing
             ep_ret, ep_cost = ep_ret[:0], ep_cost[:0]
         if not sharded:

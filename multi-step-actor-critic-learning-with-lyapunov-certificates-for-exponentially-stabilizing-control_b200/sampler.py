@@ -71,8 +71,20 @@ class ActorWeights:
         lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
         if len(lin) != 3:
             raise ValueError("expected a 2-hidden-layer policy MLP")
+        # the rollout kernels hard-wire ReLU hidden activations and a linear output layer (the reference defaults,
+        # example/msacl_train.py: policy_hidden_activation "relu"); any other module would make the sampler run a
+        # different network than the learner, silently corrupting the stored act / logp
+        other = [m for m in seq if not isinstance(m, torch.nn.Linear)]
+        if len(other) != 3 or not all(isinstance(m, torch.nn.ReLU) for m in other[:2]) or not isinstance(other[2], torch.nn.Identity):
+            raise ValueError("the fused rollout kernel is specialised for policy_hidden_activation='relu' with a linear "
+                             f"output layer; got {[type(m).__name__ for m in other]}")
         return cls([(l.weight, l.bias) for l in lin], device=device,
                    min_log_std=getattr(policy, "min_log_std", -20.0), max_log_std=getattr(policy, "max_log_std", 1.0))
+
+    @staticmethod
+    def policy_version(policy):
+        """Changes whenever a parameter of `policy` is updated in place (optimizer step, load_state_dict) or replaced."""
+        return tuple((p.data_ptr(), p._version) for p in policy.parameters())
 
 
 class TransitionBuffers:
@@ -86,7 +98,7 @@ class TransitionBuffers:
 
     NAMES = ("obs", "act", "rew", "cost", "obs2", "done", "logp", "emit")
 
-    def __init__(self, spec, n, K, n_step, device, chunks=None):
+    def __init__(self, spec, n, K, n_step, device, chunks=None, record_logits=False):
         self.H, self.K, self.n = n_step - 1, K, n
         slice_bytes = n * (4 * (2 * spec.obs_dim + spec.act_dim + 3) + 2)
         if chunks is None:
@@ -101,7 +113,10 @@ class TransitionBuffers:
         b = lambda: torch.zeros(T, n, dtype=torch.uint8, device=device)
         self._full = dict(obs=f(spec.obs_dim), act=f(spec.act_dim), rew=f(), cost=f(), obs2=f(spec.obs_dim), done=b(),
                           logp=f(), emit=b())
+        # optional diagnostic: the policy outputs (mean || log_std) every action was sampled from, [K, n, 2A] of the last launch
+        self.logits = torch.zeros(K, n, 2 * spec.act_dim, dtype=torch.float32, device=device) if record_logits else None
         self._j = self.M - 1          # the first roll_history() wraps to chunk 0
+        self.launches = 0             # number of roll_history() calls = rollout launches into this store
 
     def _view(self, name):
         base = self._j * self.K
@@ -120,10 +135,14 @@ class TransitionBuffers:
         return {k: self._view(k) for k in self.NAMES}
 
     def desc(self, t0=0):
-        return _lib.Transitions(**{k: v[t0:].data_ptr() for k, v in self.fields().items()})
+        d = _lib.Transitions(**{k: v[t0:].data_ptr() for k, v in self.fields().items()})
+        if self.logits is not None:
+            d.logits = self.logits.data_ptr()
+        return d
 
     def roll_history(self):
         """Advance to the next chunk (called once before every launch)."""
+        self.launches += 1
         self._j += 1
         if self._j < self.M:
             return
@@ -141,8 +160,15 @@ class DeviceWindowBatch:
 
     def __init__(self, tr: TransitionBuffers, n_step):
         self.tr, self.n_step = tr, n_step
+        self._launch = tr.launches          # the views of `tr` follow the current chunk: a batch is only valid until the next launch
+
+    def check_current(self):
+        if self.tr.launches != self._launch:
+            raise RuntimeError("stale DeviceWindowBatch: the sampler has launched another rollout since this batch was "
+                               "returned; add it to the buffer (or materialize() it) before the next sample()")
 
     def count(self):
+        self.check_current()
         return int(self.tr.emit[self.tr.H:].sum().item())
 
     def __len__(self):
@@ -150,6 +176,7 @@ class DeviceWindowBatch:
 
     def materialize(self):
         """Host list of nStepExperience in the reference's order (step-major, env-minor)."""
+        self.check_current()
         tr, ns = self.tr, self.n_step
         emit = self.tr.emit[tr.H:].cpu().numpy().astype(bool)
         f = {k: v.cpu().numpy() for k, v in tr.fields().items()}
@@ -168,13 +195,14 @@ class FusedRollout:
     """Owns env state + transition buffers and launches msacl_rollout_fused."""
 
     def __init__(self, env_name, num_envs, horizon, n_step=20, reward_scale=100.0, cost_scale=100.0, seed=0, env_base=0,
-                 device="cuda", max_step=None, state=None, engine="ffma", history_chunks=None):
+                 device="cuda", max_step=None, state=None, engine="ffma", history_chunks=None, record_logits=False):
         self.engine = engine
         self.spec = get_spec(env_name)
         self.state = state or EnvStateBuffers(env_name, num_envs, seed=seed, env_base=env_base, device=device, max_step=max_step)
         self.n, self.K, self.n_step = self.state.n, int(horizon), int(n_step)
         self.reward_scale, self.cost_scale = float(reward_scale), float(cost_scale)
-        self.tr = TransitionBuffers(self.spec, self.n, self.K, self.n_step, self.state.device, chunks=history_chunks)
+        self.tr = TransitionBuffers(self.spec, self.n, self.K, self.n_step, self.state.device, chunks=history_chunks,
+                                    record_logits=record_logits)
         self.stats = torch.zeros(32, dtype=torch.float64, device=self.state.device)   # [0:8) documented, rest diagnostic
         self.global_step = 0
 
@@ -184,8 +212,13 @@ class FusedRollout:
         if actor.obs_dim != self.spec.obs_dim or actor.act_dim != self.spec.act_dim:
             raise ValueError("actor dimensions do not match the environment")
         tr = self.tr
-        tr.roll_history()
-        out = tr.desc(tr.H) if write else _lib.Transitions()
+        if write:
+            tr.roll_history()
+            out = tr.desc(tr.H)
+        else:
+            # nothing is recorded: the store keeps its chunk, and the n-step run counters restart so that no window can
+            # straddle the unrecorded steps
+            out = _lib.Transitions()
         if eps is not None:
             eps = eps.contiguous()
             assert tuple(eps.shape) == (self.K, self.n, self.spec.act_dim) and eps.is_cuda
@@ -202,6 +235,9 @@ class FusedRollout:
         else:
             raise ValueError(f"unknown rollout engine {engine!r}")
         self.global_step += self.K
+        if not write:
+            self.state.run.zero_()
+            return None
         return DeviceWindowBatch(tr, self.n_step)
 
 
@@ -235,6 +271,7 @@ class B200NstepOffSampler:
                                     history_chunks=kwargs.get("history_chunks"))
         self.envs.state.reset()        # base.py:98  envs.reset(seed=None)
         self._actor = None
+        self._actor_cache = None
 
     @property
     def obs(self):
@@ -251,8 +288,19 @@ class B200NstepOffSampler:
     def set_actor(self, actor: ActorWeights):
         self._actor = actor
 
+    def _current_actor(self):
+        """Packed device copy of `networks.policy`, rebuilt (transpose + split-bf16 operand images) only when a parameter
+        changed since the last call -- at the reference's default env_num=4 the repack would otherwise dominate sample()."""
+        if self.networks is None:
+            return self._actor
+        pol = self.networks.policy
+        ver = (id(pol), ActorWeights.policy_version(pol))
+        if self._actor_cache is None or self._actor_cache[0] != ver:
+            self._actor_cache = (ver, ActorWeights.from_policy(pol, device=self.device))
+        return self._actor_cache[1]
+
     def _sample(self):
-        actor = self._actor if self.networks is None else ActorWeights.from_policy(self.networks.policy, device=self.device)
+        actor = self._current_actor()
         if actor is None:
             raise RuntimeError("sampler has no policy: assign `.networks` or call set_actor()")
         return self.rollout.run(actor)

@@ -365,7 +365,100 @@ def msacl_update_case(name="TwoLink", B=32, n_step=20, seed=21):
     return out
 
 
+# ------------------------------------------------------------------ E. NormalizeOrientMatrix incl. the det < 0 branch
+def quad_polar_case(seed=31, m=96):
+    """Reference NormalizeOrientMatrix (QuadTracking.py:308-315) on (a) the inputs the dynamics produce (a rotation times
+    I + h hat(w)) and (b) improper inputs (det < 0) with well separated singular values, which take the column-flip
+    branch (:312-314)."""
+    from RL.env.QuadTracking import NormalizeOrientMatrix
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    mats = []
+    for i in range(m):
+        Q = Rotation.from_rotvec(rng.normal(size=3) * rng.uniform(0.1, 3.0)).as_matrix()
+        if i % 2 == 0:
+            w = rng.normal(size=3) * rng.uniform(0.1, 12.0)
+            hat = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+            M = Q @ (np.eye(3) + 0.01 * hat)
+        else:
+            Q2 = Rotation.from_rotvec(rng.normal(size=3)).as_matrix()
+            sv = np.array([rng.uniform(1.2, 1.5), rng.uniform(0.9, 1.1), rng.uniform(0.5, 0.7)])
+            M = Q @ np.diag(sv * np.array([1.0, 1.0, -1.0])) @ Q2          # det < 0
+        mats.append(M.astype(f32))
+    mats = np.stack(mats)
+    out = np.stack([NormalizeOrientMatrix(M.copy()) for M in mats])
+    assert out.dtype == np.float32
+    return dict(mat_in=mats, mat_out=out, det_in=np.linalg.det(mats.astype(np.float64)))
+
+
+# ------------------------------------------------------------------ F. Evaluator.run_parallel_episodes
+def evaluator_case(name, episodes=12, max_step=60, seed=41, bias_shift=(-0.6, 0.9), spread=0.97):
+    """Reference `Evaluator.run_parallel_episodes` (RL/trainer/evaluator.py:141-204) with recorded policy weights and
+    recorded initial env states: the vector env's reset is called once by this script (states recorded), then
+    `envs.reset` on the INSTANCE returns those observations, so the evaluation starts from known states."""
+    from RL.trainer.evaluator import Evaluator
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    args = base_args(name, episodes, 20)
+    args.update(eval_env_seed=seed, num_eval_episode=episodes, is_render=False, save_folder="/tmp/msacl_golden_eval",
+                is_parallel_eval=True)
+    ev = Evaluator(**args)
+    with torch.no_grad():      # a livelier policy: some episodes leave the box before the time limit
+        last = [m for m in ev.networks.policy.policy if isinstance(m, torch.nn.Linear)][-1]
+        last.bias[: args["act_dim"]] += torch.linspace(bias_shift[0], bias_shift[1], args["act_dim"])
+    out = policy_weights(ev.networks.policy)
+    for e in ev.envs.envs:
+        e.unwrapped.max_step = max_step
+    obs0, _ = ev.envs.reset(seed=seed)
+    if name != "QuadTracking":     # spread the initial states over the box so that terminations happen
+        rng = np.random.default_rng(seed)
+        hi = ev.envs.single_observation_space.high
+        for i, e in enumerate(ev.envs.envs):
+            if i % 3 == 0:
+                e.unwrapped.obs = (rng.uniform(-spread, spread, size=hi.shape) * hi).astype(f32)
+        obs0 = np.stack([e.unwrapped.obs.copy() for e in ev.envs.envs])
+    st0 = [env_full_state(name, e) for e in ev.envs.envs]
+    for k in st0[0]:
+        out[f"init_{k}"] = np.stack([s[k] for s in st0])
+    ev.envs.reset = lambda seed=None, options=None: (obs0.copy(), {})
+    ep_len = []
+    real_step = ev.envs.step
+    first_done = np.full(episodes, -1)
+    counter = {"t": 0}
+
+    def spy(actions):
+        ret = real_step(actions)
+        d = np.logical_or(ret[2], ret[3])
+        for i in range(episodes):
+            if d[i] and first_done[i] < 0:
+                first_done[i] = counter["t"] + 1
+        counter["t"] += 1
+        return ret
+
+    ev.envs.step = spy
+    trm, trs, tcm, tcs = ev.run_parallel_episodes()
+    out.update(trm=np.float64(trm), trs=np.float64(trs), tcm=np.float64(tcm), tcs=np.float64(tcs),
+               first_episode_len=first_done.astype(np.int32), max_step=np.int32(max_step), episodes=np.int32(episodes),
+               reward_scale=f32(args["reward_scale"]), cost_scale=f32(args["cost_scale"]))
+    return out
+
+
+def extra_cases():
+    """Round-2 additions; separate seeds, so the round-1 files above reproduce bit for bit."""
+    path = os.path.join(HERE, "quad_polar.npz")
+    np.savez_compressed(path, **quad_polar_case())
+    print("wrote", path)
+    for name in ("VanderPol", "TwoLink", "QuadTracking"):
+        path = os.path.join(HERE, f"evaluator_{name}.npz")
+        kw = {"VanderPol": dict(max_step=60), "TwoLink": dict(max_step=60, bias_shift=(-0.2, 0.2), spread=0.45),
+              "QuadTracking": dict(max_step=40, bias_shift=(0.0, 0.0))}[name]
+        data = evaluator_case(name, **kw)
+        np.savez_compressed(path, **data)
+        print("wrote", path, {k: data[k] for k in ("trm", "trs", "tcm", "tcs")}, data["first_episode_len"])
+
+
 def main():
+    if "--only-extra" in sys.argv:
+        return extra_cases()
     if "--only-update" in sys.argv:
         path = os.path.join(HERE, "msacl_update_TwoLink.npz")
         np.savez_compressed(path, **msacl_update_case())
@@ -388,6 +481,7 @@ def main():
     path = os.path.join(HERE, "msacl_update_TwoLink.npz")
     np.savez_compressed(path, **msacl_update_case())
     print("wrote", path)
+    extra_cases()
 
 
 if __name__ == "__main__":

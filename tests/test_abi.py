@@ -24,7 +24,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/msacl_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES and the header disagree"
-    assert lib.msacl_abi_version() == 1
+    assert lib.msacl_abi_version() == 2
 
 
 def test_env_dims_match_spec_table():

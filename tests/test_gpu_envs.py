@@ -185,3 +185,41 @@ def test_env_step_vs_oracle_seeded_multistep(name):
         assert n_done > 0
     finally:
         object.__setattr__(spec, "max_step", 1000)
+
+
+def test_quad_polar_device_vs_reference_incl_reflection_branch():
+    """Device NormalizeOrientMatrix (Newton polar) vs the reference's SVD path on recorded inputs, including improper
+    matrices (det < 0) that take the reference's column-flip branch (QuadTracking.py:312-314).  Tolerance 2e-6: the
+    improper inputs have singular values in [0.5, 1.5], i.e. far from the near-rotations the dynamics feed it."""
+    import msacl_b200
+    from msacl_b200 import _lib
+    g = load_golden("quad_polar.npz")
+    lib = msacl_b200.load_library()
+    m = torch.as_tensor(g["mat_in"]).cuda().contiguous()
+    for theta2 in (0.0, 0.05):
+        out = torch.empty_like(m)
+        _lib.check(lib.msacl_selftest_quad_polar(m.data_ptr(), out.data_ptr(), m.shape[0], theta2, _lib.current_stream()))
+        got = out.cpu().numpy()
+        neg = g["det_in"] < 0
+        np.testing.assert_allclose(got[neg], g["mat_out"][neg], rtol=0, atol=2e-6)
+        if theta2 > 0:     # proper inputs: three sweeps converge for every |w| of the recorded set
+            np.testing.assert_allclose(got[~neg], g["mat_out"][~neg], rtol=0, atol=5e-7)
+    assert neg.sum() >= 40
+
+
+def test_bare_env_continues_from_terminal_state():
+    """B200Env (single instance, reference gym.Env surface): no autoreset -- a step after terminated=True continues from
+    the terminal state exactly as the reference class does (VanderPol.py:100-130), checked against the oracle."""
+    from msacl_b200.envs import B200Env
+    env = B200Env("VanderPol")
+    env.reset(seed=3)
+    env._v.state.set_box_state(np.array([[9.9, 9.0]], np.float32))
+    st = {"obs": np.array([[9.9, 9.0]], np.float32), "step": np.zeros(1, np.int32)}
+    seen_term = False
+    for k in range(4):
+        a = np.array([5.0], np.float32)
+        obs, rew, term, trunc, _ = env.step(a)
+        st, oobs, orew, oterm, _ = oenv.env_step("VanderPol", st, a[None])
+        assert np.array_equal(obs, oobs[0]) and rew == orew[0] and term == bool(oterm[0]) and not trunc
+        seen_term |= term
+    assert seen_term

@@ -12,25 +12,8 @@ pytestmark = pytest.mark.gpu
 
 
 def oracle_evaluate(name, weights, state, seed, max_step, reward_scale=100.0, cost_scale=100.0):
-    spec = oenv.SPECS[name]
-    n = state["obs"].shape[0]
-    venv = oroll.VectorEnv(name, state, seed=seed, env_ids=np.arange(n, dtype=np.uint64))
-    rets, costs = [[] for _ in range(n)], [[] for _ in range(n)]
-    finished = np.zeros(n, bool)
-    while not finished.all():
-        obs = venv.obs.astype(np.float32)
-        mean, _ = oactor.policy_forward(weights, obs)
-        act = oactor.tanh_gauss_mode(mean, spec.act_low, spec.act_high)          # no clip in the evaluator (:158-160)
-        next_obs, reward, term, trunc, final_obs, _ = venv.step(act)
-        done = term | trunc
-        real_next = np.where(done[:, None], final_obs, next_obs)
-        rew = reward.astype(np.float32) * reward_scale
-        cost = oenv.np_pairwise_rowsum(real_next.astype(np.float32) ** 2) * cost_scale
-        for i in range(n):
-            if not finished[i]:
-                rets[i].append(rew[i]); costs[i].append(cost[i]); finished[i] = done[i]
-    er, ec = [np.mean(r) for r in rets], [np.mean(c) for c in costs]
-    return np.mean(er), np.std(er), np.mean(ec), np.std(ec)
+    from oracle import evaluator as oeval
+    return oeval.run_parallel_episodes(name, weights, state, seed, reward_scale, cost_scale)
 
 
 @pytest.mark.parametrize("name,engine", [("VanderPol", "ffma"), ("DuctedFan", "tc"), ("QuadTracking", "ffma")])
@@ -58,3 +41,30 @@ def test_evaluator_matches_oracle(name, engine):
         object.__setattr__(spec, "max_step", 1000)
     # greedy closed-loop rollouts of up to 30 steps: trajectories agree to ~1e-4 relative
     np.testing.assert_allclose(got, want, rtol=2e-3, atol=1e-3 * max(1.0, abs(want[0])))
+
+
+@pytest.mark.parametrize("name", ["VanderPol", "TwoLink", "QuadTracking"])
+@pytest.mark.parametrize("engine", ["tc", "ffma"])
+def test_evaluator_matches_reference_golden(name, engine):
+    """The reference Evaluator's own run (tests/golden/evaluator_*.npz: its policy weights, its initial env states, its
+    TRM / TRS / TCM / TCS) reproduced by B200Evaluator on the fused kernel.  Free-running greedy closed loop of up to 60
+    steps: 2e-3 relative (split-bf16 actor 1e-4 * action range per step, amplified by the closed loop)."""
+    from conftest import load_golden
+    from msacl_b200.evaluator import B200Evaluator
+    from msacl_b200.sampler import ActorWeights
+    g = load_golden(f"evaluator_{name}.npz")
+    n, max_step = int(g["episodes"]), int(g["max_step"])
+    ev = B200Evaluator(env_name=name, num_eval_episode=n, reward_scale=float(g["reward_scale"]), cost_scale=float(g["cost_scale"]),
+                       eval_env_seed=0, max_step=max_step, eval_chunk_steps=16, rollout_engine=engine)
+
+    def init(state):
+        if name == "QuadTracking":
+            state.set_quad_state(g["init_x"], g["init_v"], g["init_R"], g["init_Om"], t=g["init_t"], Rd_last=g["init_Rd_last"],
+                                 obs=g["init_obs"], step=g["init_step"])
+        else:
+            state.set_box_state(g["init_obs"], g["init_step"])
+
+    got = ev.run_parallel_episodes(ActorWeights([(g[f"W{i}"], g[f"b{i}"]) for i in range(3)]), state_init=init)
+    want = (float(g["trm"]), float(g["trs"]), float(g["tcm"]), float(g["tcs"]))
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=1e-3 * abs(want[0]))
+    assert (ev.last_first_episode_len.cpu().numpy() == g["first_episode_len"]).all()

@@ -210,3 +210,29 @@ def test_oracle_polyak_matches_torch_ops():
         got = otg.polyak_update([t.numpy() for t in ts], [p.numpy() for p in ps], tau)
         for w, gq in zip(want, got):
             assert np.array_equal(w.numpy(), gq)
+
+
+def test_quad_polar_incl_reflection_branch():
+    """NormalizeOrientMatrix (QuadTracking.py:308-315) incl. its det < 0 column flip (:312-314)."""
+    g = load_golden("quad_polar.npz")
+    assert (g["det_in"] < 0).sum() >= 40 and (g["det_in"] > 0).sum() >= 40
+    got = envs._polar_svd(g["mat_in"])
+    np.testing.assert_allclose(got, g["mat_out"], rtol=0, atol=2e-7)
+    assert np.all(np.linalg.det(got.astype(np.float64)) > 0.99)
+
+
+@pytest.mark.parametrize("name", ["VanderPol", "TwoLink", "QuadTracking"])
+def test_evaluator_matches_reference(name):
+    """oracle.evaluator vs a recorded run of the reference Evaluator.run_parallel_episodes (evaluator.py:141-204)."""
+    from oracle import evaluator as oeval
+    g = load_golden(f"evaluator_{name}.npz")
+    spec = envs.SPECS[name]
+    object.__setattr__(spec, "max_step", int(g["max_step"]))
+    try:
+        got, lens = oeval.run_parallel_episodes(name, _weights(g), _init_state(name, g), 0, float(g["reward_scale"]),
+                                                float(g["cost_scale"]), return_lengths=True)
+    finally:
+        object.__setattr__(spec, "max_step", 1000)
+    assert np.array_equal(lens, g["first_episode_len"])
+    want = (float(g["trm"]), float(g["trs"]), float(g["tcm"]), float(g["tcs"]))
+    np.testing.assert_allclose(got, want, rtol=2e-4)
