@@ -181,6 +181,23 @@ int msacl_window_store(const msacl_transitions_t* tr, int32_t H, int32_t K, int6
 int msacl_ring_gather(const msacl_ring_t* ring, const int64_t* idx, int64_t B, const msacl_ring_t* batch,
                       void* stream);
 
+/* Index-based n-step window store: instead of copying every emitted window into a
+ * [max_size][n_step][.] ring (2 * 4 * n_step * (2D + A + 4) bytes of traffic per window), only the flat position
+ * (slice * n + env) of the window's NEWEST transition inside the caller's [T][n][.] transition store is appended to
+ * an int64 ring `win_pos[max_size]`, in the reference's append order and with the reference's ptr / size arithmetic
+ * (RL/trainer/sampler/base.py:178-217, nstep_replay_buffer.py:106-119); the n_step rows are gathered when a batch is
+ * sampled (nstep_replay_buffer.py:138-146).  The caller keeps the n_step - 1 slices in front of a window's newest slice
+ * contiguous in the store and retires windows before their slices are overwritten (buffer.B200IndexedReplayBuffer).
+ *   emit_new  [K][n] emit flags of the K new slices;  base_pos = flat position of emit_new[0][0] in the store
+ *   scratch   int64[msacl_window_store_scratch_elems(K, n)] */
+int msacl_window_index_store(const uint8_t* emit_new, int32_t K, int64_t n, int64_t base_pos, int64_t* win_pos,
+                             int64_t max_size, int64_t* ptr_size, int64_t* count_out, int64_t* scratch, void* stream);
+/* batch[b] = the window whose newest transition sits at store position win_pos[idx[b]]: rows
+ * pos - (n_step-1-r)*n, r = 0..n_step-1, of every field (done: uint8 -> 0.0/1.0 float), written as [B][n_step][.].
+ * tr: base pointers of the whole [T][n][.] store (emit / logits unused). */
+int msacl_window_gather_indexed(const msacl_transitions_t* tr, int64_t n, const int64_t* win_pos, const int64_t* idx,
+                                int64_t B, const msacl_ring_t* batch, void* stream);
+
 /* MSACL soft-TD backup (RL/algorithm/msacl.py:249-252), elementwise over B*n. */
 int msacl_q_backup(int64_t count, const float* rew, const float* done, const float* next_q1, const float* next_q2,
                    const float* next_logp, float gamma, float alpha, float* backup, void* stream);

@@ -29,8 +29,10 @@ def create_sampler(**kwargs):
 
 def create_buffer(**kwargs):
     """Drop-in for RL/create_pkg/create_buffer.py:44-66 (buffer_name 'nstep_replay_buffer')."""
-    from .buffer import B200NstepReplayBuffer
+    from .buffer import B200IndexedReplayBuffer, B200NstepReplayBuffer
     name = kwargs.get("buffer_name", "nstep_replay_buffer")
+    if name == "b200_indexed_replay_buffer":          # index-based windows over the sampler's transition store
+        return B200IndexedReplayBuffer(**kwargs)
     if name not in ("nstep_replay_buffer", "b200_nstep_replay_buffer"):
         raise KeyError(f"No registered buffer with id: {name}")
     return B200NstepReplayBuffer(**kwargs)

@@ -107,3 +107,123 @@ class B200NstepReplayBuffer:
         size = self._ptr_size[1]
         idx = torch.minimum((u * size).to(torch.int64), torch.clamp(size - 1, min=0))
         return self.gather(idx)
+
+
+class B200IndexedReplayBuffer:
+    """Index-based n-step replay with the `NstepReplayBuffer` surface (`add_batch`, `sample_batch`,
+    `size`, `ptr`, `len()`, `__get_RAM__()`; RL/trainer/buffer/nstep_replay_buffer.py:40-150).
+
+    The payload is the sampler's own `[H + M*K, n, .]` transition store (what the rollout kernel writes anyway,
+    4*(2D+A+3)+2 bytes per transition); a window is the flat position of its newest transition, kept in an int64 ring
+    of `buffer_max_size` entries with the reference's append order and ptr / size arithmetic.  Appending a chunk costs
+    8 bytes per emitted window instead of copying n_step rows twice, and a store of S transitions serves ~S windows
+    instead of S / n_step -- a replay that scales with a 2e9 env-steps/s sampler.
+
+    Retention: a window lives as long as its n_step slices are in the store, i.e. for M - 2 further launches
+    (M = chunks of the sampler's store).  `sample_batch` draws uniformly from the most recent
+    min(size, windows emitted by the last M - 2 launches) entries; with
+    M >= chunks_for(buffer_max_size, env_num, horizon) that is the whole ring whenever every transition emits, and
+    it is exactly the reference's `randint(0, size)` as long as buffer_max_size >= windows produced."""
+
+    def __init__(self, **kwargs):
+        self.obsv_dim = int(kwargs["obs_dim"])
+        self.act_dim = int(kwargs["act_dim"])
+        self.max_size = int(kwargs["buffer_max_size"])
+        self.n_step = int(kwargs["n_step"])
+        self.device = torch.device(kwargs.get("device", "cuda"))
+        self.win_pos = torch.zeros(self.max_size, dtype=torch.int64, device=self.device)
+        self._ptr_size = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._scratch = None
+        self._host_ps = (0, 0)
+        self._tr = None                  # the sampler's TransitionBuffers, bound on the first add_batch
+        self._launch_counts = None       # windows emitted by each of the last M - 2 launches (device, circular)
+        self._adds = 0
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(int(kwargs.get("seed") or 0))
+
+    @staticmethod
+    def chunks_for(buffer_max_size, num_envs, horizon):
+        """Chunks of K = horizon slices the sampler's store needs so that buffer_max_size windows stay resident."""
+        per_launch = max(1, int(num_envs) * int(horizon))
+        return max(3, -(-int(buffer_max_size) // per_launch) + 2)
+
+    def _host_counters(self):
+        if self._host_ps is None:
+            self._host_ps = tuple(int(x) for x in self._ptr_size.tolist())
+        return self._host_ps
+
+    ptr = property(lambda self: self._host_counters()[0])
+    size = property(lambda self: self._host_counters()[1])
+
+    def __len__(self):
+        return self.size
+
+    def __get_RAM__(self):
+        """MB the stored windows occupy: their share of the transition store + the position ring."""
+        if self._tr is None or self.size == 0:
+            return 0.0
+        per = 4 * (2 * self.obsv_dim + self.act_dim + 3) + 2 + 8
+        return round(per * self.size / (1024 * 1024), 2)
+
+    def store(self, *a, **k):
+        raise NotImplementedError("the index-based buffer stores windows by reference to the sampler's device transition store; "
+                                  "use B200NstepReplayBuffer for host-side store()")
+
+    def add_batch(self, batch):
+        if not isinstance(batch, DeviceWindowBatch):
+            raise NotImplementedError("B200IndexedReplayBuffer.add_batch takes the DeviceWindowBatch returned by sampler.sample()")
+        batch.check_current()
+        tr = batch.tr
+        if self._tr is None:
+            if tr.M < 3:
+                raise ValueError("index-based replay needs a transition store of >= 3 chunks (sampler kwarg history_chunks, "
+                                 "or buffer_name='b200_indexed_replay_buffer' in the sampler's kwargs)")
+            if tr.H < self.n_step - 1:
+                raise ValueError("transition store history is shorter than n_step - 1")
+            self._tr = tr
+            self._launch_counts = torch.zeros(tr.M - 2, dtype=torch.int64, device=self.device)
+        elif tr is not self._tr:
+            raise ValueError("B200IndexedReplayBuffer is bound to one sampler's transition store")
+        lib = _lib.load()
+        need = int(lib.msacl_window_store_scratch_elems(tr.K, tr.n))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.zeros(need, dtype=torch.int64, device=self.device)
+        base = tr.chunk_base_slice * tr.n
+        emit_new = tr._full["emit"][tr.chunk_base_slice:]
+        self._host_ps = None
+        _lib.check(lib.msacl_window_index_store(emit_new.data_ptr(), tr.K, tr.n, base, self.win_pos.data_ptr(), self.max_size,
+                                                self._ptr_size.data_ptr(), self._count.data_ptr(), self._scratch.data_ptr(),
+                                                _lib.current_stream()))
+        self._launch_counts[self._adds % (tr.M - 2)] = self._count[0]
+        self._adds += 1
+        return self._count
+
+    add_device_batch = add_batch
+
+    def valid_count(self):
+        """Device scalar: number of most-recent ring entries whose slices are still resident."""
+        return torch.minimum(self._ptr_size[1], self._launch_counts.sum())
+
+    def gather(self, idx):
+        """idx: ring slots (as the reference's fancy indexing of n_step_buf)."""
+        idx = torch.as_tensor(idx, dtype=torch.int64, device=self.device).contiguous()
+        B = idx.numel()
+        n, D, A = self.n_step, self.obsv_dim, self.act_dim
+        z = lambda *s: torch.empty(B, n, *s, dtype=torch.float32, device=self.device)
+        out = {"obs": z(D), "act": z(A), "rew": z(), "cost": z(), "obs2": z(D), "done": z(), "logp": z()}
+        dst = _lib.Ring(max_size=B, n_step=n, obs_dim=D, act_dim=A, **{k: out[k].data_ptr() for k in FIELDS})
+        desc = self._tr.full_desc()
+        _lib.check(_lib.load().msacl_window_gather_indexed(C.byref(desc), self._tr.n, self.win_pos.data_ptr(), idx.data_ptr(), B,
+                                                          C.byref(dst), _lib.current_stream()))
+        return out
+
+    def sample_batch(self, batch_size: int) -> dict:
+        """Uniform with replacement over the resident windows (nstep_replay_buffer.py:138), drawn on the device."""
+        if self._tr is None:
+            raise RuntimeError("sample_batch before any add_batch")
+        u = torch.rand(int(batch_size), device=self.device, generator=self._gen, dtype=torch.float64)
+        valid = self.valid_count()
+        back = torch.minimum((u * valid).to(torch.int64), torch.clamp(valid - 1, min=0))      # 0 = newest entry
+        slot = torch.remainder(self._ptr_size[0] - 1 - back, self.max_size)
+        return self.gather(slot)

@@ -70,65 +70,40 @@ __global__ void __launch_bounds__(1024) window_scan_kernel(int64_t* __restrict__
   }
 }
 
-constexpr int SC_IT = 3;   // register-resident path of the scatter: up to 96 obs vectors and 96 act scalars per window
+constexpr int SC_IT = 3;   // register-resident path of the copy: up to 96 obs vectors and 96 act scalars per window
 template <int N> struct ObsVec;
 template <> struct ObsVec<4> { using type = float4; };
 template <> struct ObsVec<2> { using type = float2; };
 template <> struct ObsVec<1> { using type = float; };
 
-// W = obs vector width in floats (4 if obs_dim % 4 == 0, 2 if even, else 1)
+// One warp copies one n-step window out of the [T][n][.] transition store into entry `slot` of a [.][n_step][.] window
+// array (the replay ring of window_scatter_kernel, or the sampled batch of window_gather_indexed_kernel).
+// A window's rows come from ns transition slices (stride n rows), its destination entry is contiguous per field.  Work
+// items are OW-float vectors of the obs / obs2 rows (OW = 4, 2 or 1: the widest that divides obs_dim), scalars of the act
+// rows, and one lane per row for the four per-step scalars.  The item -> (row, offset) map is the same for every
+// window: each lane derives it once and then walks it with additions only (no division per window).
 template <int W>
-__global__ void __launch_bounds__(WB)
-window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_flags, msacl_ring_t ring,
-                      const int64_t* __restrict__ block_offsets, const int64_t* __restrict__ header) {
-  __shared__ int warp_counts[WB / 32];
-  __shared__ int64_t s_slot[WB];
-  __shared__ int64_t s_src[WB];   // flat (t, i) index of the newest transition of the window
-  __shared__ int s_num;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t f = (int64_t)blockIdx.x * WB + tid;
-  const uint8_t* emit_new = tr.emit + (int64_t)H * n;
-  const int flag = (f < total_flags && emit_new[f]) ? 1 : 0;
-  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
-  if (lane == 0) warp_counts[warp] = __popc(ballot);
-  __syncthreads();
-  int before = 0;
-  for (int w = 0; w < warp; ++w) before += warp_counts[w];
-  const int local = before + __popc(ballot & ((1u << lane) - 1u));
-  if (tid == 0) {
-    int s = 0;
-    for (int w = 0; w < WB / 32; ++w) s += warp_counts[w];
-    s_num = s;
+struct WindowCopier {
+  using VecT = typename ObsVec<W>::type;
+  static constexpr int OW = W;
+  const msacl_transitions_t& tr;
+  const msacl_ring_t& ring;
+  int64_t n, row_stride, arow_stride;
+  int lane, ns, D, A, vpr, nv, na, r0, q0, dr, dq, ar0, aj0, adr, adj;
+
+  __device__ __forceinline__ WindowCopier(const msacl_transitions_t& tr_, int64_t n_, const msacl_ring_t& ring_, int lane_)
+      : tr(tr_), ring(ring_), n(n_), lane(lane_) {
+    ns = ring.n_step; D = ring.obs_dim; A = ring.act_dim;
+    vpr = D / OW;                         // obs vectors per row
+    nv = ns * vpr; na = ns * A;
+    r0 = lane / vpr; q0 = lane - r0 * vpr; dr = 32 / vpr; dq = 32 - dr * vpr;
+    ar0 = lane / A; aj0 = lane - ar0 * A; adr = 32 / A; adj = 32 - adr * A;
+    row_stride = n * (int64_t)D; arow_stride = n * (int64_t)A;
   }
-  const int64_t old_ptr = header[0], total = header[1];
-  if (flag) {
-    const int64_t order = block_offsets[blockIdx.x] + local;   // position in the reference's append order
-    // windows that a later window of the same call would overwrite are skipped (sequential
-    // store semantics: the last writer wins)
-    const bool live = (total - order) <= ring.max_size;
-    s_slot[local] = live ? (old_ptr + order) % ring.max_size : -1;
-    s_src[local] = f + (int64_t)H * n;
-  }
-  __syncthreads();
-  const int num = s_num;
-  const int ns = ring.n_step, D = ring.obs_dim, A = ring.act_dim;
-  // A window's rows come from ns transition slices (stride n rows), its ring entry is contiguous per field.  Work items
-  // are OW-float vectors of the obs / obs2 rows (OW = 4, 2 or 1: the widest that divides obs_dim), scalars of the act
-  // rows, and one lane per row for the four per-step scalars.  The item -> (row, offset) map is the same for every
-  // window: each lane derives it once and then walks it with additions only (no division in the window loop).
-  constexpr int OW = W;
-  const int vpr = D / OW;                         // obs vectors per row
-  const int nv = ns * vpr, na = ns * A;
-  const int r0 = lane / vpr, q0 = lane - r0 * vpr, dr = 32 / vpr, dq = 32 - dr * vpr;
-  const int ar0 = lane / A, aj0 = lane - ar0 * A, adr = 32 / A, adj = 32 - adr * A;
-  const int64_t row_stride = n * (int64_t)D, arow_stride = n * (int64_t)A;
-  using VecT = typename ObsVec<OW>::type;
-  for (int w = warp; w < num; w += WB / 32) {
-    const int64_t slot = s_slot[w];
-    if (slot < 0) continue;
-    const int64_t newest = s_src[w];
-    const int64_t t_new = newest / n, i = newest - t_new * n;
-    const int64_t first = (t_new - (ns - 1)) * n + i;              // flat (t, i) row index of the window's oldest transition
+
+  // newest = flat (t, i) index of the window's newest transition in the store
+  __device__ __forceinline__ void copy(int64_t newest, int64_t slot) const {
+    const int64_t first = newest - (int64_t)(ns - 1) * n;           // flat (t, i) row index of the window's oldest transition
     const float* so = tr.obs + first * D;
     const float* so2 = tr.obs2 + first * D;
     const float* sa = tr.act + first * A;
@@ -181,7 +156,7 @@ window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_fl
         ring.done[slot * ns + lane] = vd ? 1.0f : 0.0f;
         ring.logp[slot * ns + lane] = vl;
       }
-      continue;
+      return;
     }
     {
       int r = r0, q = q0;
@@ -209,6 +184,82 @@ window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_fl
       ring.logp[slot * ns + r] = tr.logp[src];
     }
   }
+};
+
+// W = obs vector width in floats (4 if obs_dim % 4 == 0, 2 if even, else 1)
+template <int W>
+__global__ void __launch_bounds__(WB)
+window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_flags, msacl_ring_t ring,
+                      const int64_t* __restrict__ block_offsets, const int64_t* __restrict__ header) {
+  __shared__ int warp_counts[WB / 32];
+  __shared__ int64_t s_slot[WB];
+  __shared__ int64_t s_src[WB];   // flat (t, i) index of the newest transition of the window
+  __shared__ int s_num;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t f = (int64_t)blockIdx.x * WB + tid;
+  const uint8_t* emit_new = tr.emit + (int64_t)H * n;
+  const int flag = (f < total_flags && emit_new[f]) ? 1 : 0;
+  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) warp_counts[warp] = __popc(ballot);
+  __syncthreads();
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += warp_counts[w];
+  const int local = before + __popc(ballot & ((1u << lane) - 1u));
+  if (tid == 0) {
+    int s = 0;
+    for (int w = 0; w < WB / 32; ++w) s += warp_counts[w];
+    s_num = s;
+  }
+  const int64_t old_ptr = header[0], total = header[1];
+  if (flag) {
+    const int64_t order = block_offsets[blockIdx.x] + local;   // position in the reference's append order
+    // windows that a later window of the same call would overwrite are skipped (sequential
+    // store semantics: the last writer wins)
+    const bool live = (total - order) <= ring.max_size;
+    s_slot[local] = live ? (old_ptr + order) % ring.max_size : -1;
+    s_src[local] = f + (int64_t)H * n;
+  }
+  __syncthreads();
+  const int num = s_num;
+  WindowCopier<W> cp(tr, n, ring, lane);
+  for (int w = warp; w < num; w += WB / 32) {
+    const int64_t slot = s_slot[w];
+    if (slot < 0) continue;
+    cp.copy(s_src[w], slot);
+  }
+}
+
+// ---- index-based window store: a window is the flat position of its newest transition in the
+// [T][n][.] transition store the rollout kernel already wrote; nothing is copied at append time (8 bytes per window
+// instead of 8 * n_step * (2D + A + 4)), and the n rows are gathered when a batch is sampled.
+__global__ void __launch_bounds__(WB)
+window_index_scatter_kernel(const uint8_t* __restrict__ emit_new, int64_t total_flags, int64_t base_pos,
+                            int64_t* __restrict__ win_pos, int64_t max_size, const int64_t* __restrict__ block_offsets,
+                            const int64_t* __restrict__ header) {
+  __shared__ int warp_counts[WB / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t f = (int64_t)blockIdx.x * WB + tid;
+  const int flag = (f < total_flags && emit_new[f]) ? 1 : 0;
+  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) warp_counts[warp] = __popc(ballot);
+  __syncthreads();
+  if (!flag) return;
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += warp_counts[w];
+  const int64_t order = block_offsets[blockIdx.x] + before + __popc(ballot & ((1u << lane) - 1u));
+  const int64_t old_ptr = header[0], total = header[1];
+  if ((total - order) <= max_size) win_pos[(old_ptr + order) % max_size] = base_pos + f;     // last writer wins
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+window_gather_indexed_kernel(msacl_transitions_t tr, int64_t n, const int64_t* __restrict__ win_pos,
+                             const int64_t* __restrict__ idx, int64_t B, msacl_ring_t batch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x / 32);
+  WindowCopier<W> cp(tr, n, batch, lane);
+  for (int64_t b = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); b < B; b += wstride)
+    cp.copy(win_pos[idx[b]], b);
 }
 
 // One warp per sampled window (grid-stride).  Every field of a window is a contiguous run of floats; with
@@ -319,6 +370,44 @@ extern "C" int msacl_window_store(const msacl_transitions_t* tr, int32_t H, int3
   else if (W == 2) window_scatter_kernel<2><<<(unsigned)nb, WB, 0, s>>>(*tr, H, n, total, *ring, scratch + 2, scratch);
   else window_scatter_kernel<1><<<(unsigned)nb, WB, 0, s>>>(*tr, H, n, total, *ring, scratch + 2, scratch);
   return check_launch("window_store");
+}
+
+extern "C" int msacl_window_index_store(const uint8_t* emit_new, int32_t K, int64_t n, int64_t base_pos, int64_t* win_pos,
+                                        int64_t max_size, int64_t* ptr_size, int64_t* count_out, int64_t* scratch,
+                                        void* stream) {
+  if (!emit_new || !win_pos || !ptr_size || !scratch || K <= 0 || n <= 0 || max_size <= 0 || base_pos < 0) {
+    set_error("window_index_store: bad argument");
+    return MSACL_ERR_BAD_ARG;
+  }
+  const int64_t total = (int64_t)K * n;
+  const int64_t nb = (total + WB - 1) / WB;
+  cudaStream_t s = (cudaStream_t)stream;
+  window_count_kernel<<<(unsigned)nb, WB, 0, s>>>(emit_new, total, scratch + 2);
+  window_scan_kernel<<<1, 1024, 0, s>>>(scratch + 2, nb, scratch, ptr_size, count_out, max_size);
+  window_index_scatter_kernel<<<(unsigned)nb, WB, 0, s>>>(emit_new, total, base_pos, win_pos, max_size, scratch + 2, scratch);
+  return check_launch("window_index_store");
+}
+
+extern "C" int msacl_window_gather_indexed(const msacl_transitions_t* tr, int64_t n, const int64_t* win_pos,
+                                           const int64_t* idx, int64_t B, const msacl_ring_t* batch, void* stream) {
+  if (int rc = validate_ring(batch)) return rc;
+  if (!tr || !tr->obs || !tr->act || !tr->rew || !tr->cost || !tr->obs2 || !tr->done || !tr->logp || !win_pos || !idx ||
+      B <= 0 || n <= 0) {
+    set_error("window_gather_indexed: bad argument");
+    return MSACL_ERR_BAD_ARG;
+  }
+  const int wpb = 8;
+  const int64_t want = (B + wpb - 1) / wpb, cap = (int64_t)kNumSMs * 8;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  const int D = batch->obs_dim;
+  auto misaligned = [&](const void* p, int w) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(4 * w - 1)) != 0; };
+  int W = (D % 4 == 0) ? 4 : ((D % 2 == 0) ? 2 : 1);
+  while (W > 1 && (misaligned(tr->obs, W) || misaligned(tr->obs2, W) || misaligned(batch->obs, W) || misaligned(batch->obs2, W))) W >>= 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (W == 4) window_gather_indexed_kernel<4><<<grid, wpb * 32, 0, st>>>(*tr, n, win_pos, idx, B, *batch);
+  else if (W == 2) window_gather_indexed_kernel<2><<<grid, wpb * 32, 0, st>>>(*tr, n, win_pos, idx, B, *batch);
+  else window_gather_indexed_kernel<1><<<grid, wpb * 32, 0, st>>>(*tr, n, win_pos, idx, B, *batch);
+  return check_launch("window_gather_indexed");
 }
 
 extern "C" int msacl_ring_gather(const msacl_ring_t* ring, const int64_t* idx, int64_t B, const msacl_ring_t* batch,

@@ -140,6 +140,15 @@ class TransitionBuffers:
             d.logits = self.logits.data_ptr()
         return d
 
+    def full_desc(self):
+        """Base pointers of the whole [H + M*K, n, .] store (index-based replay: positions are absolute)."""
+        return _lib.Transitions(**{k: v.data_ptr() for k, v in self._full.items()})
+
+    @property
+    def chunk_base_slice(self):
+        """Slice index, in the whole store, of the first NEW slice of the current chunk."""
+        return self._j * self.K + self.H
+
     def roll_history(self):
         """Advance to the next chunk (called once before every launch)."""
         self.launches += 1
@@ -266,9 +275,14 @@ class B200NstepOffSampler:
         self.networks = kwargs.get("networks")
         self.total_sample_number = 0
         # actor engine: "tc" = tcgen05 split-bf16 tensor cores (default), "ffma" = FP32 FFMA (bit-closer to torch fp32)
+        chunks = kwargs.get("history_chunks")
+        if chunks is None and kwargs.get("buffer_name") == "b200_indexed_replay_buffer":
+            # the transition store IS the replay payload: retain enough chunks for buffer_max_size windows
+            from .buffer import B200IndexedReplayBuffer
+            chunks = B200IndexedReplayBuffer.chunks_for(int(kwargs["buffer_max_size"]), self.num_envs, self.horizon)
         self.rollout = FusedRollout(self.env_id, self.num_envs, self.horizon, self.n_step, self.reward_scale, self.cost_scale,
                                     device=self.device, state=self.envs.state, engine=kwargs.get("rollout_engine", "tc"),
-                                    history_chunks=kwargs.get("history_chunks"))
+                                    history_chunks=chunks)
         self.envs.state.reset()        # base.py:98  envs.reset(seed=None)
         self._actor = None
         self._actor_cache = None

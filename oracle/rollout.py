@@ -93,6 +93,16 @@ def sampler_step(venv: VectorEnv, weights, eps, reward_scale=100.0, cost_scale=1
                 mean=mean, std=std, stats=stats)
 
 
+def env_outputs_for_action(name, state, act_clip, reward_scale=100.0, cost_scale=100.0):
+    """The env half of base.py:148-163 for a GIVEN clipped action (no actor): (scaled reward, scaled cost, real_next_obs,
+    term, trunc) from `state`, which is not modified.  Parity tests feed it the kernel's own action so that the
+    reward / cost comparison is free of the actor's summation-order difference."""
+    _, obs, reward, term, trunc = envs.env_step(name, clone_state(state), np.asarray(act_clip, f32))
+    rew = (reward.astype(f32) * f32(reward_scale)).astype(f32)
+    cost = (envs.np_pairwise_rowsum(obs.astype(f32) ** 2) * f32(cost_scale)).astype(f32)
+    return rew, cost, obs.astype(f32), term, trunc
+
+
 class WindowEmitter:
     """base.py:95,178-217: per-env deque(maxlen=n); after appending the newest transition a
     window [n, .] is emitted iff the deque is full; the deque is cleared when the newest

@@ -18,6 +18,12 @@ from oracle import rollout as oroll
 
 pytestmark = pytest.mark.gpu
 
+# scaled (x100) reward / cost vs the oracle env stepped with the kernel's own action: (rtol, atol).  Box envs: the env
+# kernels' 2e-6 (abs + rel) per-step tolerance doubles in the quadratic forms -> 1e-5 relative, 1e-5 of the scale.
+# QuadTracking: obs tolerance 2e-5 abs (Newton polar vs LAPACK SVD, float64 desired-frame pipeline) on |obs| ~ 1
+# -> 1e-4 relative, 2e-4 of the scale.
+REW_TOL = {False: (1e-5, 1e-3), True: (1e-4, 2e-2)}
+
 
 def _mk(name, n, K, n_step=5, seed=3, max_step=None, weights=None):
     from msacl_b200.sampler import ActorWeights, FusedRollout
@@ -67,6 +73,7 @@ def test_fused_step_vs_oracle_teacher_forced(name):
         _sync_state(ro, name, venv.state)     # device reset == oracle reset only to float32 round-off (Quad trig)
         for t in range(T):
             eps = rng.standard_normal((n, spec.act_dim)).astype(np.float32)
+            before = oroll.clone_state(venv.state)
             tr = oroll.sampler_step(venv, w, eps)
             emit, _ = emitter.push(tr)
             ro.run(aw, eps=torch.as_tensor(eps[None]).cuda())
@@ -76,8 +83,13 @@ def test_fused_step_vs_oracle_teacher_forced(name):
             _assert_logp(g["logp"], tr["logp"], tr["act"], spec)
             tol = 2e-3 if name == "QuadTracking" else 5e-4
             np.testing.assert_allclose(g["obs2"], tr["obs2"], rtol=1e-4, atol=tol)
-            np.testing.assert_allclose(g["rew"], tr["rew"], rtol=2e-3, atol=0.5)
-            np.testing.assert_allclose(g["cost"], tr["cost"], rtol=2e-3, atol=0.5)
+            # reward / cost: the oracle env is given the KERNEL's clipped action, which removes the actor difference --
+            # 1e-5 relative (+1e-5 of the x100 scale), tight enough to expose a wrong bonus branch (a shift of >= 100)
+            rew_k, cost_k, obs2_k, _, _ = oroll.env_outputs_for_action(name, before, g["act"])
+            rt, at = REW_TOL[name == "QuadTracking"]
+            np.testing.assert_allclose(g["obs2"], obs2_k, rtol=1e-5, atol=2e-5)
+            np.testing.assert_allclose(g["rew"], rew_k, rtol=rt, atol=at)
+            np.testing.assert_allclose(g["cost"], cost_k, rtol=rt, atol=at)
             near = (np.abs(tr["obs2"] - spec.obs_low) < 5e-3).any(1) | (np.abs(tr["obs2"] - spec.obs_high) < 5e-3).any(1)
             assert np.array_equal(g["done"].astype(bool)[~near], tr["done"][~near])
             assert np.array_equal(g["emit"].astype(bool), emit)
@@ -163,6 +175,12 @@ def test_golden_sampler_actions_and_logp_from_reference():
             tol = 2e-3 if name == "QuadTracking" else 5e-4
             np.testing.assert_allclose(out["obs2"], g["step_obs2"][t], rtol=1e-4, atol=tol)
             assert np.array_equal(out["done"].astype(bool), g["step_done"][t] > 0)
+            # the kernel's action differs from the reference's by <= 2e-5 * range; with it factored out (oracle env, itself
+            # bit-exact vs the reference, stepped with the kernel's action) reward and cost agree to 1e-5
+            rew_k, cost_k, _, _, _ = oroll.env_outputs_for_action(name, prev, out["act"])
+            rt, at = REW_TOL[name == "QuadTracking"]
+            np.testing.assert_allclose(out["rew"], rew_k, rtol=rt, atol=at)
+            np.testing.assert_allclose(out["cost"], cost_k, rtol=rt, atol=at)
             np.testing.assert_allclose(out["rew"][v], g["step_rew"][t][v], rtol=2e-3, atol=0.5)
             np.testing.assert_allclose(out["cost"][v], g["step_cost"][t][v], rtol=2e-3, atol=0.5)
             prev = {k: post[k][t] for k in post}

@@ -129,3 +129,63 @@ def test_chunked_transition_store_equals_rolled_store():
     assert bufs[0].size > 0
     for k in FIELDS:
         assert torch.equal(bufs[0].n_step_buf[k], bufs[1].n_step_buf[k]), k
+
+
+@pytest.mark.parametrize("name,ring_size,chunks", [("Pendulum", 100000, 8), ("QuadTracking", 100000, 8), ("TwoLink", 1500, 5)])
+def test_indexed_replay_equals_reference_layout_ring(name, ring_size, chunks):
+    """Index-based store (window = position of its newest transition in the sampler's transition store) vs the
+    reference-layout ring fed by the same launches: ptr / size / per-call counts identical, and every resident slot
+    gathers bit-identical [n_step, .] payloads -- across chunk wraps of the store (history carry-over) and, for the small
+    ring, across wraps of the position ring.  The reference-layout ring is itself bit-exact vs the oracle / the reference's
+    recorded ring (tests above)."""
+    from msacl_b200.buffer import B200IndexedReplayBuffer, B200NstepReplayBuffer
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    n, K, n_step = 300, 7, 5
+    spec = oenv.SPECS[name]
+    ro = FusedRollout(name, n, K, n_step=n_step, seed=8, max_step=11, engine="tc", history_chunks=chunks)
+    ro.state.reset()
+    aw = ActorWeights(oactor.init_policy_weights(spec.obs_dim, spec.act_dim, seed=2))
+    kw = dict(obs_dim=spec.obs_dim, act_dim=spec.act_dim, buffer_max_size=ring_size, n_step=n_step)
+    ref, ixb = B200NstepReplayBuffer(**kw), B200IndexedReplayBuffer(**kw)
+    rng = np.random.default_rng(0)
+    per_launch = []
+    for launch in range(3 * chunks + 2):
+        batch = ro.run(aw)
+        c1 = int(ref.add_batch(batch).item())
+        c2 = int(ixb.add_batch(batch).item())
+        per_launch.append(c2)
+        assert c1 == c2 and (ref.ptr, ref.size) == (ixb.ptr, ixb.size)
+        resident = min(ixb.size, sum(per_launch[-(chunks - 2):]))
+        assert int(ixb.valid_count().item()) == resident
+        # the `resident` most recent slots, walking back from ptr - 1
+        back = rng.integers(0, resident, size=257)
+        slots = (ixb.ptr - 1 - back) % ring_size
+        a, b = ref.gather(slots), ixb.gather(slots)
+        for k in FIELDS:
+            assert torch.equal(a[k], b[k]), (launch, k)
+    assert ref.size > 0 and launch >= 2 * chunks
+    s = ixb.sample_batch(64)
+    assert set(s) == set(FIELDS) and s["obs"].shape == (64, n_step, spec.obs_dim) and s["done"].dtype == torch.float32
+    with pytest.raises(NotImplementedError):
+        ixb.store(None)
+
+
+def test_indexed_replay_through_registries():
+    """create_sampler / create_buffer with buffer_name='b200_indexed_replay_buffer': the sampler sizes its transition
+    store from buffer_max_size, the buffer binds to it on the first add_batch."""
+    import msacl_b200
+    from msacl_b200.buffer import B200IndexedReplayBuffer
+    kw = dict(env_name="DuctedFan", env_num=64, sample_batch_size=8, reward_scale=100.0, cost_scale=100.0, noise_params=None,
+              n_step=4, obs_dim=6, act_dim=2, buffer_max_size=2000, buffer_name="b200_indexed_replay_buffer", env_seed=1)
+    sampler = msacl_b200.create_sampler(**kw)
+    buf = msacl_b200.create_buffer(**kw)
+    assert isinstance(buf, B200IndexedReplayBuffer)
+    assert sampler.rollout.tr.M == B200IndexedReplayBuffer.chunks_for(2000, 64, 8) == 6
+    sampler.set_actor(__import__("msacl_b200.sampler", fromlist=["ActorWeights"]).ActorWeights(
+        oactor.init_policy_weights(6, 2, seed=0)))
+    for _ in range(9):
+        data, _ = sampler.sample()
+        buf.add_batch(data)
+    assert 0 < buf.size <= 2000 and len(buf) == buf.size and buf.__get_RAM__() > 0
+    out = buf.sample_batch(32)
+    assert out["obs"].shape == (32, 4, 6) and torch.isfinite(out["rew"]).all()
