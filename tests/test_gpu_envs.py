@@ -213,8 +213,8 @@ def test_bare_env_continues_from_terminal_state():
     from msacl_b200.envs import B200Env
     env = B200Env("VanderPol")
     env.reset(seed=3)
-    env._v.state.set_box_state(np.array([[9.9, 9.0]], np.float32))
-    st = {"obs": np.array([[9.9, 9.0]], np.float32), "step": np.zeros(1, np.int32)}
+    env._v.state.set_box_state(np.array([[9.99, 9.9]], np.float32))
+    st = {"obs": np.array([[9.99, 9.9]], np.float32), "step": np.zeros(1, np.int32)}
     seen_term = False
     for k in range(4):
         a = np.array([5.0], np.float32)
