@@ -92,21 +92,23 @@ class B200NstepReplayBuffer:
         return self._count
 
     # ---- reads
-    def gather(self, idx):
+    def gather(self, idx, out=None):
+        """out: optional preallocated {field: [B, n_step, .]} float32 CUDA tensors (e.g. views of a packed exchange buffer)."""
         idx = torch.as_tensor(idx, dtype=torch.int64, device=self.device).contiguous()
         B = idx.numel()
-        out = {k: torch.empty(B, *v.shape[1:], dtype=torch.float32, device=self.device) for k, v in self.n_step_buf.items()}
+        if out is None:
+            out = {k: torch.empty(B, *v.shape[1:], dtype=torch.float32, device=self.device) for k, v in self.n_step_buf.items()}
         dst = self._make_ring(out, B)
         _lib.check(_lib.load().msacl_ring_gather(C.byref(self._ring), idx.data_ptr(), B, C.byref(dst), _lib.current_stream()))
         return out
 
-    def sample_batch(self, batch_size: int) -> dict:
+    def sample_batch(self, batch_size: int, out=None) -> dict:
         """Uniform sampling with replacement over the valid range (nstep_replay_buffer.py:138)."""
         # idx ~ U{0..size-1} drawn on the device from the device-resident size (no host synchronisation)
         u = torch.rand(int(batch_size), device=self.device, generator=self._gen, dtype=torch.float64)
         size = self._ptr_size[1]
         idx = torch.minimum((u * size).to(torch.int64), torch.clamp(size - 1, min=0))
-        return self.gather(idx)
+        return self.gather(idx, out=out)
 
 
 class B200IndexedReplayBuffer:
@@ -205,20 +207,21 @@ class B200IndexedReplayBuffer:
         """Device scalar: number of most-recent ring entries whose slices are still resident."""
         return torch.minimum(self._ptr_size[1], self._launch_counts.sum())
 
-    def gather(self, idx):
+    def gather(self, idx, out=None):
         """idx: ring slots (as the reference's fancy indexing of n_step_buf)."""
         idx = torch.as_tensor(idx, dtype=torch.int64, device=self.device).contiguous()
         B = idx.numel()
         n, D, A = self.n_step, self.obsv_dim, self.act_dim
         z = lambda *s: torch.empty(B, n, *s, dtype=torch.float32, device=self.device)
-        out = {"obs": z(D), "act": z(A), "rew": z(), "cost": z(), "obs2": z(D), "done": z(), "logp": z()}
+        if out is None:
+            out = {"obs": z(D), "act": z(A), "rew": z(), "cost": z(), "obs2": z(D), "done": z(), "logp": z()}
         dst = _lib.Ring(max_size=B, n_step=n, obs_dim=D, act_dim=A, **{k: out[k].data_ptr() for k in FIELDS})
         desc = self._tr.full_desc()
         _lib.check(_lib.load().msacl_window_gather_indexed(C.byref(desc), self._tr.n, self.win_pos.data_ptr(), idx.data_ptr(), B,
                                                           C.byref(dst), _lib.current_stream()))
         return out
 
-    def sample_batch(self, batch_size: int) -> dict:
+    def sample_batch(self, batch_size: int, out=None) -> dict:
         """Uniform with replacement over the resident windows (nstep_replay_buffer.py:138), drawn on the device."""
         if self._tr is None:
             raise RuntimeError("sample_batch before any add_batch")
@@ -226,4 +229,4 @@ class B200IndexedReplayBuffer:
         valid = self.valid_count()
         back = torch.minimum((u * valid).to(torch.int64), torch.clamp(valid - 1, min=0))      # 0 = newest entry
         slot = torch.remainder(self._ptr_size[0] - 1 - back, self.max_size)
-        return self.gather(slot)
+        return self.gather(slot, out=out)

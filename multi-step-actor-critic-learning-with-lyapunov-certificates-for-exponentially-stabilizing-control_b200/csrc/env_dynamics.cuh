@@ -308,49 +308,71 @@ template <> struct Env<kSingleTrackCar> {
 // orthogonal polar factor of M (det -1) and v3 the right-singular vector of the smallest singular value = the eigenvector
 // of the smallest eigenvalue of P = Q^T M (symmetric positive definite).  v3 is the dominant eigenvector of adj(P)
 // (= det(P) P^-1), found by repeated squaring.  Unreachable from the dynamics (the input there is a rotation times
-// I + h hat(w), det ~ +1), so it lives out of line, in float64, and costs the hot path one predicate.
-static __device__ __noinline__ void quad_polar_reflected(float* Rm) {
-  double M[9], Q[9];
+// I + h hat(w), det ~ +1).  Written as rolled loops over local-memory arrays (dynamic indexing, float64): an out-of-line
+// call here cost the hot path 8.5 % (the rotation matrix was forced into local memory around the call), a rolled inline
+// block costs a predicate.
+__device__ __forceinline__ void quad_polar_reflected(float (&R)[9]) {
+  double M[9], Q[9], C[9], S[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) { M[i] = (double)Rm[i]; Q[i] = M[i]; }
-  auto cofactors = [](const double* X, double* C) {
-    C[0] = X[4] * X[8] - X[5] * X[7]; C[1] = X[5] * X[6] - X[3] * X[8]; C[2] = X[3] * X[7] - X[4] * X[6];
-    C[3] = X[2] * X[7] - X[1] * X[8]; C[4] = X[0] * X[8] - X[2] * X[6]; C[5] = X[1] * X[6] - X[0] * X[7];
-    C[6] = X[1] * X[5] - X[2] * X[4]; C[7] = X[2] * X[3] - X[0] * X[5]; C[8] = X[0] * X[4] - X[1] * X[3];
+  for (int i = 0; i < 9; ++i) { M[i] = (double)R[i]; Q[i] = M[i]; }
+  // signed cofactors by the cyclic rule: C_ij = X_(i+1)(j+1) X_(i+2)(j+2) - X_(i+1)(j+2) X_(i+2)(j+1), indices mod 3
+  auto cofactors = [](const double* X, double* Cf) {
+#pragma unroll 1
+    for (int e = 0; e < 9; ++e) {
+      const int i = e / 3, j = e - 3 * i;
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      Cf[e] = X[3 * i1 + j1] * X[3 * i2 + j2] - X[3 * i1 + j2] * X[3 * i2 + j1];
+    }
   };
+#pragma unroll 1
   for (int it = 0; it < 40; ++it) {            // Newton: Q <- (Q + Q^-T)/2, converges to the orthogonal factor (det -1)
-    double C[9];
     cofactors(Q, C);
     const double det = Q[0] * C[0] + Q[1] * C[1] + Q[2] * C[2];
     double delta = 0.0;
-    for (int i = 0; i < 9; ++i) { const double q = 0.5 * (Q[i] + C[i] / det); delta += fabs(q - Q[i]); Q[i] = q; }
+#pragma unroll 1
+    for (int e = 0; e < 9; ++e) { const double q = 0.5 * (Q[e] + C[e] / det); delta += fabs(q - Q[e]); Q[e] = q; }
     if (delta < 1e-15) break;
   }
-  double P[9], B[9];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) P[3 * i + j] = Q[i] * M[j] + Q[3 + i] * M[3 + j] + Q[6 + i] * M[6 + j];      // Q^T M
-  for (int i = 0; i < 3; ++i)
-    for (int j = i + 1; j < 3; ++j) { const double a = 0.5 * (P[3 * i + j] + P[3 * j + i]); P[3 * i + j] = a; P[3 * j + i] = a; }
-  cofactors(P, B);                              // symmetric P: adj(P) = cofactor matrix
-  for (int it = 0; it < 12; ++it) {             // B <- B^2 / trace: rank-1 projector on the smallest eigenvector of P
-    double S[9];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) S[3 * i + j] = B[3 * i] * B[j] + B[3 * i + 1] * B[3 + j] + B[3 * i + 2] * B[6 + j];
+#pragma unroll 1
+  for (int e = 0; e < 9; ++e) {                 // S = Q^T M
+    const int i = e / 3, j = e - 3 * i;
+    S[e] = Q[i] * M[j] + Q[3 + i] * M[3 + j] + Q[6 + i] * M[6 + j];
+  }
+#pragma unroll 1
+  for (int e = 0; e < 9; ++e) {                 // P = sym(S), kept in M
+    const int i = e / 3, j = e - 3 * i;
+    M[e] = 0.5 * (S[e] + S[3 * j + i]);
+  }
+  cofactors(M, C);                              // symmetric P: adj(P) = cofactor matrix
+#pragma unroll 1
+  for (int it = 0; it < 12; ++it) {             // C <- C^2 / trace: rank-1 projector on the smallest eigenvector of P
+#pragma unroll 1
+    for (int e = 0; e < 9; ++e) {
+      const int i = e / 3, j = e - 3 * i;
+      S[e] = C[3 * i] * C[j] + C[3 * i + 1] * C[3 + j] + C[3 * i + 2] * C[6 + j];
+    }
     const double tr = S[0] + S[4] + S[8];
-    for (int i = 0; i < 9; ++i) B[i] = S[i] / tr;
+#pragma unroll 1
+    for (int e = 0; e < 9; ++e) C[e] = S[e] / tr;
   }
   int best = 0;
   double bn = -1.0;
+#pragma unroll 1
   for (int j = 0; j < 3; ++j) {
-    const double nn = B[j] * B[j] + B[3 + j] * B[3 + j] + B[6 + j] * B[6 + j];
+    const double nn = C[j] * C[j] + C[3 + j] * C[3 + j] + C[6 + j] * C[6 + j];
     if (nn > bn) { bn = nn; best = j; }
   }
   const double inv = rsqrt(bn);
-  const double v[3] = {B[best] * inv, B[3 + best] * inv, B[6 + best] * inv};
+#pragma unroll 1
+  for (int i = 0; i < 3; ++i) S[i] = C[3 * i + best] * inv;          // v3
+#pragma unroll 1
   for (int i = 0; i < 3; ++i) {                 // R' = Q - 2 (Q v) v^T
-    const double qv = Q[3 * i] * v[0] + Q[3 * i + 1] * v[1] + Q[3 * i + 2] * v[2];
-    for (int j = 0; j < 3; ++j) Rm[3 * i + j] = (float)(Q[3 * i + j] - 2.0 * qv * v[j]);
+    const double qv = Q[3 * i] * S[0] + Q[3 * i + 1] * S[1] + Q[3 * i + 2] * S[2];
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) M[3 * i + j] = Q[3 * i + j] - 2.0 * qv * S[j];
   }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = (float)M[i];
 }
 
 __device__ __forceinline__ void quad_polar_f32(float (&R)[9], float theta2) {
@@ -369,7 +391,9 @@ __device__ __forceinline__ void quad_polar_f32(float (&R)[9], float theta2) {
     const float c10 = cof(R[2], R[7], R[1], R[8]), c11 = cof(R[0], R[8], R[2], R[6]), c12 = cof(R[1], R[6], R[0], R[7]);
     const float c20 = cof(R[1], R[5], R[2], R[4]), c21 = cof(R[2], R[3], R[0], R[5]), c22 = cof(R[0], R[4], R[1], R[3]);
     const float det = __fmaf_rn(R[2], c02, __fmaf_rn(R[1], c01, R[0] * c00));
+#ifndef MSACL_QUAD_NO_REFLECT
     if (first && det < 0.0f) return false;
+#endif
     const float hid = 0.5f / det;                 // (an approximate reciprocal here measured 1.5 % slower end to end)
     R[0] = __fmaf_rn(c00, hid, 0.5f * R[0]); R[1] = __fmaf_rn(c01, hid, 0.5f * R[1]); R[2] = __fmaf_rn(c02, hid, 0.5f * R[2]);
     R[3] = __fmaf_rn(c10, hid, 0.5f * R[3]); R[4] = __fmaf_rn(c11, hid, 0.5f * R[4]); R[5] = __fmaf_rn(c12, hid, 0.5f * R[5]);

@@ -64,6 +64,84 @@ def exchange_batch_and_stats(sub_batch, stats):
     return out, stats_all.sum(dim=0)
 
 
+class BatchExchange:
+    """Per-chunk exchange of the replay sub-batches and the episode statistics, overlapped with the next rollout.
+
+    One preallocated packed float32 buffer per rank holds the 7 batch fields ([B/G, n, .] each; `views()` hands them out
+    so that the buffer's gather kernel writes the sampled windows straight into it -- no torch.cat) followed by the [8]
+    float64 statistics bit-cast to 16 floats.  `exchange()` issues ONE all-gather of that buffer on a side stream and
+    returns the PREVIOUS call's gathered result: the learner's batch is one iteration stale (as it already is in the
+    reference loop, where the batch is drawn before the current chunk's windows matter), so the collective's latency hides
+    behind the next rollout launch instead of blocking it.  Buffers are double-buffered; the first call returns its own
+    result.  On CPU tensors (gloo tests) the same protocol runs synchronously."""
+
+    def __init__(self, fields, sub_batch, n_step, device, group=None):
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.group, self.device = group, torch.device(device)
+        self.keys = sorted(fields)
+        self.shapes = {k: (int(sub_batch), int(n_step)) + tuple(fields[k]) for k in self.keys}
+        self.offsets, off = {}, 0
+        for k in self.keys:
+            numel = 1
+            for d in self.shapes[k]:
+                numel *= d
+            self.offsets[k] = (off, numel)
+            off += (numel + 3) // 4 * 4                 # keep every field 16-byte aligned
+        self.stats_off, self.P = off, off + 16
+        self.send = [torch.zeros(self.P, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.recv = [torch.zeros(self.world, self.P, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self.done = [None, None]
+        self.t = 0
+
+    def views(self):
+        """{field: [B/G, n, .]} views of the CURRENT send buffer: pass as `out=` to buffer.sample_batch."""
+        buf = self.send[self.t & 1]
+        return {k: buf[o:o + m].view(self.shapes[k]) for k, (o, m) in self.offsets.items()}
+
+    def _unpack(self, recv):
+        out = {}
+        for k, (o, m) in self.offsets.items():
+            shp = self.shapes[k]
+            out[k] = recv[:, o:o + m].reshape((self.world * shp[0],) + shp[1:])
+        stats = recv[:, self.stats_off:self.stats_off + 16].contiguous().view(torch.float64).sum(dim=0)    # rank order
+        return out, stats
+
+    def exchange(self, sub_batch, stats, unpack=True):
+        """sub_batch: `views()` already filled by the gather kernel, or any {field: tensor} (copied in).  Returns the
+        previous call's (global batch {field: [B, n, .]}, rank-summed statistics [8] float64) -- with unpack=False the raw
+        gathered [G, P] buffer instead (one contiguous D2H copy; unpack on the host with `host_views`)."""
+        cur = self.t & 1
+        mine = self.views()
+        for k in self.keys:
+            if sub_batch[k].data_ptr() != mine[k].data_ptr():
+                mine[k].copy_(sub_batch[k])
+        self.send[cur][self.stats_off:].view(torch.float64).copy_(stats.detach().to(torch.float64))
+        if self.world == 1:
+            self.recv[cur].copy_(self.send[cur][None])
+        elif self.side is None:
+            dist.all_gather_into_tensor(self.recv[cur].view(-1), self.send[cur], group=self.group)
+        else:
+            ready = torch.cuda.Event()
+            ready.record()
+            self.side.wait_event(ready)
+            with torch.cuda.stream(self.side):
+                dist.all_gather_into_tensor(self.recv[cur].view(-1), self.send[cur], group=self.group)
+                ev = torch.cuda.Event()
+                ev.record()
+            self.done[cur] = ev
+        take = cur if self.t == 0 else 1 - cur
+        if self.side is not None and self.done[take] is not None:
+            torch.cuda.current_stream().wait_event(self.done[take])
+        self.t += 1
+        return self._unpack(self.recv[take]) if unpack else self.recv[take]
+
+    def host_views(self, host_packed):
+        """Unpack a host copy [G, P] of a gathered buffer: ({field: [B, n, .]}, statistics [8] float64); the batch fields are
+        strided views when G > 1 (rank-major rows), plain views when G == 1."""
+        return self._unpack(host_packed)
+
+
 def broadcast_parameters(module_or_tensors, src=0):
     """Learner -> rollout ranks: broadcast a module's parameters (e.g. `networks.policy`, 285 KB) from rank `src`
     in ONE collective (flattened bucket) and copy them back in place, so that every rank samples with the same actor."""

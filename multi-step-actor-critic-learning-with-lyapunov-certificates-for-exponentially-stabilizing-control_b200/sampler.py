@@ -215,9 +215,11 @@ class FusedRollout:
         self.stats = torch.zeros(32, dtype=torch.float64, device=self.state.device)   # [0:8) documented, rest diagnostic
         self.global_step = 0
 
-    def run(self, actor: ActorWeights, eps=None, deterministic=False, write=True, engine=None):
+    def run(self, actor: ActorWeights, eps=None, deterministic=False, write=True, engine=None, timing=None):
         """One K-step chunk.  eps: optional CUDA float32 [K, n, act_dim] explicit N(0,1) draws.
-        engine: "ffma" (FP32 FFMA actor) or "tc" (tcgen05 split-bf16 actor); default self.engine."""
+        engine: "ffma" (FP32 FFMA actor) or "tc" (tcgen05 split-bf16 actor); default self.engine.
+        timing: optional (start, end) torch.cuda.Event pair recorded on the current stream directly around the kernel
+        launch (excludes the history carry-over copy of the transition store)."""
         if actor.obs_dim != self.spec.obs_dim or actor.act_dim != self.spec.act_dim:
             raise ValueError("actor dimensions do not match the environment")
         tr = self.tr
@@ -237,12 +239,17 @@ class FusedRollout:
                   _lib.current_stream())
         if engine == "tc":
             w1p, w2p = actor.tc_images()
+        if timing is not None:
+            timing[0].record()
+        if engine == "tc":
             _lib.check(_lib.load().msacl_rollout_fused_tc(C.byref(self.state.desc), C.byref(actor.desc), w1p.data_ptr(),
                                                          w2p.data_ptr(), *common))
         elif engine == "ffma":
             _lib.check(_lib.load().msacl_rollout_fused(C.byref(self.state.desc), C.byref(actor.desc), *common))
         else:
             raise ValueError(f"unknown rollout engine {engine!r}")
+        if timing is not None:
+            timing[1].record()
         self.global_step += self.K
         if not write:
             self.state.run.zero_()

@@ -47,6 +47,21 @@ def _worker(rank, world, port, q):
     (m, sd), (m2, sd2) = mdist.mean_std_over_ranks(allv[lo:hi], -2.0 * allv[lo:hi])
     assert abs(m - float(allv.mean())) < 1e-12 and abs(sd - float(allv.std(unbiased=False))) < 1e-12
     assert abs(m2 + 2.0 * float(allv.mean())) < 1e-12 and abs(sd2 - 2.0 * float(allv.std(unbiased=False))) < 1e-12
+    # overlapped exchange protocol (packed buffer, results consumed one call later); synchronous on CPU / gloo
+    ex = mdist.BatchExchange({"obs": (2,), "rew": ()}, 3, 4, "cpu")
+    got_prev = []
+    for step in range(3):
+        views = ex.views()
+        views["obs"].fill_(float(10 * step + rank)); views["rew"].fill_(float(10 * step + rank) + 0.5)   # "gather kernel" output
+        batch, st = ex.exchange(views, stats * (step + 1))
+        got_prev.append((batch["obs"][:, 0, 0].tolist(), batch["rew"][:, 0].tolist(), st.tolist()))
+        host, st_h = ex.host_views(ex.recv[0 if step == 0 else 1 - ((step) & 1)].clone())
+        assert torch.equal(host["obs"], batch["obs"]) and torch.equal(st_h, st)
+    # call 0 returns its own result, call t > 0 the result of call t - 1 (one step stale)
+    for step, src in enumerate((0, 0, 1)):
+        assert got_prev[step][0] == [10.0 * src] * 3 + [10.0 * src + 1] * 3
+        assert got_prev[step][1] == [10.0 * src + 0.5] * 3 + [10.0 * src + 1.5] * 3
+        assert got_prev[step][2] == (red * (src + 1)).tolist()
     q.put((rank, red.tolist(), {k: v.tolist() for k, v in full.items()}, mdist.episode_summary(red)))
     dist.destroy_process_group()
 
