@@ -230,6 +230,89 @@ int msacl_advantage_normalize(int64_t B, const float* adv_raw, const double* mom
 int msacl_polyak_update(int32_t count, const float* const* src, float* const* dst, const int64_t* numel,
                         int64_t max_numel, float polyak, float one_minus, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Learner networks and update (RL/apprfunc/mlp.py:18-52,72-88,111-136; RL/algorithm/msacl.py:227-460;
+ * RL/utils/act_distribution_cls.py:59-84).  With these entry points a whole MSACL.model_update runs as a fixed
+ * sequence of launches without autograd: dense layers forward / backward on the tcgen05 tensor cores, every scalar
+ * (alpha, losses, entropy) resident on the device.
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* One dense layer, forward or backward, as a split-bf16 ("bf16x3") tcgen05 GEMM with a fused epilogue:
+ *     C[r][n] = epilogue( sum_k A(r,k) * B(n,k) ),   A(r,k) = a[r*a_row_stride + k*a_k_stride],  B likewise (FP32, device)
+ *   forward  (mlp.py:18-33)  H = act(X W^T + b):       a = X [rows][in], b = W [out][in] (nn.Linear layout), bias, act
+ *   dgrad                    dX = (dY W) * act'(Xpost): a = dY, B(n,k) = W[k][n] (b_row_stride 1, b_k_stride in), mask_src = Xpost
+ *   wgrad                    dW = dY^T X:              A(r,k) = dY[k][r], B(n,k) = X[k][n], k = rows, split_k partials
+ * act / mask_act: 0 none, 1 relu, 2 tanh.  mask_src holds POST-activation values (relu' = [h > 0], tanh' = 1 - h^2).
+ * split_k > 1: split z writes its partial product to c + z * c_split_stride (no epilogue allowed); the consumer
+ * (msacl_adam_multi / msacl_reduce_splits) adds the partials in a fixed order.
+ * row_sumsq: optional [m], receives sum_n C[r][n]^2 (LyapunovValue.forward, mlp.py:86-88); needs n <= 256. */
+typedef struct {
+  const float* a; int64_t a_row_stride, a_k_stride;
+  const float* b; int64_t b_row_stride, b_k_stride;
+  int32_t m, n, k;
+  float* c; int64_t ldc;
+  int32_t split_k; int64_t c_split_stride;
+  const float* bias;
+  int32_t act;
+  const float* mask_src; int64_t mask_ld; int32_t mask_act;
+  float* row_sumsq;
+} msacl_gemm_t;
+int msacl_gemm_tc(const msacl_gemm_t* g, void* stream);
+
+/* out[z][c] = sum over the rows of split z (rows divided evenly over `splits`) of x[r*ld + c]; cols <= 256.  Bias gradients. */
+int msacl_colsum(const float* x, int64_t rows, int32_t cols, int64_t ld, int32_t splits, float* out, void* stream);
+/* out[r] = [a[r] | b[r]]  (ActionValue input, mlp.py:50-52) */
+int msacl_concat2(const float* a, int32_t da, const float* b, int32_t db, int64_t rows, float* out, void* stream);
+/* out[i] = sum_z parts[z*numel + i], z ascending */
+int msacl_reduce_splits(const float* parts, int64_t numel, int32_t nsplit, float* out, void* stream);
+
+/* TanhGaussDistribution on logits = [mean || log_std] rows [rows][2*act_dim] (StochaPolicy output BEFORE clamp / exp,
+ * mlp.py:132-136); act_low / act_high: device float[act_dim].
+ *   rsample  (act_distribution_cls.py:59-71) with explicit N(0,1) draws eps [rows][act_dim] -> act, logp
+ *   log_prob (act_distribution_cls.py:73-84) of given (limited) actions -> logp
+ *   log_prob_bwd: grad_logits[r] (+)= grad_logp[r] * d logp / d logits  (the clamp of log_std passes gradients inside its range) */
+int msacl_tanh_gauss_rsample(int64_t rows, int32_t act_dim, const float* logits, const float* eps, const float* act_low,
+                             const float* act_high, float min_log_std, float max_log_std, float* act, float* logp, void* stream);
+int msacl_tanh_gauss_log_prob(int64_t rows, int32_t act_dim, const float* logits, const float* act, const float* act_low,
+                              const float* act_high, float min_log_std, float max_log_std, float* logp, void* stream);
+int msacl_tanh_gauss_log_prob_bwd(int64_t rows, int32_t act_dim, const float* logits, const float* act, const float* act_low,
+                                  const float* act_high, float min_log_std, float max_log_std, const float* grad_logp,
+                                  int32_t accumulate, float* grad_logits, void* stream);
+
+/* msacl_q_backup with alpha = exp(*log_alpha) read on the device (no host synchronisation; msacl.py:249-252,339-346). */
+int msacl_q_backup_dev_alpha(int64_t count, const float* rew, const float* done, const float* next_q1, const float* next_q2,
+                             const float* next_logp, float gamma, const float* log_alpha, float* backup, void* stream);
+/* Critic loss (msacl.py:254-257): dq{1,2} = 2 (q - backup) / count; sums (device double[4], zeroed by the call) receive
+ * sum (q1-y)^2, sum (q2-y)^2, sum q1, sum q2. */
+int msacl_q_loss_grad(int64_t count, const float* q1, const float* q2, const float* backup, float* dq1, float* dq2, double* sums,
+                      void* stream);
+/* LyapunovValue backward through V = sum_j z_j^2: dz[r][j] = 2 z[r][j] dv[r] */
+int msacl_sumsq_bwd(int64_t rows, int32_t cols, const float* z, const float* dv, float* dz, void* stream);
+/* Policy update (msacl.py:349-411), loss_policy = -mean(min(Q1,Q2)(obs, a_new) - alpha logp_new) - L_lya.
+ *   policy_q_route: d loss / d q1, q2 (torch.min routing) and sums (device double[3], zeroed by the call):
+ *                   [0] sum (min_q - alpha logp_new), [1] sum logp_new
+ *   policy_logits_grad: d loss / d logits through (a) the critics' input gradients dxq{1,2} [rows][obs_dim+act_dim]
+ *                   (action columns) and the reparameterised tanh sample, (b) the entropy term, (c) the clipped
+ *                   stability-advantage surrogate on the first step of every window (adv: normalised advantage [rows/n_step]);
+ *                   sums[2] += sum_b min(surr1, surr2) */
+int msacl_policy_q_route(int64_t rows, const float* q1, const float* q2, const float* logp_new, const float* log_alpha, float* dq1,
+                         float* dq2, double* sums, void* stream);
+int msacl_policy_logits_grad(int64_t rows, int32_t n_step, int32_t obs_dim, int32_t act_dim, const float* logits, const float* eps,
+                             const float* dxq1, const float* dxq2, const float* log_alpha, const float* old_act,
+                             const float* old_logp, const float* adv, float clip_coef, const float* act_low, const float* act_high,
+                             float min_log_std, float max_log_std, float* grad_logits, double* sums, void* stream);
+/* Entropy coefficient (msacl.py:425-438): entropy = -sums[1] / rows; one Adam step on log_alpha with gradient
+ * exp(log_alpha) (entropy - target_entropy); adam_state = device float[2] {exp_avg, exp_avg_sq}; clamp_max = log(alpha_bound) or +inf. */
+int msacl_alpha_update(float* log_alpha, const double* sums, int64_t rows, float target_entropy, float* adam_state,
+                       float one_minus_beta1, float beta2, float one_minus_beta2, float step_size, float bc2_sqrt, float eps,
+                       float clamp_max, float* entropy_out, void* stream);
+/* torch.optim.Adam step (defaults: no weight decay, no amsgrad) over a whole parameter list in one launch.  params / grads /
+ * exp_avg / exp_avg_sq: DEVICE pointer tables of length count; grads[t] holds nsplit[t] partial gradients of numel[t]
+ * elements each, summed in order.  step_size = lr / (1 - beta1^step), bc2_sqrt = sqrt(1 - beta2^step) (host, float64 -> float32). */
+int msacl_adam_multi(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                     const int64_t* numel, const int32_t* nsplit, int64_t max_numel, float one_minus_beta1, float beta2,
+                     float one_minus_beta2, float step_size, float bc2_sqrt, float eps, void* stream);
+
 /* Device FP32 FFMA peak probes used by bench.py for the roofline denominator.
  * mode 0: independent FFMA chains with immediate operands (pipe peak);
  * mode 1: register-resident 8x8 outer-product accumulation, i.e. a register-tiled SGEMM inner

@@ -40,6 +40,18 @@ class Ring(C.Structure):
                 ("obs", vp), ("act", vp), ("rew", vp), ("cost", vp), ("obs2", vp), ("done", vp), ("logp", vp)]
 
 
+class Gemm(C.Structure):
+    _fields_ = [("a", vp), ("a_row_stride", C.c_int64), ("a_k_stride", C.c_int64),
+                ("b", vp), ("b_row_stride", C.c_int64), ("b_k_stride", C.c_int64),
+                ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+                ("c", vp), ("ldc", C.c_int64), ("split_k", C.c_int32), ("c_split_stride", C.c_int64),
+                ("bias", vp), ("act", C.c_int32), ("mask_src", vp), ("mask_ld", C.c_int64), ("mask_act", C.c_int32),
+                ("row_sumsq", vp)]
+
+
+f32 = C.c_float
+i32, i64 = C.c_int32, C.c_int64
+
 # name -> (restype, argtypes); must list every symbol of include/msacl_b200.h
 SIGNATURES = {
     "msacl_last_error": (C.c_char_p, []),
@@ -70,6 +82,20 @@ SIGNATURES = {
     "msacl_advantage_normalize": (C.c_int, [C.c_int64, vp, vp, vp, vp]),
     "msacl_selftest_tc_gemm": (C.c_int, [vp, vp, vp, C.c_int32, vp]),
     "msacl_polyak_update": (C.c_int, [C.c_int32, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp]),
+    "msacl_gemm_tc": (C.c_int, [C.POINTER(Gemm), vp]),
+    "msacl_colsum": (C.c_int, [vp, i64, i32, i64, i32, vp, vp]),
+    "msacl_concat2": (C.c_int, [vp, i32, vp, i32, i64, vp, vp]),
+    "msacl_reduce_splits": (C.c_int, [vp, i64, i32, vp, vp]),
+    "msacl_tanh_gauss_rsample": (C.c_int, [i64, i32, vp, vp, vp, vp, f32, f32, vp, vp, vp]),
+    "msacl_tanh_gauss_log_prob": (C.c_int, [i64, i32, vp, vp, vp, vp, f32, f32, vp, vp]),
+    "msacl_tanh_gauss_log_prob_bwd": (C.c_int, [i64, i32, vp, vp, vp, vp, f32, f32, vp, i32, vp, vp]),
+    "msacl_q_backup_dev_alpha": (C.c_int, [i64, vp, vp, vp, vp, vp, f32, vp, vp, vp]),
+    "msacl_q_loss_grad": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp]),
+    "msacl_sumsq_bwd": (C.c_int, [i64, i32, vp, vp, vp, vp]),
+    "msacl_policy_q_route": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "msacl_policy_logits_grad": (C.c_int, [i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, f32, f32, vp, vp, vp]),
+    "msacl_alpha_update": (C.c_int, [vp, vp, i64, f32, vp, f32, f32, f32, f32, f32, f32, f32, vp, vp]),
+    "msacl_adam_multi": (C.c_int, [i32, vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp]),
     "msacl_ffma_probe": (C.c_int, [C.c_int32, C.c_int32, vp, c_f64p, vp]),
     "msacl_umma_probe": (C.c_int, [C.c_int32, C.c_int32, vp, vp]),
 }

@@ -7,10 +7,14 @@ lyapunov, log_alpha, the five Adam optimisers, `create_action_distributions`), s
 (`q1.q.0.weight`, `policy.policy.0.weight`, `policy.act_high_lim`, `lyapunov.lya.0.weight`, ...), so
 reference checkpoints (`apprfunc_*.pkl`) load unchanged.
 
-Network forwards/backwards are plain PyTorch (`nn.Linear` -> cuBLAS); everything between the
-network outputs and the scalar losses runs in the kernels of csrc/targets.cu (soft-TD backup,
-Lyapunov risk with analytic backward, stability advantage).  V(obs) is evaluated once per Lyapunov
-update instead of twice (the reference's two forwards at :289 and :317 are identical).
+Two learner engines behind the same `model_update`:
+  * "fused" (default): learner.FusedLearner -- every dense layer forward / backward is the hand-written tcgen05
+    split-bf16 GEMM `msacl_gemm_tc`, the distribution / loss gradients are the kernels of csrc/learner.cu, Adam is one
+    multi-tensor launch per optimizer; no autograd, no cuBLAS, alpha / losses stay on the device.
+  * "torch": network forwards / backwards through PyTorch autograd (`nn.Linear` -> cuBLAS), kept as the A/B baseline;
+    everything between the network outputs and the scalar losses still runs in csrc/targets.cu.
+V(obs) is evaluated once per Lyapunov update instead of twice (the reference's two forwards at :289 and :317 are
+identical).
 """
 import math
 import time
@@ -125,8 +129,9 @@ class ApproxContainer(nn.Module):
 class B200MSACL:
     def __init__(self, gamma=0.99, retrace_lambda=0.95, lya_eta=0.15, tau=0.005, alpha=math.e, target_entropy=None,
                  policy_frequency=2, target_network_frequency=1, lya_diff_scale=1.0, lya_zero_scale=1.0,
-                 lya_positive_scale=1.0, device="cuda", **kwargs):
+                 lya_positive_scale=1.0, device="cuda", learner_engine="fused", **kwargs):
         self.device = torch.device(device)
+        self.engine_name = learner_engine
         self.networks = ApproxContainer(**kwargs).to(self.device)
         self.gamma, self.retrace_lambda, self.lya_eta, self.tau = gamma, retrace_lambda, lya_eta, tau
         self.policy_frequency, self.target_network_frequency = policy_frequency, target_network_frequency
@@ -141,6 +146,15 @@ class B200MSACL:
         self.alpha1, self.alpha2 = kwargs.get("alpha1", 1.0), kwargs.get("alpha2", 2.0)
         self.clip_coef = kwargs.get("clip_coef", 0.1)
         self.coef = tg.Coefficients(self.n_step, lya_eta, retrace_lambda, self.alpha1, self.alpha2, device=self.device)
+        self._fused = None
+        if learner_engine not in ("fused", "torch"):
+            raise ValueError(f"unknown learner_engine {learner_engine!r}")
+
+    def _fused_learner(self):
+        if self._fused is None:
+            from .learner import FusedLearner
+            self._fused = FusedLearner(self)
+        return self._fused
 
     def _get_alpha(self, requires_grad=False):
         a = self.networks.log_alpha.exp()
@@ -154,6 +168,8 @@ class B200MSACL:
         noise = iter(noise) if noise is not None else None
         nxt = (lambda: next(noise)) if noise is not None else (lambda: None)
         data = {k: v.to(self.device, non_blocking=True) for k, v in data.items()}
+        if self.engine_name == "fused":
+            return self._model_update_fused(data, global_iteration, nxt, start)
         loss_q, q1_mean, q2_mean = self._q_update(data, nxt())
         if global_iteration % self.target_network_frequency == 0:
             self._target_update()
@@ -166,6 +182,25 @@ class B200MSACL:
             return {"MSACL/entropy-RL iter": entropy.item(), "MSACL/alpha-RL iter": self._get_alpha(),
                     "MSACL/q1_mean-RL iter": q1_mean.item(), "MSACL/q2_mean-RL iter": q2_mean.item(),
                     TB["loss_critic"]: loss_q.item(), TB["loss_lyapunov"]: loss_lya.item(), TB["loss_actor"]: loss_policy.item(),
+                    TB["alg_time"]: (time.time() - start) * 1000}
+        return None
+
+    def _model_update_fused(self, data, global_iteration, nxt, start):
+        """Same schedule as above (msacl.py:191-224) on the autograd-free learner; one host read at the end."""
+        fl = self._fused_learner()
+        fl.q_update(data, nxt())
+        if global_iteration % self.target_network_frequency == 0:
+            self._target_update()
+        fl.lyapunov_update(data)
+        if global_iteration % self.policy_frequency == 0:
+            for _ in range(self.policy_frequency):
+                fl.policy_update(data, nxt())
+                if self.auto_alpha:
+                    fl.alpha_update()
+            s = fl.read_stats()
+            return {"MSACL/entropy-RL iter": s["entropy"], "MSACL/alpha-RL iter": self._get_alpha(),
+                    "MSACL/q1_mean-RL iter": s["q1_mean"], "MSACL/q2_mean-RL iter": s["q2_mean"],
+                    TB["loss_critic"]: s["loss_q"], TB["loss_lyapunov"]: s["loss_lya"], TB["loss_actor"]: s["loss_policy"],
                     TB["alg_time"]: (time.time() - start) * 1000}
         return None
 

@@ -1,0 +1,262 @@
+// tcgen05 split-bf16 GEMM with fused MLP epilogues: the dense layers of the MSACL learner's networks
+// (ActionValue / LyapunovValue / StochaPolicy, RL/apprfunc/mlp.py:18-52,72-88,111-136) forward AND backward.
+//
+//     C[r][n] = epilogue( sum_k A(r, k) * B(n, k) ),   r < m, n < n_total, k < k_total
+//
+// A and B are FP32 in global memory behind (row stride, k stride) pairs, so the same kernel covers
+//   forward   H = act(X W^T + b)          A = X [rows][in]      B = W [out][in]  (torch nn.Linear layout, K-major as is)
+//   dgrad     dX = (dY W) * act'(X)       A = dY [rows][out]    B(n, k) = W[k][n]          (strided read of W)
+//   wgrad     dW = dY^T X                 A(r, k) = dY[k][r]    B(n, k) = X[k][n]          (K = rows, split over CTAs)
+// Operand tiles are converted on the fly by 4 loader warps: FP32 -> bf16 hi + bf16 residual lo (x = hi + lo + O(2^-17 x)),
+// written into the UMMA canonical K-major no-swizzle layout (tcgen05.cuh); one elected thread issues
+// a_hi*b_hi + a_hi*b_lo + a_lo*b_hi per 16-wide k-step (FP32 accumulation in TMEM, "bf16x3": FP32-class products,
+// measured 1e-5 relative on a 256-long dot product); 4 epilogue warps read the accumulator with tcgen05.ld and apply
+// bias / activation / activation-derivative mask / row sum of squares, then store (or store split-K partials).
+// CTA tile 128 x (<= 256) x 32 per stage, 2 stages, 96 KB of shared memory -> 2 CTAs per SM, so one CTA's epilogue
+// overlaps the other's main loop.  Roofline: tensor (3 UMMAs per algorithmic product).
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace msacl {
+
+constexpr int GM = 128, GN = 256, GK = 32;
+constexpr int G_STAGES = 2;
+constexpr int GA_HALF = GM * GK * 2;       // 8 KB: hi (or lo) image of an A stage
+constexpr int GB_HALF = GN * GK * 2;       // 16 KB
+constexpr int GA_LBO = GM * 16, GB_LBO = GN * 16, G_SBO = 128;
+constexpr int G_THREADS = 288;             // warps 0-3 epilogue (TMEM lane quadrant = warp), 4-7 loaders, 8 MMA issuer
+constexpr int G_LOADERS = 128;
+
+struct GemmSmem {
+  alignas(128) unsigned char a[G_STAGES][2 * GA_HALF];
+  alignas(128) unsigned char b[G_STAGES][2 * GB_HALF];
+  unsigned long long full[G_STAGES], empty[G_STAGES], accfull;
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ uint32_t g_pack_bf16x2_rn(float lo, float hi) {   // {hi:lo} packed, RNE
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void g_split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    h[p] = g_pack_bf16x2_rn(v[2 * p], v[2 * p + 1]);
+    const float r0 = v[2 * p] - __uint_as_float(h[p] << 16);
+    const float r1 = v[2 * p + 1] - __uint_as_float(h[p] & 0xFFFF0000u);
+    l[p] = g_pack_bf16x2_rn(r0, r1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// One operand row (local index rl, global row index `row`) of a 32-wide K stage -> 4 K blocks of 8 into the hi / lo images.
+// All 32 loads are issued before the first conversion (memory-level parallelism).
+template <int LBO>
+__device__ __forceinline__ void g_load_row(unsigned char* hi_img, unsigned char* lo_img, const float* __restrict__ src, int64_t rs,
+                                           int64_t ks, int64_t row, bool row_ok, int k0, int kend, int rl, bool vec) {
+  float v[4][8];
+  if (row_ok && vec && k0 + GK <= kend) {
+    const float4* p = reinterpret_cast<const float4*>(src + row * rs + k0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = p[i];
+      v[i >> 1][(i & 1) * 4 + 0] = t.x; v[i >> 1][(i & 1) * 4 + 1] = t.y; v[i >> 1][(i & 1) * 4 + 2] = t.z; v[i >> 1][(i & 1) * 4 + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + kb * 8 + j;
+        v[kb][j] = (row_ok && k < kend) ? src[row * rs + (int64_t)k * ks] : 0.f;
+      }
+  }
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    uint4 hi, lo;
+    g_split8(v[kb], hi, lo);
+    *reinterpret_cast<uint4*>(hi_img + kb * LBO + rl * 16) = hi;
+    *reinterpret_cast<uint4*>(lo_img + kb * LBO + rl * 16) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(G_THREADS, 2) gemm_tc_kernel(msacl_gemm_t g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+  // K range of this split (multiples of the stage width)
+  const int kper = ((g.k + g.split_k - 1) / g.split_k + GK - 1) / GK * GK;
+  const int kbeg = blockIdx.z * kper;
+  const int kend = min(g.k, kbeg + kper);
+  const int nk = kend > kbeg ? (kend - kbeg + GK - 1) / GK : 0;
+  const int n_rem = g.n - n0;
+  const int n_mma = n_rem >= GN ? GN : ((n_rem + 15) / 16) * 16;        // UMMA N: multiple of 16, 16..256
+
+  if (tid == 0) {
+    for (int s = 0; s < G_STAGES; ++s) { tc::mbar_init(&sm.full[s], G_LOADERS); tc::mbar_init(&sm.empty[s], 1); }
+    tc::mbar_init(&sm.accfull, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&sm.tmem_slot, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sm.tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // =========================== loaders: FP32 global -> split-bf16 operand images ===========================
+    const int t = tid - 128;
+    const bool avec = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (kbeg & 3) == 0;
+    const bool bvec = g.b_k_stride == 1 && (g.b_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0 && (kbeg & 3) == 0;
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % G_STAGES;
+      if (it >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((it / G_STAGES - 1) & 1));
+      const int k0 = kbeg + it * GK;
+      g_load_row<GA_LBO>(sm.a[s], sm.a[s] + GA_HALF, g.a, g.a_row_stride, g.a_k_stride, m0 + t, m0 + t < g.m, k0, kend, t, avec);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int rl = t + h * 128;
+        if (rl < n_mma)
+          g_load_row<GB_LBO>(sm.b[s], sm.b[s] + GB_HALF, g.b, g.b_row_stride, g.b_k_stride, n0 + rl, n0 + rl < g.n, k0, kend, rl, bvec);
+      }
+      tc::fence_async_smem();
+      tc::mbar_arrive(&sm.full[s]);
+    }
+  } else if (warp == 8) {
+    // =========================== MMA issuer ===========================
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(GM, n_mma);
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % G_STAGES;
+        tc::mbar_wait(&sm.full[s], (uint32_t)((it / G_STAGES) & 1));
+        tc::tc_fence_after();
+        const uint32_t ab = tc::smem_u32(sm.a[s]), bb = tc::smem_u32(sm.b[s]);
+#pragma unroll
+        for (int j = 0; j < GK / 16; ++j) {
+          const uint64_t da1 = tc::make_smem_desc(ab + j * 2 * GA_LBO, GA_LBO, G_SBO);
+          const uint64_t da2 = tc::make_smem_desc(ab + GA_HALF + j * 2 * GA_LBO, GA_LBO, G_SBO);
+          const uint64_t db1 = tc::make_smem_desc(bb + j * 2 * GB_LBO, GB_LBO, G_SBO);
+          const uint64_t db2 = tc::make_smem_desc(bb + GB_HALF + j * 2 * GB_LBO, GB_LBO, G_SBO);
+          tc::umma_bf16(tmem, da1, db1, idesc, (it > 0 || j > 0) ? 1u : 0u);
+          tc::umma_bf16(tmem, da1, db2, idesc, 1u);
+          tc::umma_bf16(tmem, da2, db1, idesc, 1u);
+        }
+        tc::umma_commit(&sm.empty[s]);
+      }
+      tc::umma_commit(&sm.accfull);
+    }
+  } else {
+    // =========================== epilogue: TMEM -> bias / activation / mask -> global ===========================
+    const int row = m0 + warp * 32 + lane;
+    const bool row_ok = row < g.m;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    float* crow = g.c + (int64_t)blockIdx.z * g.c_split_stride + (int64_t)row * g.ldc + n0;
+    const float* mrow = g.mask_src ? g.mask_src + (int64_t)row * g.mask_ld + n0 : nullptr;
+    const bool cvec = (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(g.c) & 15) == 0 && (g.c_split_stride & 3) == 0;
+    const bool mvec = mrow && (g.mask_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask_src) & 15) == 0;
+    float ss = 0.f;
+    if (nk > 0) {
+      tc::mbar_wait(&sm.accfull, 0u);
+      tc::tc_fence_after();
+    }
+    for (int c = 0; c < n_mma; c += 32) {
+      uint32_t v[32];
+      if (nk == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      } else if (n_mma - c >= 32) {
+        tc::tmem_ld32(tmem + lane_addr + (uint32_t)c, v);
+        tc::tmem_ld_wait();
+      } else {
+        uint32_t w[16];
+        tc::tmem_ld16(tmem + lane_addr + (uint32_t)c, w);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
+      }
+      if (!row_ok) continue;
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const int col = c + j4;                 // tile-local column
+        if (col >= n_rem) break;
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = __uint_as_float(v[j4 + j]);
+        const bool full4 = col + 3 < n_rem;
+        if (g.bias) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (col + j < n_rem) x[j] += g.bias[n0 + col + j];
+        }
+        if (g.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
+        } else if (g.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+        }
+        if (mrow) {
+          float hsrc[4];
+          if (mvec && full4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(mrow + col);
+            hsrc[0] = t4.x; hsrc[1] = t4.y; hsrc[2] = t4.z; hsrc[3] = t4.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hsrc[j] = (col + j < n_rem) ? mrow[col + j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (g.mask_act == 1) x[j] = hsrc[j] > 0.f ? x[j] : 0.f;                       // relu'(pre) = [post > 0]
+            else if (g.mask_act == 2) x[j] = x[j] * (1.0f - hsrc[j] * hsrc[j]);           // tanh'(pre) = 1 - post^2
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (col + j < n_rem) ss = __fmaf_rn(x[j], x[j], ss);
+        if (cvec && full4) {
+          *reinterpret_cast<float4*>(crow + col) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (col + j < n_rem) crow[col + j] = x[j];
+        }
+      }
+    }
+    if (g.row_sumsq && row_ok) g.row_sumsq[row] = ss;
+  }
+  // ---- teardown
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace msacl
+
+using namespace msacl;
+
+extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
+  if (!g || !g->a || !g->b || !g->c || g->m <= 0 || g->n <= 0 || g->k <= 0 || g->split_k < 1 || g->ldc < 1) {
+    set_error("gemm_tc: bad argument");
+    return MSACL_ERR_BAD_ARG;
+  }
+  if (g->act < 0 || g->act > 2 || g->mask_act < 0 || g->mask_act > 2 || (g->mask_src && g->mask_act == 0)) {
+    set_error("gemm_tc: unknown activation code (0 none, 1 relu, 2 tanh)");
+    return MSACL_ERR_BAD_ARG;
+  }
+  if (g->split_k > 1 && (g->bias || g->act || g->mask_src || g->row_sumsq)) {
+    set_error("gemm_tc: split-K partials take no epilogue (bias / act / mask / row_sumsq)");
+    return MSACL_ERR_BAD_ARG;
+  }
+  if (g->row_sumsq && g->n > GN) { set_error("gemm_tc: row_sumsq needs n <= 256 (one column tile)"); return MSACL_ERR_BAD_ARG; }
+  const size_t smem = sizeof(GemmSmem) + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("gemm_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)((g->m + GM - 1) / GM), (unsigned)((g->n + GN - 1) / GN), (unsigned)g->split_k);
+  gemm_tc_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(*g);
+  return check_launch("gemm_tc");
+}

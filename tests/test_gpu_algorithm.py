@@ -19,10 +19,13 @@ def _kwargs(g):
                 lyapunov_output_dim=256)
 
 
-def test_model_update_matches_reference():
+@pytest.mark.parametrize("engine", ["fused", "torch"])
+def test_model_update_matches_reference(engine):
+    """engine "fused": every dense layer forward / backward is msacl_gemm_tc (tcgen05 split-bf16), no autograd;
+    engine "torch": autograd + cuBLAS.  Both must reproduce the reference's recorded model_update."""
     import msacl_b200
     g = load_golden("msacl_update_TwoLink.npz")
-    alg = msacl_b200.create_alg(algorithm="msacl", **_kwargs(g))
+    alg = msacl_b200.create_alg(algorithm="msacl", learner_engine=engine, **_kwargs(g))
     keys = [str(k) for k in g["state_keys"]]
     sd = {k: torch.as_tensor(g["before_" + k]) for k in keys}
     assert set(alg.networks.state_dict().keys()) == set(keys)              # reference checkpoints load unchanged
