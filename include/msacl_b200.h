@@ -237,7 +237,7 @@ int msacl_polyak_update(int32_t count, const float* const* src, float* const* ds
  * (alpha, losses, entropy) resident on the device.
  * --------------------------------------------------------------------------------------------------------------- */
 
-/* One dense layer, forward or backward, as a split-bf16 ("bf16x3") tcgen05 GEMM with a fused epilogue:
+/* One dense layer, forward or backward, as a split-bf16 tcgen05 GEMM with a fused epilogue:
  *     C[r][n] = epilogue( sum_k A(r,k) * B(n,k) ),   A(r,k) = a[r*a_row_stride + k*a_k_stride],  B likewise (FP32, device)
  *   forward  (mlp.py:18-33)  H = act(X W^T + b):       a = X [rows][in], b = W [out][in] (nn.Linear layout), bias, act
  *   dgrad                    dX = (dY W) * act'(Xpost): a = dY, B(n,k) = W[k][n] (b_row_stride 1, b_k_stride in), mask_src = Xpost
@@ -256,6 +256,8 @@ typedef struct {
   int32_t act;
   const float* mask_src; int64_t mask_ld; int32_t mask_act;
   float* row_sumsq;
+  int32_t precision;   /* bf16 products per algorithmic product: 6 (or 0 = default; 3-term operand split, FP32-class ~2^-23)
+                          or 3 (2-term split, ~1.5e-5 relative per product, half the tensor work) */
 } msacl_gemm_t;
 int msacl_gemm_tc(const msacl_gemm_t* g, void* stream);
 

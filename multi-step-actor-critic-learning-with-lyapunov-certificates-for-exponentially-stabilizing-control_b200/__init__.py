@@ -5,7 +5,8 @@ upstream project; `msacl_b200.py` at the repo root aliases it).
 """
 from .specs import ENV_NAMES, SPECS, get_spec  # noqa: F401
 
-__all__ = ["ENV_NAMES", "SPECS", "get_spec", "create_envs", "create_sampler", "create_buffer", "create_alg", "load_library"]
+__all__ = ["ENV_NAMES", "SPECS", "get_spec", "create_envs", "create_sampler", "create_buffer", "create_alg", "create_evaluator",
+           "create_trainer", "load_library"]
 
 
 def load_library():
@@ -45,3 +46,21 @@ def create_alg(**kwargs):
     if name not in ("msacl", "msacl_b200"):
         raise KeyError(f"No registered algorithm with id: {name}")
     return B200MSACL(**kwargs)
+
+
+def create_evaluator(**kwargs):
+    """Drop-in for RL/create_pkg/create_evaluator.py (evaluator_name 'evaluator'): greedy evaluation on the fused kernel."""
+    from .evaluator import B200Evaluator
+    name = kwargs.get("evaluator_name", "evaluator")
+    if name not in ("evaluator", "b200_evaluator"):
+        raise KeyError(f"No registered evaluator with id: {name}")
+    return B200Evaluator(**kwargs)
+
+
+def create_trainer(alg, sampler, buffer, evaluator, **kwargs):
+    """Drop-in for RL/create_pkg/create_trainer.py:41-61 (trainer 'nstep_off_serial_trainer')."""
+    from .trainer import B200NstepOffSerialTrainer
+    name = kwargs.get("trainer", "nstep_off_serial_trainer")
+    if name not in ("nstep_off_serial_trainer", "b200_nstep_off_serial_trainer"):
+        raise KeyError(f"No registered trainer with id: {name}")
+    return B200NstepOffSerialTrainer(alg, sampler, buffer, evaluator, **kwargs)

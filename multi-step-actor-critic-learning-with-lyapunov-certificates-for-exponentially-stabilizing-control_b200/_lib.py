@@ -46,7 +46,7 @@ class Gemm(C.Structure):
                 ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
                 ("c", vp), ("ldc", C.c_int64), ("split_k", C.c_int32), ("c_split_stride", C.c_int64),
                 ("bias", vp), ("act", C.c_int32), ("mask_src", vp), ("mask_ld", C.c_int64), ("mask_act", C.c_int32),
-                ("row_sumsq", vp)]
+                ("row_sumsq", vp), ("precision", C.c_int32)]
 
 
 f32 = C.c_float

@@ -132,6 +132,8 @@ class B200MSACL:
                  lya_positive_scale=1.0, device="cuda", learner_engine="fused", **kwargs):
         self.device = torch.device(device)
         self.engine_name = learner_engine
+        # bf16 products per algorithmic product in the fused learner's GEMMs: 6 = FP32-class (default), 3 = half the tensor work
+        self.learner_precision = int(kwargs.get("learner_precision", 6))
         self.networks = ApproxContainer(**kwargs).to(self.device)
         self.gamma, self.retrace_lambda, self.lya_eta, self.tau = gamma, retrace_lambda, lya_eta, tau
         self.policy_frequency, self.target_network_frequency = policy_frequency, target_network_frequency

@@ -7,13 +7,16 @@
 //   forward   H = act(X W^T + b)          A = X [rows][in]      B = W [out][in]  (torch nn.Linear layout, K-major as is)
 //   dgrad     dX = (dY W) * act'(X)       A = dY [rows][out]    B(n, k) = W[k][n]          (strided read of W)
 //   wgrad     dW = dY^T X                 A(r, k) = dY[k][r]    B(n, k) = X[k][n]          (K = rows, split over CTAs)
-// Operand tiles are converted on the fly by 4 loader warps: FP32 -> bf16 hi + bf16 residual lo (x = hi + lo + O(2^-17 x)),
-// written into the UMMA canonical K-major no-swizzle layout (tcgen05.cuh); one elected thread issues
-// a_hi*b_hi + a_hi*b_lo + a_lo*b_hi per 16-wide k-step (FP32 accumulation in TMEM, "bf16x3": FP32-class products,
-// measured 1e-5 relative on a 256-long dot product); 4 epilogue warps read the accumulator with tcgen05.ld and apply
-// bias / activation / activation-derivative mask / row sum of squares, then store (or store split-K partials).
-// CTA tile 128 x (<= 256) x 32 per stage, 2 stages, 96 KB of shared memory -> 2 CTAs per SM, so one CTA's epilogue
-// overlaps the other's main loop.  Roofline: tensor (3 UMMAs per algorithmic product).
+// Operand tiles are converted on the fly by 4 loader warps: FP32 -> a sum of bf16 terms, written into the UMMA canonical
+// K-major no-swizzle layout (tcgen05.cuh); one elected thread issues the cross products per 16-wide k-step with FP32
+// accumulation in TMEM; 4 epilogue warps read the accumulator with tcgen05.ld and apply bias / activation /
+// activation-derivative mask / row sum of squares, then store (or store split-K partials).  Two precisions:
+//   NIMG = 3 ("bf16x6", default of the learner): x = x1 + x2 + x3 (24 mantissa bits), products a1b1 + a1b2 + a2b1 + a2b2 +
+//            a1b3 + a3b1 -- error ~2^-23 per product, i.e. FP32-class: hidden units land on the same side of the ReLU kink
+//            as an FP32 GEMM's, so post-Adam parameters reproduce the reference's at the cuBLAS engine's tolerance;
+//   NIMG = 2 ("bf16x3", the rollout kernel's scheme): x = x1 + x2 (16 bits), a1b1 + a1b2 + a2b1 -- ~1.5e-5 per product,
+//            half the tensor work and 2 CTAs per SM.
+// CTA tile 128 x (<= 256) x 32 per stage, 2 stages (144 KB / 96 KB of shared memory).  Roofline: tensor.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -27,9 +30,10 @@ constexpr int GA_LBO = GM * 16, GB_LBO = GN * 16, G_SBO = 128;
 constexpr int G_THREADS = 288;             // warps 0-3 epilogue (TMEM lane quadrant = warp), 4-7 loaders, 8 MMA issuer
 constexpr int G_LOADERS = 128;
 
+template <int NIMG>
 struct GemmSmem {
-  alignas(128) unsigned char a[G_STAGES][2 * GA_HALF];
-  alignas(128) unsigned char b[G_STAGES][2 * GB_HALF];
+  alignas(128) unsigned char a[G_STAGES][NIMG * GA_HALF];
+  alignas(128) unsigned char b[G_STAGES][NIMG * GB_HALF];
   unsigned long long full[G_STAGES], empty[G_STAGES], accfull;
   uint32_t tmem_slot;
 };
@@ -39,23 +43,29 @@ __device__ __forceinline__ uint32_t g_pack_bf16x2_rn(float lo, float hi) {   // 
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-__device__ __forceinline__ void g_split8(const float (&v)[8], uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
+// 8 floats -> NIMG images of 8 bf16: image i holds bf16(x - sum of the previous images) (every subtraction is exact)
+template <int NIMG>
+__device__ __forceinline__ void g_split8(const float (&v)[8], uint4 (&img)[NIMG]) {
+  float r[8];
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    h[p] = g_pack_bf16x2_rn(v[2 * p], v[2 * p + 1]);
-    const float r0 = v[2 * p] - __uint_as_float(h[p] << 16);
-    const float r1 = v[2 * p + 1] - __uint_as_float(h[p] & 0xFFFF0000u);
-    l[p] = g_pack_bf16x2_rn(r0, r1);
+  for (int j = 0; j < 8; ++j) r[j] = v[j];
+#pragma unroll
+  for (int i = 0; i < NIMG; ++i) {
+    uint32_t h[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      h[p] = g_pack_bf16x2_rn(r[2 * p], r[2 * p + 1]);
+      r[2 * p] -= __uint_as_float(h[p] << 16);
+      r[2 * p + 1] -= __uint_as_float(h[p] & 0xFFFF0000u);
+    }
+    img[i] = make_uint4(h[0], h[1], h[2], h[3]);
   }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // One operand row (local index rl, global row index `row`) of a 32-wide K stage -> 4 K blocks of 8 into the hi / lo images.
 // All 32 loads are issued before the first conversion (memory-level parallelism).
-template <int LBO>
-__device__ __forceinline__ void g_load_row(unsigned char* hi_img, unsigned char* lo_img, const float* __restrict__ src, int64_t rs,
+template <int LBO, int HALF, int NIMG>
+__device__ __forceinline__ void g_load_row(unsigned char* img0, const float* __restrict__ src, int64_t rs,
                                            int64_t ks, int64_t row, bool row_ok, int k0, int kend, int rl, bool vec) {
   float v[4][8];
   if (row_ok && vec && k0 + GK <= kend) {
@@ -76,16 +86,17 @@ __device__ __forceinline__ void g_load_row(unsigned char* hi_img, unsigned char*
   }
 #pragma unroll
   for (int kb = 0; kb < 4; ++kb) {
-    uint4 hi, lo;
-    g_split8(v[kb], hi, lo);
-    *reinterpret_cast<uint4*>(hi_img + kb * LBO + rl * 16) = hi;
-    *reinterpret_cast<uint4*>(lo_img + kb * LBO + rl * 16) = lo;
+    uint4 img[NIMG];
+    g_split8<NIMG>(v[kb], img);
+#pragma unroll
+    for (int i = 0; i < NIMG; ++i) *reinterpret_cast<uint4*>(img0 + i * HALF + kb * LBO + rl * 16) = img[i];
   }
 }
 
-__global__ void __launch_bounds__(G_THREADS, 2) gemm_tc_kernel(msacl_gemm_t g) {
+template <int NIMG>
+__global__ void __launch_bounds__(G_THREADS, NIMG == 2 ? 2 : 1) gemm_tc_kernel(msacl_gemm_t g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
+  GemmSmem<NIMG>& sm = *reinterpret_cast<GemmSmem<NIMG>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
   // K range of this split (multiples of the stage width)
@@ -116,12 +127,12 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_tc_kernel(msacl_gemm_t g) {
       const int s = it % G_STAGES;
       if (it >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((it / G_STAGES - 1) & 1));
       const int k0 = kbeg + it * GK;
-      g_load_row<GA_LBO>(sm.a[s], sm.a[s] + GA_HALF, g.a, g.a_row_stride, g.a_k_stride, m0 + t, m0 + t < g.m, k0, kend, t, avec);
+      g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, m0 + t, m0 + t < g.m, k0, kend, t, avec);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int rl = t + h * 128;
         if (rl < n_mma)
-          g_load_row<GB_LBO>(sm.b[s], sm.b[s] + GB_HALF, g.b, g.b_row_stride, g.b_k_stride, n0 + rl, n0 + rl < g.n, k0, kend, rl, bvec);
+          g_load_row<GB_LBO, GB_HALF, NIMG>(sm.b[s], g.b, g.b_row_stride, g.b_k_stride, n0 + rl, n0 + rl < g.n, k0, kend, rl, bvec);
       }
       tc::fence_async_smem();
       tc::mbar_arrive(&sm.full[s]);
@@ -137,13 +148,21 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_tc_kernel(msacl_gemm_t g) {
         const uint32_t ab = tc::smem_u32(sm.a[s]), bb = tc::smem_u32(sm.b[s]);
 #pragma unroll
         for (int j = 0; j < GK / 16; ++j) {
-          const uint64_t da1 = tc::make_smem_desc(ab + j * 2 * GA_LBO, GA_LBO, G_SBO);
-          const uint64_t da2 = tc::make_smem_desc(ab + GA_HALF + j * 2 * GA_LBO, GA_LBO, G_SBO);
-          const uint64_t db1 = tc::make_smem_desc(bb + j * 2 * GB_LBO, GB_LBO, G_SBO);
-          const uint64_t db2 = tc::make_smem_desc(bb + GB_HALF + j * 2 * GB_LBO, GB_LBO, G_SBO);
-          tc::umma_bf16(tmem, da1, db1, idesc, (it > 0 || j > 0) ? 1u : 0u);
-          tc::umma_bf16(tmem, da1, db2, idesc, 1u);
-          tc::umma_bf16(tmem, da2, db1, idesc, 1u);
+          uint64_t da[NIMG], db[NIMG];
+#pragma unroll
+          for (int i = 0; i < NIMG; ++i) {
+            da[i] = tc::make_smem_desc(ab + i * GA_HALF + j * 2 * GA_LBO, GA_LBO, G_SBO);
+            db[i] = tc::make_smem_desc(bb + i * GB_HALF + j * 2 * GB_LBO, GB_LBO, G_SBO);
+          }
+          // smallest cross terms first would be ideal for the FP32 accumulator; the order below keeps the accumulate flag simple
+          tc::umma_bf16(tmem, da[0], db[0], idesc, (it > 0 || j > 0) ? 1u : 0u);
+          tc::umma_bf16(tmem, da[0], db[1], idesc, 1u);
+          tc::umma_bf16(tmem, da[1], db[0], idesc, 1u);
+          if constexpr (NIMG == 3) {
+            tc::umma_bf16(tmem, da[1], db[1], idesc, 1u);
+            tc::umma_bf16(tmem, da[0], db[2], idesc, 1u);
+            tc::umma_bf16(tmem, da[2], db[0], idesc, 1u);
+          }
         }
         tc::umma_commit(&sm.empty[s]);
       }
@@ -249,14 +268,16 @@ extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
     return MSACL_ERR_BAD_ARG;
   }
   if (g->row_sumsq && g->n > GN) { set_error("gemm_tc: row_sumsq needs n <= 256 (one column tile)"); return MSACL_ERR_BAD_ARG; }
-  const size_t smem = sizeof(GemmSmem) + 128;
+  if (g->precision != 0 && g->precision != 3 && g->precision != 6) { set_error("gemm_tc: precision must be 6 (default, bf16x6) or 3 (bf16x3)"); return MSACL_ERR_BAD_ARG; }
+  const dim3 grid((unsigned)((g->m + GM - 1) / GM), (unsigned)((g->n + GN - 1) / GN), (unsigned)g->split_k);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("gemm_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem<2>) + 128);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem<3>) + 128);
+    if (e != cudaSuccess) { set_error("gemm_tc: smem attr: %s", cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
     attr_set = true;
   }
-  const dim3 grid((unsigned)((g->m + GM - 1) / GM), (unsigned)((g->n + GN - 1) / GN), (unsigned)g->split_k);
-  gemm_tc_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(*g);
+  if (g->precision == 3) gemm_tc_kernel<2><<<grid, G_THREADS, sizeof(GemmSmem<2>) + 128, (cudaStream_t)stream>>>(*g);
+  else gemm_tc_kernel<3><<<grid, G_THREADS, sizeof(GemmSmem<3>) + 128, (cudaStream_t)stream>>>(*g);
   return check_launch("gemm_tc");
 }

@@ -44,11 +44,11 @@ class _Launcher:
 
 
 def _desc(a, a_rs, a_ks, b, b_rs, b_ks, m, n, k, c, ldc, split_k=1, c_split_stride=0, bias=None, act=0, mask=None, mask_ld=0,
-          mask_act=0, row_sumsq=None):
+          mask_act=0, row_sumsq=None, precision=0):
     p = lambda t: None if t is None else (t if isinstance(t, int) else t.data_ptr())
     return _lib.Gemm(a=p(a), a_row_stride=a_rs, a_k_stride=a_ks, b=p(b), b_row_stride=b_rs, b_k_stride=b_ks, m=m, n=n, k=k, c=p(c),
                      ldc=ldc, split_k=split_k, c_split_stride=c_split_stride, bias=p(bias), act=act, mask_src=p(mask), mask_ld=mask_ld,
-                     mask_act=mask_act, row_sumsq=p(row_sumsq))
+                     mask_act=mask_act, row_sumsq=p(row_sumsq), precision=precision)
 
 
 class MLPWorkspace:
@@ -60,6 +60,8 @@ class MLPWorkspace:
         self.rows, self.train = rows, train
         M, Din, Dout, a = rows, mlp.din, mlp.dout, mlp.act
         (W1, b1), (W2, b2), (W3, b3) = mlp.layers
+        import functools
+        _desc = functools.partial(globals()["_desc"], precision=mlp.precision)
         self.h1, self.h2, self.y = f(M, HID), f(M, HID), f(M, Dout)
         self.v = f(M) if sumsq else None
         self.x = None
@@ -95,7 +97,10 @@ class FusedMLP:
     """A reference-style 3-layer MLP (mlp.py:18-33: Linear-act-Linear-act-Linear-Identity, hidden width 256) driven by
     msacl_gemm_tc.  `seq` is the nn.Sequential whose parameters stay the single source of truth."""
 
-    def __init__(self, seq, device):
+    def __init__(self, seq, device, precision=6):
+        if precision not in (3, 6):
+            raise ValueError("precision: 6 (bf16x6, FP32-class) or 3 (bf16x3)")
+        self.precision = precision
         lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
         other = [m for m in seq if not isinstance(m, torch.nn.Linear)]
         if len(lin) != 3 or lin[0].out_features != HID or lin[1].in_features != HID or lin[1].out_features != HID or lin[2].in_features != HID:
@@ -105,21 +110,33 @@ class FusedMLP:
             raise ValueError(f"FusedMLP: unsupported activations {[type(m).__name__ for m in other]} (relu / tanh hidden, linear output)")
         self.act = ACT_CODE[type(other[0])]
         self.device = torch.device(device)
-        self.layers = [(l.weight.data, l.bias.data) for l in lin]
-        for w, b in self.layers:
-            if not (w.is_cuda and w.is_contiguous() and b.is_contiguous() and w.dtype == torch.float32):
-                raise ValueError("FusedMLP needs contiguous CUDA float32 parameters")
+        self._lin = lin
         self.din, self.dout = lin[0].in_features, lin[2].out_features
-        self.params = [t for wb in self.layers for t in wb]
         self._ws = {}
         self._l = _Launcher()
+        self._bind()
+
+    def _key(self):
+        return tuple(t.data_ptr() for l in self._lin for t in (l.weight, l.bias))
+
+    def _bind(self):
+        """(Re)capture the parameter storages.  `nn.Module.to()` replaces them -- e.g. the reference trainer's
+        ModuleOnDevice shuffle (nstep_off_serial_trainer.py:78) moves the networks to the CPU and back every iteration --
+        so descriptors built over the old storages must be dropped."""
+        self.layers = [(l.weight.data, l.bias.data) for l in self._lin]
+        for w, b in self.layers:
+            if not (w.is_cuda and w.is_contiguous() and b.is_contiguous() and w.dtype == torch.float32):
+                raise ValueError("FusedMLP needs contiguous CUDA float32 parameters (is the module on the GPU?)")
+        self.params = [t for wb in self.layers for t in wb]
+        self._bound = self._key()
+        self._ws.clear()
 
     def workspace(self, tag, rows, train=False, need_dx=False, sumsq=False):
+        if self._key() != self._bound:
+            self._bind()
         key = (tag, int(rows), train, need_dx, sumsq)
         ws = self._ws.get(key)
         if ws is None:
-            if any((p.data_ptr() != q.data_ptr()) for p, q in zip(self.params, [t for wb in self.layers for t in wb])):
-                raise RuntimeError("a parameter changed its storage")
             ws = self._ws[key] = MLPWorkspace(self, int(rows), train, need_dx, sumsq)
         return ws
 
@@ -174,17 +191,30 @@ class FusedAdam:
             if not st:
                 optimizer.state[p] = {"step": torch.tensor(0.0), "exp_avg": torch.zeros_like(p.data), "exp_avg_sq": torch.zeros_like(p.data)}
         self.step_count = int(optimizer.state[self.params[0]]["step"])
-        t64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
-        self._p = t64([p.data.data_ptr() for p in self.params])
-        self._m = t64([optimizer.state[p]["exp_avg"].data_ptr() for p in self.params])
-        self._v = t64([optimizer.state[p]["exp_avg_sq"].data_ptr() for p in self.params])
-        self._n = t64([p.numel() for p in self.params])
         self._max = max(p.numel() for p in self.params)
         self._grad_key, self._g, self._s = None, None, None
+        self._param_key = None
         self.lib = _lib.load()
+
+    def _tables(self):
+        key = tuple(p.data.data_ptr() for p in self.params)
+        if key != self._param_key:                   # first call, or the module was moved (new parameter storages)
+            dev = self.params[0].device
+            t64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
+            st = self.opt.state
+            for p in self.params:                    # optimizer state follows the parameters' device
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if st[p][k].device != dev:
+                        st[p][k] = st[p][k].to(dev)
+            self._p = t64(list(key))
+            self._m = t64([st[p]["exp_avg"].data_ptr() for p in self.params])
+            self._v = t64([st[p]["exp_avg_sq"].data_ptr() for p in self.params])
+            self._n = t64([p.numel() for p in self.params])
+            self._param_key = key
 
     def step(self, grads):
         """grads: [(partials tensor [nsplit, *param.shape], nsplit)] aligned with the parameter list."""
+        self._tables()
         key = tuple((t.data_ptr(), s) for t, s in grads)
         if key != self._grad_key:
             dev = self.params[0].device
@@ -210,14 +240,14 @@ class FusedLearner:
         self.alg = alg
         net, dev = alg.networks, alg.device
         self.dev, self.lib = dev, _lib.load()
-        self.P = FusedMLP(net.policy.policy, dev)
-        self.Q1, self.Q2 = FusedMLP(net.q1.q, dev), FusedMLP(net.q2.q, dev)
-        self.Q1t, self.Q2t = FusedMLP(net.q1_target.q, dev), FusedMLP(net.q2_target.q, dev)
-        self.L = FusedMLP(net.lyapunov.lya, dev)
+        pr = int(getattr(alg, "learner_precision", 6))
+        self.P = FusedMLP(net.policy.policy, dev, pr)
+        self.Q1, self.Q2 = FusedMLP(net.q1.q, dev, pr), FusedMLP(net.q2.q, dev, pr)
+        self.Q1t, self.Q2t = FusedMLP(net.q1_target.q, dev, pr), FusedMLP(net.q2_target.q, dev, pr)
+        self.L = FusedMLP(net.lyapunov.lya, dev, pr)
         if self.P.act != 1 or self.Q1.act != 1:
             pass      # any supported activation works for the learner; the ROLLOUT kernels additionally require ReLU policies
         self.D, self.A = self.P.din, self.P.dout // 2
-        self.lo, self.hi = net.policy.act_low_lim.data.float().contiguous(), net.policy.act_high_lim.data.float().contiguous()
         self.min_ls, self.max_ls = float(net.policy.min_log_std), float(net.policy.max_log_std)
         self.adam_q1 = FusedAdam(net.q1_optimizer, list(net.q1.parameters()))
         self.adam_q2 = FusedAdam(net.q2_optimizer, list(net.q2.parameters()))
@@ -231,6 +261,14 @@ class FusedLearner:
         self._buf = {}
 
     # ---- small helpers
+    @property
+    def lo(self):      # fetched per call: module.to() replaces buffer storages
+        return self.alg.networks.policy.act_low_lim.data
+
+    @property
+    def hi(self):
+        return self.alg.networks.policy.act_high_lim.data
+
     def _tmp(self, name, *shape):
         key = (name,) + tuple(shape)
         t = self._buf.get(key)

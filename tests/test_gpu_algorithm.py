@@ -40,9 +40,10 @@ def test_model_update_matches_reference(engine):
     after = alg.networks.state_dict()
     for k in keys:
         got, ref = after[k].cpu().numpy(), g["after_" + k]
-        close = np.isclose(got, ref, rtol=1e-4, atol=2e-6)
-        # Adam's first step is lr * sign-like: a gradient entry at round-off level may flip; allow 0.1 %
-        assert close.mean() > 0.999, (k, 1 - close.mean(), np.abs(got - ref).max())
+        bad = (~np.isclose(got, ref, rtol=1e-4, atol=2e-6)).sum()
+        # Adam's first step is lr * sign-like: a gradient entry at round-off level may flip; allow 0.1 % (>= 3 entries:
+        # the smallest tensors have only 256 ... 1536 of them)
+        assert bad <= max(3, 0.001 * got.size), (k, bad, got.size, np.abs(got - ref).max())
     assert alg.model_update(data, 3) is None                                  # odd iteration: no policy update, returns None
 
 
