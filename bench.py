@@ -610,18 +610,31 @@ def main():
     # straight into it, N>1 all-gathers it on a side stream (consumed one step later), and ONE contiguous D2H copy brings
     # the [G, P] result into pinned host memory, where the learner-facing {field: [B, n, .]} dict is a set of views.
     exch = mdist.BatchExchange(fields, Bq, n_step, dev)
-    host_packed = torch.empty(world, exch.P, dtype=torch.float32).pin_memory()
-    host_batch, host_stats = exch.host_views(host_packed)
-    d2h_bytes = host_packed.numel() * 4
+    host_packed = [torch.empty(world, exch.P, dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_ready = [None, None]
+    d2h_bytes = host_packed[0].numel() * 4
+    step_no = [0]
+    consumed = [0.0]
 
     def e2e_step():
+        cur = step_no[0] & 1
         a = upload_actor()                               # H2D: the learner's current policy (pinned host memory)
         batch = ro.run(a)                                # fused K-step rollout
         buf.add_batch(batch)                             # n-step windows -> device replay store
         sub = buf.sample_batch(Bq, out=exch.views())     # replay batch for the learner, gathered into the packed buffer
         packed = exch.exchange(sub, ro.stats[:8], unpack=False)   # N>1: NCCL all-gather on a side stream, previous result back
-        host_packed.copy_(packed, non_blocking=True)     # D2H: the replay batch + episode statistics
-        stream.synchronize()
+        host_packed[cur].copy_(packed, non_blocking=True)         # D2H: the replay batch + episode statistics
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        host_ready[cur] = ev
+        # the host (learner side) consumes the batch of the PREVIOUS step while this step's launches are in flight: the
+        # learner's data is one iteration stale by design, so the per-step host wait never drains the GPU queue
+        prev = host_ready[1 - cur]
+        if prev is not None:
+            prev.synchronize()
+            hb, hs = exch.host_views(host_packed[1 - cur])
+            consumed[0] += float(hs[0]) + float(hb["rew"][0, 0])       # touch the data like a consumer would
+        step_no[0] += 1
 
     for _ in range(args.warmup):
         e2e_step()
@@ -630,6 +643,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         e2e_step()
+    host_ready[(step_no[0] - 1) & 1].synchronize()       # the last step's batch has reached the host inside the timed region
     e1.record(stream)
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -730,7 +744,8 @@ def main():
                     "replay_capacity_windows": cap, "replay_windows_resident_after_run": windows_kept,
                     "what": "per step: H2D actor weights (pinned) -> sampler rollout -> buffer.add_batch (device window index scatter) -> "
                             "buffer.sample_batch (n-step gather) -> [one packed NCCL all-gather of the sub-batches + statistics on a side "
-                            "stream, consumed one step later, if N>1] -> D2H replay batch + episode stats (pinned)"},
+                            "stream, consumed one step later, if N>1] -> D2H replay batch + episode stats (pinned, double-buffered: the host reads step t-1's "
+                            "batch while step t runs)"},
             "roofline": roofline,
         }
         if configs is not None:

@@ -27,8 +27,9 @@ constexpr int G_STAGES = 2;
 constexpr int GA_HALF = GM * GK * 2;       // 8 KB: hi (or lo) image of an A stage
 constexpr int GB_HALF = GN * GK * 2;       // 16 KB
 constexpr int GA_LBO = GM * 16, GB_LBO = GN * 16, G_SBO = 128;
-constexpr int G_THREADS = 288;             // warps 0-3 epilogue (TMEM lane quadrant = warp), 4-7 loaders, 8 MMA issuer
-constexpr int G_LOADERS = 128;
+constexpr int G_LOADERS = 384;             // 12 loader warps: threads 0..127 own the A tile, 128..383 the B tile
+constexpr int G_MMA_WARP = 4 + G_LOADERS / 32;
+constexpr int G_THREADS = 32 * (G_MMA_WARP + 1);   // warps 0-3 epilogue (TMEM lane quadrant = warp), 4-15 loaders, 16 MMA issuer
 
 template <int NIMG>
 struct GemmSmem {
@@ -59,6 +60,48 @@ __device__ __forceinline__ void g_split8(const float (&v)[8], uint4 (&img)[NIMG]
       r[2 * p + 1] -= __uint_as_float(h[p] & 0xFFFF0000u);
     }
     img[i] = make_uint4(h[0], h[1], h[2], h[3]);
+  }
+}
+
+// k-contiguous operand (k stride 1, rows 16-byte aligned): a group of GSZ threads loads a `rows` x 32 tile as float4 chunks,
+// consecutive lanes on consecutive chunks (a warp instruction covers 4 whole 128-byte rows: fully coalesced, 4 L1 tags
+// instead of 32).  Thread t keeps chunk c = t % 8 (K block c / 2, half c % 2) of rows t / 8 + j * GSZ / 8; each chunk becomes one
+// 8-byte store per image (4-way bank conflict among the 4 K blocks of a row group, ~1k cycles per stage).
+template <int LBO, int HALF, int NIMG, int GSZ, int ROWS>
+__device__ __forceinline__ void g_load_tile_kcontig(unsigned char* img0, const float* __restrict__ src, int64_t rs, int64_t row0,
+                                                    int64_t row_limit, int rows_used, int k0, int kend, int t) {
+  constexpr int NIT = ROWS * 8 / GSZ;
+  const int c = t & 7;
+  const int kk = k0 + c * 4;
+  float4 v[NIT];
+#pragma unroll
+  for (int j = 0; j < NIT; ++j) {
+    const int rl = (t >> 3) + j * (GSZ / 8);
+    const int64_t row = row0 + rl;
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < rows_used && row < row_limit) {
+      const float* p = src + row * rs + kk;
+      if (kk + 3 < kend) v[j] = *reinterpret_cast<const float4*>(p);
+      else {
+        if (kk < kend) v[j].x = p[0];
+        if (kk + 1 < kend) v[j].y = p[1];
+        if (kk + 2 < kend) v[j].z = p[2];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NIT; ++j) {
+    const int rl = (t >> 3) + j * (GSZ / 8);
+    if (rl >= rows_used) continue;
+    float r[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+    unsigned char* dst = img0 + (c >> 1) * LBO + rl * 16 + (c & 1) * 8;
+#pragma unroll
+    for (int i = 0; i < NIMG; ++i) {
+      const uint32_t h0 = g_pack_bf16x2_rn(r[0], r[1]), h1 = g_pack_bf16x2_rn(r[2], r[3]);
+      r[0] -= __uint_as_float(h0 << 16); r[1] -= __uint_as_float(h0 & 0xFFFF0000u);
+      r[2] -= __uint_as_float(h1 << 16); r[3] -= __uint_as_float(h1 & 0xFFFF0000u);
+      *reinterpret_cast<uint2*>(dst + i * HALF) = make_uint2(h0, h1);
+    }
   }
 }
 
@@ -112,32 +155,35 @@ __global__ void __launch_bounds__(G_THREADS, NIMG == 2 ? 2 : 1) gemm_tc_kernel(m
     tc::mbar_init(&sm.accfull, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 8) tc::tmem_alloc(&sm.tmem_slot, 256);
+  if (warp == G_MMA_WARP) tc::tmem_alloc(&sm.tmem_slot, 256);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = sm.tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < G_MMA_WARP) {
     // =========================== loaders: FP32 global -> split-bf16 operand images ===========================
+    // threads 0..127 of the loader group own the A tile (128 rows), threads 128..383 the B tile (<= 256 rows): one row (or
+    // 8 coalesced float4 chunks) per thread per stage, so a stage costs one global round trip.
     const int t = tid - 128;
-    const bool avec = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (kbeg & 3) == 0;
-    const bool bvec = g.b_k_stride == 1 && (g.b_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0 && (kbeg & 3) == 0;
+    const bool avec = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0;
+    const bool bvec = g.b_k_stride == 1 && (g.b_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0;
     for (int it = 0; it < nk; ++it) {
       const int s = it % G_STAGES;
       if (it >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((it / G_STAGES - 1) & 1));
       const int k0 = kbeg + it * GK;
-      g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, m0 + t, m0 + t < g.m, k0, kend, t, avec);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int rl = t + h * 128;
-        if (rl < n_mma)
-          g_load_row<GB_LBO, GB_HALF, NIMG>(sm.b[s], g.b, g.b_row_stride, g.b_k_stride, n0 + rl, n0 + rl < g.n, k0, kend, rl, bvec);
+      if (t < 128) {
+        if (avec) g_load_tile_kcontig<GA_LBO, GA_HALF, NIMG, 128, GM>(sm.a[s], g.a, g.a_row_stride, m0, g.m, GM, k0, kend, t);
+        else g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, m0 + t, m0 + t < g.m, k0, kend, t, false);
+      } else {
+        const int tb = t - 128;
+        if (bvec) g_load_tile_kcontig<GB_LBO, GB_HALF, NIMG, 256, GN>(sm.b[s], g.b, g.b_row_stride, n0, g.n, n_mma, k0, kend, tb);
+        else if (tb < n_mma) g_load_row<GB_LBO, GB_HALF, NIMG>(sm.b[s], g.b, g.b_row_stride, g.b_k_stride, n0 + tb, n0 + tb < g.n, k0, kend, tb, false);
       }
       tc::fence_async_smem();
       tc::mbar_arrive(&sm.full[s]);
     }
-  } else if (warp == 8) {
+  } else if (warp == G_MMA_WARP) {
     // =========================== MMA issuer ===========================
     if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_bf16(GM, n_mma);
@@ -247,7 +293,7 @@ __global__ void __launch_bounds__(G_THREADS, NIMG == 2 ? 2 : 1) gemm_tc_kernel(m
   // ---- teardown
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, 256);
+  if (warp == G_MMA_WARP) tc::tmem_dealloc(tmem, 256);
 }
 
 }  // namespace msacl

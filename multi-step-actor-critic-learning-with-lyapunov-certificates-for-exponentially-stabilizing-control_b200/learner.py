@@ -81,16 +81,17 @@ class MLPWorkspace:
             return
         # wgrad (K = rows, split over CTAs; partials summed by the Adam kernel): dW = dY^T X, db = column sums of dY
         S = self.S = _splits(M)
-        self.gw1, self.gb1 = f(S, HID, Din), f(S, HID)
-        self.gw2, self.gb2 = f(S, HID, HID), f(S, HID)
-        self.gw3, self.gb3 = f(S, Dout, HID), f(S, Dout)
+        Sb = self.Sb = max(1, min(1184, -(-M // 64)))       # bias gradients: many short row blocks (memory-level parallelism)
+        self.gw1, self.gb1 = f(S, HID, Din), f(Sb, HID)
+        self.gw2, self.gb2 = f(S, HID, HID), f(Sb, HID)
+        self.gw3, self.gb3 = f(S, Dout, HID), f(Sb, Dout)
         self.w3 = _desc(0, 1, Dout, self.h2, 1, HID, Dout, HID, M, self.gw3, HID, split_k=S, c_split_stride=Dout * HID)
         self.w2 = _desc(self.da2, 1, HID, self.h1, 1, HID, HID, HID, M, self.gw2, HID, split_k=S, c_split_stride=HID * HID)
         self.w1 = _desc(self.da1, 1, HID, 0, 1, Din, HID, Din, M, self.gw1, Din, split_k=S, c_split_stride=HID * Din)
 
     def grads(self):
         """[(partials tensor, nsplit)] in nn.Module.parameters() order: W1, b1, W2, b2, W3, b3."""
-        return [(self.gw1, self.S), (self.gb1, self.S), (self.gw2, self.S), (self.gb2, self.S), (self.gw3, self.S), (self.gb3, self.S)]
+        return [(self.gw1, self.S), (self.gb1, self.Sb), (self.gw2, self.S), (self.gb2, self.Sb), (self.gw3, self.S), (self.gb3, self.Sb)]
 
 
 class FusedMLP:
@@ -162,9 +163,9 @@ class FusedMLP:
             ws.w3.a = dy.data_ptr()
             ws.w1.b = ws.x.data_ptr()
             l.gemm(ws.w3); l.gemm(ws.w2); l.gemm(ws.w1)
-            _lib.check(lib.msacl_colsum(dy.data_ptr(), ws.rows, self.dout, self.dout, ws.S, ws.gb3.data_ptr(), st))
-            _lib.check(lib.msacl_colsum(ws.da2.data_ptr(), ws.rows, HID, HID, ws.S, ws.gb2.data_ptr(), st))
-            _lib.check(lib.msacl_colsum(ws.da1.data_ptr(), ws.rows, HID, HID, ws.S, ws.gb1.data_ptr(), st))
+            _lib.check(lib.msacl_colsum(dy.data_ptr(), ws.rows, self.dout, self.dout, ws.Sb, ws.gb3.data_ptr(), st))
+            _lib.check(lib.msacl_colsum(ws.da2.data_ptr(), ws.rows, HID, HID, ws.Sb, ws.gb2.data_ptr(), st))
+            _lib.check(lib.msacl_colsum(ws.da1.data_ptr(), ws.rows, HID, HID, ws.Sb, ws.gb1.data_ptr(), st))
         return ws.dx
 
     def reduced_grads(self, ws):
