@@ -307,13 +307,17 @@ int msacl_policy_logits_grad(int64_t rows, int32_t n_step, int32_t obs_dim, int3
  * exp(log_alpha) (entropy - target_entropy); adam_state = device float[2] {exp_avg, exp_avg_sq}; clamp_max = log(alpha_bound) or +inf. */
 int msacl_alpha_update(float* log_alpha, const double* sums, int64_t rows, float target_entropy, float* adam_state,
                        float one_minus_beta1, float beta2, float one_minus_beta2, float step_size, float bc2_sqrt, float eps,
-                       float clamp_max, float* entropy_out, void* stream);
+                       float clamp_max, float* entropy_out, const float* dyn, void* stream);
 /* torch.optim.Adam step (defaults: no weight decay, no amsgrad) over a whole parameter list in one launch.  params / grads /
  * exp_avg / exp_avg_sq: DEVICE pointer tables of length count; grads[t] holds nsplit[t] partial gradients of numel[t]
  * elements each, summed in order.  step_size = lr / (1 - beta1^step), bc2_sqrt = sqrt(1 - beta2^step) (host, float64 -> float32). */
 int msacl_adam_multi(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                      const int64_t* numel, const int32_t* nsplit, int64_t max_numel, float one_minus_beta1, float beta2,
-                     float one_minus_beta2, float step_size, float bc2_sqrt, float eps, void* stream);
+                     float one_minus_beta2, float step_size, float bc2_sqrt, float eps, const float* dyn, void* stream);
+/* Adam bias-correction scalars on the device: *step += 1; dyn[0] = lr / (1 - beta1^step), dyn[1] = sqrt(1 - beta2^step)
+ * (float64 arithmetic, as torch on the host).  msacl_adam_multi / msacl_alpha_update read step_size / bc2_sqrt from `dyn`
+ * (device float[2]) when it is non-NULL, so a captured CUDA graph of the whole update advances correctly on every replay. */
+int msacl_adam_tick(int32_t* step, float* dyn, double lr, double beta1, double beta2, void* stream);
 
 /* Device FP32 FFMA peak probes used by bench.py for the roofline denominator.
  * mode 0: independent FFMA chains with immediate operands (pipe peak);

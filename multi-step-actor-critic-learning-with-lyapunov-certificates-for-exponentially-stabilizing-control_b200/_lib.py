@@ -94,8 +94,9 @@ SIGNATURES = {
     "msacl_sumsq_bwd": (C.c_int, [i64, i32, vp, vp, vp, vp]),
     "msacl_policy_q_route": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "msacl_policy_logits_grad": (C.c_int, [i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, f32, f32, vp, vp, vp]),
-    "msacl_alpha_update": (C.c_int, [vp, vp, i64, f32, vp, f32, f32, f32, f32, f32, f32, f32, vp, vp]),
-    "msacl_adam_multi": (C.c_int, [i32, vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp]),
+    "msacl_alpha_update": (C.c_int, [vp, vp, i64, f32, vp, f32, f32, f32, f32, f32, f32, f32, vp, vp, vp]),
+    "msacl_adam_multi": (C.c_int, [i32, vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, vp]),
+    "msacl_adam_tick": (C.c_int, [vp, vp, C.c_double, C.c_double, C.c_double, vp]),
     "msacl_ffma_probe": (C.c_int, [C.c_int32, C.c_int32, vp, c_f64p, vp]),
     "msacl_umma_probe": (C.c_int, [C.c_int32, C.c_int32, vp, vp]),
 }

@@ -134,6 +134,8 @@ class B200MSACL:
         self.engine_name = learner_engine
         # bf16 products per algorithmic product in the fused learner's GEMMs: 6 = FP32-class (default), 3 = half the tensor work
         self.learner_precision = int(kwargs.get("learner_precision", 6))
+        # replay the whole update as one CUDA graph after a warm-up call (False: launch the ~100 kernels one by one)
+        self.learner_graph = bool(kwargs.get("learner_graph", True))
         self.networks = ApproxContainer(**kwargs).to(self.device)
         self.gamma, self.retrace_lambda, self.lya_eta, self.tau = gamma, retrace_lambda, lya_eta, tau
         self.policy_frequency, self.target_network_frequency = policy_frequency, target_network_frequency
@@ -171,7 +173,7 @@ class B200MSACL:
         nxt = (lambda: next(noise)) if noise is not None else (lambda: None)
         data = {k: v.to(self.device, non_blocking=True) for k, v in data.items()}
         if self.engine_name == "fused":
-            return self._model_update_fused(data, global_iteration, nxt, start)
+            return self._model_update_fused(data, global_iteration, nxt, noise is not None, start)
         loss_q, q1_mean, q2_mean = self._q_update(data, nxt())
         if global_iteration % self.target_network_frequency == 0:
             self._target_update()
@@ -187,18 +189,12 @@ class B200MSACL:
                     TB["alg_time"]: (time.time() - start) * 1000}
         return None
 
-    def _model_update_fused(self, data, global_iteration, nxt, start):
+    def _model_update_fused(self, data, global_iteration, nxt, has_noise, start):
         """Same schedule as above (msacl.py:191-224) on the autograd-free learner; one host read at the end."""
         fl = self._fused_learner()
-        fl.q_update(data, nxt())
-        if global_iteration % self.target_network_frequency == 0:
-            self._target_update()
-        fl.lyapunov_update(data)
-        if global_iteration % self.policy_frequency == 0:
-            for _ in range(self.policy_frequency):
-                fl.policy_update(data, nxt())
-                if self.auto_alpha:
-                    fl.alpha_update()
+        do_policy = global_iteration % self.policy_frequency == 0
+        fl.update(data, global_iteration % self.target_network_frequency == 0, do_policy, noise=nxt if has_noise else None)
+        if do_policy:
             s = fl.read_stats()
             return {"MSACL/entropy-RL iter": s["entropy"], "MSACL/alpha-RL iter": self._get_alpha(),
                     "MSACL/q1_mean-RL iter": s["q1_mean"], "MSACL/q2_mean-RL iter": s["q2_mean"],

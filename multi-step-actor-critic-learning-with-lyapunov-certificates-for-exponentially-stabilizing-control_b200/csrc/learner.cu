@@ -258,8 +258,9 @@ policy_logits_grad_kernel(int64_t rows, int n_step, int D, int A, const float* _
 // sums[1] = sum logp_new over `rows` rows (entropy = -mean); state = {exp_avg, exp_avg_sq}; out[0] = entropy
 __global__ void alpha_update_kernel(float* __restrict__ log_alpha, const double* __restrict__ sums, int64_t rows, float target_entropy,
                                     float* __restrict__ state, float one_m_b1, float b2, float one_m_b2, float step_size,
-                                    float bc2_sqrt, float eps, float clamp_max, float* __restrict__ out) {
+                                    float bc2_sqrt, float eps, float clamp_max, float* __restrict__ out, const float* __restrict__ dyn) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (dyn) { step_size = dyn[0]; bc2_sqrt = dyn[1]; }
   const float entropy = -(float)(sums[1] / (double)rows);
   const float g = expf(log_alpha[0]) * (entropy - target_entropy);
   float m = state[0], v = state[1];
@@ -280,7 +281,8 @@ __global__ void alpha_update_kernel(float* __restrict__ log_alpha, const double*
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(float* const* __restrict__ params, const float* const* __restrict__ grads, float* const* __restrict__ exp_avg,
                   float* const* __restrict__ exp_avg_sq, const int64_t* __restrict__ numel, const int32_t* __restrict__ nsplit,
-                  float one_m_b1, float b2, float one_m_b2, float step_size, float bc2_sqrt, float eps) {
+                  float one_m_b1, float b2, float one_m_b2, float step_size, float bc2_sqrt, float eps, const float* __restrict__ dyn) {
+  if (dyn) { step_size = dyn[0]; bc2_sqrt = dyn[1]; }
   const int t = blockIdx.y;
   const int64_t n = numel[t];
   const int ns = nsplit[t];
@@ -299,6 +301,16 @@ adam_multi_kernel(float* const* __restrict__ params, const float* const* __restr
     const float denom = sqrtf(v) / bc2_sqrt + eps;
     p[i] = p[i] - step_size * (m / denom);
   }
+}
+
+// Bias-correction scalars of an Adam step computed on the device (so that a captured CUDA graph advances them on every
+// replay): step <- step + 1; dyn = {lr / (1 - beta1^step), sqrt(1 - beta2^step)} in float64, as torch does on the host.
+__global__ void adam_tick_kernel(int32_t* __restrict__ step, float* __restrict__ dyn, double lr, double beta1, double beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int32_t s = step[0] + 1;
+  step[0] = s;
+  dyn[0] = (float)(lr / (1.0 - pow(beta1, (double)s)));
+  dyn[1] = (float)sqrt(1.0 - pow(beta2, (double)s));
 }
 
 // sum of split partials into one tensor (tests / gradient inspection)
@@ -409,22 +421,28 @@ int msacl_policy_logits_grad(int64_t rows, int32_t n_step, int32_t obs_dim, int3
 
 int msacl_alpha_update(float* log_alpha, const double* sums, int64_t rows, float target_entropy, float* adam_state,
                        float one_minus_beta1, float beta2, float one_minus_beta2, float step_size, float bc2_sqrt, float eps,
-                       float clamp_max, float* entropy_out, void* stream) {
+                       float clamp_max, float* entropy_out, const float* dyn, void* stream) {
   LCHECK(log_alpha && sums && rows > 0 && adam_state, "alpha_update");
   alpha_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(log_alpha, sums, rows, target_entropy, adam_state, one_minus_beta1, beta2,
-                                                         one_minus_beta2, step_size, bc2_sqrt, eps, clamp_max, entropy_out);
+                                                         one_minus_beta2, step_size, bc2_sqrt, eps, clamp_max, entropy_out, dyn);
   return check_launch("alpha_update");
 }
 
 int msacl_adam_multi(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                      const int64_t* numel, const int32_t* nsplit, int64_t max_numel, float one_minus_beta1, float beta2,
-                     float one_minus_beta2, float step_size, float bc2_sqrt, float eps, void* stream) {
+                     float one_minus_beta2, float step_size, float bc2_sqrt, float eps, const float* dyn, void* stream) {
   LCHECK(count > 0 && params && grads && exp_avg && exp_avg_sq && numel && nsplit && max_numel > 0, "adam_multi");
   int64_t bx = (max_numel + 255) / 256;
   if (bx > 64) bx = 64;
   adam_multi_kernel<<<dim3((unsigned)bx, (unsigned)count), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, numel, nsplit,
-                                                                                        one_minus_beta1, beta2, one_minus_beta2, step_size, bc2_sqrt, eps);
+                                                                                        one_minus_beta1, beta2, one_minus_beta2, step_size, bc2_sqrt, eps, dyn);
   return check_launch("adam_multi");
+}
+
+int msacl_adam_tick(int32_t* step, float* dyn, double lr, double beta1, double beta2, void* stream) {
+  LCHECK(step && dyn, "adam_tick");
+  adam_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step, dyn, lr, beta1, beta2);
+  return check_launch("adam_tick");
 }
 
 int msacl_reduce_splits(const float* parts, int64_t numel, int32_t nsplit, float* out, void* stream) {

@@ -192,6 +192,10 @@ class FusedAdam:
             if not st:
                 optimizer.state[p] = {"step": torch.tensor(0.0), "exp_avg": torch.zeros_like(p.data), "exp_avg_sq": torch.zeros_like(p.data)}
         self.step_count = int(optimizer.state[self.params[0]]["step"])
+        # step counter and bias-correction scalars live on the device (msacl_adam_tick), so a captured CUDA graph of the update
+        # advances them on every replay; `step_count` mirrors the counter on the host
+        self._step_dev = torch.full((1,), self.step_count, dtype=torch.int32, device=dev)
+        self._dyn = torch.zeros(2, dtype=torch.float32, device=dev)
         self._max = max(p.numel() for p in self.params)
         self._grad_key, self._g, self._s = None, None, None
         self._param_key = None
@@ -223,13 +227,20 @@ class FusedAdam:
             self._s = torch.tensor([s for _, s in grads], dtype=torch.int32, device=dev)
             self._keep = [t for t, _ in grads]
             self._grad_key = key
-        self.step_count += 1
         b1, b2 = self.group["betas"]
-        lr, eps = self.group["lr"], self.group["eps"]
-        bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
+        self.captured_lr = lr = self.group["lr"]
+        eps = self.group["eps"]
+        st = _lib.current_stream()
+        _lib.check(self.lib.msacl_adam_tick(self._step_dev.data_ptr(), self._dyn.data_ptr(), lr, b1, b2, st))
         _lib.check(self.lib.msacl_adam_multi(len(self.params), self._p.data_ptr(), self._g.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
-                                             self._n.data_ptr(), self._s.data_ptr(), self._max, 1 - b1, b2, 1 - b2, lr / bc1,
-                                             math.sqrt(bc2), eps, _lib.current_stream()))
+                                             self._n.data_ptr(), self._s.data_ptr(), self._max, 1 - b1, b2, 1 - b2, 0.0, 1.0, eps,
+                                             self._dyn.data_ptr(), st))
+        if not torch.cuda.is_current_stream_capturing():
+            self.count_step()
+
+    def count_step(self):
+        """Host mirror of one executed step (called per launch, or per graph replay)."""
+        self.step_count += 1
         for p in self.params:       # keep the torch optimizer's own step counters in sync (host tensors)
             self.opt.state[p]["step"].fill_(float(self.step_count))
 
@@ -256,6 +267,9 @@ class FusedLearner:
         self.adam_p = FusedAdam(net.policy_optimizer, list(net.policy.parameters()))
         self.alpha_state = torch.zeros(2, dtype=torch.float32, device=dev)
         self.alpha_steps = 0
+        self._alpha_step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._alpha_dyn = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._graphs, self._warm, self._static = {}, set(), {}
         # device statistics: [0:4) critic sums, [4:7) Lyapunov loss parts, [8:11) policy sums
         self.stats = torch.zeros(16, dtype=torch.float64, device=dev)
         self.entropy = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -395,12 +409,74 @@ class FusedLearner:
         alg, net = self.alg, self.alg.networks
         g = net.alpha_optimizer.param_groups[0]
         b1, b2 = g["betas"]
-        self.alpha_steps += 1
-        bc1, bc2 = 1 - b1 ** self.alpha_steps, 1 - b2 ** self.alpha_steps
         clamp = math.log(alg.alpha_bound) if alg.set_alpha_bound else float("inf")
+        _lib.check(self.lib.msacl_adam_tick(self._alpha_step_dev.data_ptr(), self._alpha_dyn.data_ptr(), g["lr"], b1, b2, self._st()))
         _lib.check(self.lib.msacl_alpha_update(net.log_alpha.data.data_ptr(), self.stats[8:].data_ptr(), self._M_p, float(alg.target_entropy),
-                                               self.alpha_state.data_ptr(), 1 - b1, b2, 1 - b2, g["lr"] / bc1, math.sqrt(bc2), g["eps"], clamp,
-                                               self.entropy.data_ptr(), self._st()))
+                                               self.alpha_state.data_ptr(), 1 - b1, b2, 1 - b2, 0.0, 1.0, g["eps"], clamp,
+                                               self.entropy.data_ptr(), self._alpha_dyn.data_ptr(), self._st()))
+        if not torch.cuda.is_current_stream_capturing():
+            self.alpha_steps += 1
+
+    # ---- the whole update as one CUDA graph per schedule variant
+    def _sequence(self, data, do_target, do_policy, eps_list):
+        """msacl.py:191-224 schedule.  eps_list: [q eps, policy eps ...] tensors or Nones (None -> torch.randn)."""
+        alg = self.alg
+        self.q_update(data, eps_list[0])
+        if do_target:
+            alg._target_update()
+        self.lyapunov_update(data)
+        if do_policy:
+            for i in range(alg.policy_frequency):
+                self.policy_update(data, eps_list[1 + i])
+                if alg.auto_alpha:
+                    self.alpha_update()
+
+    def _count_replay(self, do_policy):
+        for a in (self.adam_q1, self.adam_q2, self.adam_l):
+            a.count_step()
+        if do_policy:
+            for _ in range(self.alg.policy_frequency):
+                self.adam_p.count_step()
+                if self.alg.auto_alpha:
+                    self.alpha_steps += 1
+
+    def update(self, data, do_target, do_policy, noise=None):
+        """One model_update.  The first call of a schedule variant (batch shape, target / policy flags, explicit noise or
+        not) runs eagerly (it builds the workspaces and pointer tables), the second is captured into a CUDA graph, later ones
+        replay it: ~100 launches become one graph launch.  Inputs are staged into static buffers; alpha, the Adam step
+        counters and the losses live on the device, so nothing in the graph depends on host state."""
+        alg = self.alg
+        B, n = data["rew"].shape
+        n_eps = 1 + (alg.policy_frequency if do_policy else 0)
+        eps_in = [None] * n_eps
+        if noise is not None:
+            eps_in = [noise() for _ in range(n_eps)]
+        has_noise = eps_in[0] is not None
+        lrs = tuple(a.group["lr"] for a in (self.adam_q1, self.adam_q2, self.adam_l, self.adam_p)) + (alg.networks.alpha_optimizer.param_groups[0]["lr"],)
+        key = (B, n, bool(do_target), bool(do_policy), has_noise, lrs, self.P._key(), self.Q1._key(), self.L._key())
+        if not getattr(alg, "learner_graph", True):
+            return self._sequence(data, do_target, do_policy, eps_in)
+        if key not in self._graphs:
+            if key not in self._warm:                      # first time: eager (allocations, tables, smem attributes)
+                if len(self._warm) > 64:                   # e.g. a trainer that moves the module every iteration: stay eager
+                    self._warm.clear()
+                self._warm.add(key)
+                return self._sequence(data, do_target, do_policy, eps_in)
+            static = {k: torch.empty_like(v, dtype=torch.float32).contiguous() for k, v in data.items()}
+            static_eps = [torch.empty(B, n, self.A, dtype=torch.float32, device=self.dev) if has_noise else None for _ in range(n_eps)]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._sequence(static, do_target, do_policy, static_eps)
+            self._graphs[key] = (g, static, static_eps)
+        g, static, static_eps = self._graphs[key]
+        for k, v in static.items():
+            v.copy_(data[k])
+        if has_noise:
+            for dst, src in zip(static_eps, eps_in):
+                dst.copy_(src.reshape(dst.shape))
+        g.replay()
+        self._count_replay(do_policy)
 
     def read_stats(self):
         """One device -> host read: the scalars of the reference's tb_info dict."""
