@@ -136,6 +136,8 @@ class B200MSACL:
         self.learner_precision = int(kwargs.get("learner_precision", 6))
         # replay the whole update as one CUDA graph after a warm-up call (False: launch the ~100 kernels one by one)
         self.learner_graph = bool(kwargs.get("learner_graph", True))
+        # run independent network evaluations of one update on forked side streams (parallel graph branches)
+        self.learner_streams = bool(kwargs.get("learner_streams", True))
         self.networks = ApproxContainer(**kwargs).to(self.device)
         self.gamma, self.retrace_lambda, self.lya_eta, self.tau = gamma, retrace_lambda, lya_eta, tau
         self.policy_frequency, self.target_network_frequency = policy_frequency, target_network_frequency

@@ -22,20 +22,18 @@
 
 namespace msacl {
 
-constexpr int GM = 128, GN = 256, GK = 32;
-constexpr int G_STAGES = 2;
-constexpr int GA_HALF = GM * GK * 2;       // 8 KB: hi (or lo) image of an A stage
-constexpr int GB_HALF = GN * GK * 2;       // 16 KB
-constexpr int GA_LBO = GM * 16, GB_LBO = GN * 16, G_SBO = 128;
+constexpr int GM = 128, GN = 256, GK = 32;  // GN = widest column tile (template BN: 256, or 64 for small row counts)
+constexpr int GA_HALF = GM * GK * 2;       // 8 KB: one bf16 image of an A stage
+constexpr int GA_LBO = GM * 16, G_SBO = 128;
 constexpr int G_LOADERS = 384;             // 12 loader warps: threads 0..127 own the A tile, 128..383 the B tile
 constexpr int G_MMA_WARP = 4 + G_LOADERS / 32;
 constexpr int G_THREADS = 32 * (G_MMA_WARP + 1);   // warps 0-3 epilogue (TMEM lane quadrant = warp), 4-15 loaders, 16 MMA issuer
 
-template <int NIMG>
+template <int NIMG, int BN, int STAGES>
 struct GemmSmem {
-  alignas(128) unsigned char a[G_STAGES][NIMG * GA_HALF];
-  alignas(128) unsigned char b[G_STAGES][NIMG * GB_HALF];
-  unsigned long long full[G_STAGES], empty[G_STAGES], accfull;
+  alignas(128) unsigned char a[STAGES][NIMG * GA_HALF];
+  alignas(128) unsigned char b[STAGES][NIMG * BN * GK * 2];
+  unsigned long long full[STAGES], empty[STAGES], accfull;
   uint32_t tmem_slot;
 };
 
@@ -136,10 +134,16 @@ __device__ __forceinline__ void g_load_row(unsigned char* img0, const float* __r
   }
 }
 
-template <int NIMG>
-__global__ void __launch_bounds__(G_THREADS, NIMG == 2 ? 2 : 1) gemm_tc_kernel(msacl_gemm_t g) {
+// BN = column tile (UMMA N <= BN), STAGES = shared-memory stages.  <*, 256, 2>: large row counts (one column tile covers a
+// 256-wide layer); <*, 64, 4>: small row counts -- 4x more CTAs and a deeper prefetch, so a GEMM over a few thousand rows
+// (the reference's replay batch: 256 windows x 20 steps) is not serialised behind one tile's load latency.
+template <int NIMG, int BN, int STAGES>
+__global__ void __launch_bounds__(G_THREADS, (NIMG == 2 && BN == 256) ? 2 : 1) gemm_tc_kernel(msacl_gemm_t g) {
+  constexpr int G_STAGES = STAGES;
+  constexpr int GN = BN, GB_HALF = BN * GK * 2, GB_LBO = BN * 16;
+  constexpr uint32_t TMEM_COLS = BN >= 256 ? 256 : (BN >= 128 ? 128 : 64);
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  GemmSmem<NIMG>& sm = *reinterpret_cast<GemmSmem<NIMG>*>(smem_raw);
+  GemmSmem<NIMG, BN, STAGES>& sm = *reinterpret_cast<GemmSmem<NIMG, BN, STAGES>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
   // K range of this split (multiples of the stage width)
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(G_THREADS, NIMG == 2 ? 2 : 1) gemm_tc_kernel(m
     tc::mbar_init(&sm.accfull, 1);
     tc::mbar_fence_init();
   }
-  if (warp == G_MMA_WARP) tc::tmem_alloc(&sm.tmem_slot, 256);
+  if (warp == G_MMA_WARP) tc::tmem_alloc(&sm.tmem_slot, TMEM_COLS);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(G_THREADS, NIMG == 2 ? 2 : 1) gemm_tc_kernel(m
         else g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, m0 + t, m0 + t < g.m, k0, kend, t, false);
       } else {
         const int tb = t - 128;
-        if (bvec) g_load_tile_kcontig<GB_LBO, GB_HALF, NIMG, 256, GN>(sm.b[s], g.b, g.b_row_stride, n0, g.n, n_mma, k0, kend, tb);
+        if (bvec) g_load_tile_kcontig<GB_LBO, GB_HALF, NIMG, 256, (GN >= 32 ? GN : 32)>(sm.b[s], g.b, g.b_row_stride, n0, g.n, n_mma, k0, kend, tb);
         else if (tb < n_mma) g_load_row<GB_LBO, GB_HALF, NIMG>(sm.b[s], g.b, g.b_row_stride, g.b_k_stride, n0 + tb, n0 + tb < g.n, k0, kend, tb, false);
       }
       tc::fence_async_smem();
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(G_THREADS, NIMG == 2 ? 2 : 1) gemm_tc_kernel(m
   // ---- teardown
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == G_MMA_WARP) tc::tmem_dealloc(tmem, 256);
+  if (warp == G_MMA_WARP) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace msacl
@@ -315,15 +319,40 @@ extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
   }
   if (g->row_sumsq && g->n > GN) { set_error("gemm_tc: row_sumsq needs n <= 256 (one column tile)"); return MSACL_ERR_BAD_ARG; }
   if (g->precision != 0 && g->precision != 3 && g->precision != 6) { set_error("gemm_tc: precision must be 6 (default, bf16x6) or 3 (bf16x3)"); return MSACL_ERR_BAD_ARG; }
-  const dim3 grid((unsigned)((g->m + GM - 1) / GM), (unsigned)((g->n + GN - 1) / GN), (unsigned)g->split_k);
+  // Column tile.  Large problems (>= one CTA per SM from the row tiles alone): 256, the A tile is converted once per 256 output
+  // columns.  Small problems are bound by the latency of ONE CTA (its K stages run back to back), so the tile that gives the
+  // fewest waves over the 148 SMs wins, and among those the narrowest (most CTAs in flight).
+  const int64_t mt = (g->m + GM - 1) / GM;
+  int bn = 256;
+  if (!g->row_sumsq && mt * g->split_k < kNumSMs) {
+    int64_t best_waves = -1;
+    for (int cand : {64, 128, 256}) {
+      if (cand > 64 && g->n <= cand / 2) continue;
+      const int64_t ctas = mt * ((g->n + cand - 1) / cand) * g->split_k;
+      const int64_t waves = (ctas + kNumSMs - 1) / kNumSMs;
+      if (best_waves < 0 || waves < best_waves) { best_waves = waves; bn = cand; }
+    }
+  }
+  const dim3 grid((unsigned)mt, (unsigned)((g->n + bn - 1) / bn), (unsigned)g->split_k);
   static bool attr_set = false;
+  auto set_attr = [&](auto kern, size_t bytes) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+  };
+#define MSACL_GEMM_VARIANTS(X) X(2, 256, 2) X(3, 256, 2) X(2, 128, 3) X(3, 128, 3) X(2, 64, 4) X(3, 64, 4)
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem<2>) + 128);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem<3>) + 128);
-    if (e != cudaSuccess) { set_error("gemm_tc: smem attr: %s", cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
+    bool ok = true;
+#define X(NI, BN_, ST) ok = ok && set_attr(gemm_tc_kernel<NI, BN_, ST>, sizeof(GemmSmem<NI, BN_, ST>) + 128);
+    MSACL_GEMM_VARIANTS(X)
+#undef X
+    if (!ok) { set_error("gemm_tc: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"); return MSACL_ERR_CUDA; }
     attr_set = true;
   }
-  if (g->precision == 3) gemm_tc_kernel<2><<<grid, G_THREADS, sizeof(GemmSmem<2>) + 128, (cudaStream_t)stream>>>(*g);
-  else gemm_tc_kernel<3><<<grid, G_THREADS, sizeof(GemmSmem<3>) + 128, (cudaStream_t)stream>>>(*g);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nimg = g->precision == 3 ? 2 : 3;
+#define X(NI, BN_, ST) \
+  if (nimg == NI && bn == BN_) gemm_tc_kernel<NI, BN_, ST><<<grid, G_THREADS, sizeof(GemmSmem<NI, BN_, ST>) + 128, st>>>(*g);
+  MSACL_GEMM_VARIANTS(X)
+#undef X
+#undef MSACL_GEMM_VARIANTS
   return check_launch("gemm_tc");
 }

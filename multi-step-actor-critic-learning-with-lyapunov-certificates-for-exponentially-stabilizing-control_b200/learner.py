@@ -30,7 +30,7 @@ HID = 256
 
 
 def _splits(rows):
-    return max(1, min(74, -(-int(rows) // 512)))
+    return max(1, min(74, -(-int(rows) // 256)))
 
 
 class _Launcher:
@@ -270,6 +270,7 @@ class FusedLearner:
         self._alpha_step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._alpha_dyn = torch.zeros(2, dtype=torch.float32, device=dev)
         self._graphs, self._warm, self._static = {}, set(), {}
+        self._side = [torch.cuda.Stream(dev) for _ in range(2)] if getattr(alg, "learner_streams", True) else []
         # device statistics: [0:4) critic sums, [4:7) Lyapunov loss parts, [8:11) policy sums
         self.stats = torch.zeros(16, dtype=torch.float64, device=dev)
         self.entropy = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -293,6 +294,30 @@ class FusedLearner:
 
     def _st(self):
         return _lib.current_stream()
+
+    def _par(self, *fns):
+        """Run independent launch sequences concurrently: fns[0] on the current stream, the others on side streams forked
+        from / joined back into it with events (under CUDA-graph capture these become parallel branches of the graph).  A GEMM
+        over a few thousand rows fills 40-80 of the 148 SMs, so two or three of them overlap almost perfectly."""
+        if not self._side or len(fns) == 1:
+            for fn in fns:
+                fn()
+            return
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        joins = []
+        for i, fn in enumerate(fns[1:]):
+            side = self._side[i % len(self._side)]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                fn()
+                ev = torch.cuda.Event()
+                ev.record(side)
+            joins.append(ev)
+        fns[0]()
+        for ev in joins:
+            cur.wait_event(ev)
 
     def _concat(self, a, b, name):
         rows = a.shape[0]
@@ -325,12 +350,19 @@ class FusedLearner:
         lib, st = self.lib, self._st()
         xq = self._concat(f["obs"], f["act"], "xq")
         w1, w2 = self.Q1.workspace("q", M, train=True), self.Q2.workspace("q", M, train=True)
-        q1, q2 = self.Q1.forward(xq, w1), self.Q2.forward(xq, w2)
-        logits2 = self.P.forward(f["obs2"], self.P.workspace("nograd", M))
-        next_act, next_logp = self._rsample(logits2, self._eps(eps, M), "next")
-        xq2 = self._concat(f["obs2"], next_act, "xq2")
-        tq1 = self.Q1t.forward(xq2, self.Q1t.workspace("t", M))
-        tq2 = self.Q2t.forward(xq2, self.Q2t.workspace("t", M))
+        wpn, wt1, wt2 = self.P.workspace("nograd", M), self.Q1t.workspace("t", M), self.Q2t.workspace("t", M)
+        eps = self._eps(eps, M)
+        r = {}
+
+        def next_action():
+            logits2 = self.P.forward(f["obs2"], wpn)
+            r["next_act"], r["next_logp"] = self._rsample(logits2, eps, "next")
+            r["xq2"] = self._concat(f["obs2"], r["next_act"], "xq2")
+
+        self._par(next_action, lambda: self.Q1.forward(xq, w1), lambda: self.Q2.forward(xq, w2))
+        q1, q2, next_logp, xq2 = w1.y, w2.y, r["next_logp"], r["xq2"]
+        self._par(lambda: self.Q1t.forward(xq2, wt1), lambda: self.Q2t.forward(xq2, wt2))
+        tq1, tq2 = wt1.y, wt2.y
         backup = self._tmp("backup", M)
         _lib.check(lib.msacl_q_backup_dev_alpha(M, f["rew"].data_ptr(), f["done"].data_ptr(), tq1.data_ptr(), tq2.data_ptr(),
                                                 next_logp.data_ptr(), float(self.alg.gamma), self.alg.networks.log_alpha.data_ptr(),
@@ -338,10 +370,11 @@ class FusedLearner:
         dq1, dq2 = self._tmp("dq1", M), self._tmp("dq2", M)
         _lib.check(lib.msacl_q_loss_grad(M, q1.data_ptr(), q2.data_ptr(), backup.data_ptr(), dq1.data_ptr(), dq2.data_ptr(),
                                          self.stats.data_ptr(), st))
-        self.Q1.backward(w1, dq1)
-        self.Q2.backward(w2, dq2)
-        self.adam_q1.step(w1.grads())
-        self.adam_q2.step(w2.grads())
+        def upd(Q, w, dq, adam):
+            Q.backward(w, dq)
+            adam.step(w.grads())
+
+        self._par(lambda: upd(self.Q1, w1, dq1, self.adam_q1), lambda: upd(self.Q2, w2, dq2, self.adam_q2))
         self._M_q = M
 
     # ---- msacl.py:265-336
@@ -350,15 +383,22 @@ class FusedLearner:
         M = B * n
         f = self._flat(d, B, n)
         lib, st, alg = self.lib, self._st(), self.alg
-        logits = self.P.forward(f["obs"], self.P.workspace("nograd", M))
         logp = self._tmp("lya_logp", M)
-        _lib.check(lib.msacl_tanh_gauss_log_prob(M, self.A, logits.data_ptr(), f["act"].data_ptr(), self.lo.data_ptr(), self.hi.data_ptr(),
-                                                 self.min_ls, self.max_ls, logp.data_ptr(), st))
+        wpn = self.P.workspace("nograd", M)
         xl = self._tmp("xl", 2 * M, self.D)
-        xl[:M].copy_(f["obs"]); xl[M:].copy_(f["obs2"])
         ws = self.L.workspace("train", 2 * M, train=True, sumsq=True)
-        z = self.L.forward(xl, ws)            # one forward of V over [obs; obs2] (the reference's second V(obs) is identical)
-        V = ws.v
+
+        def new_logp():
+            logits = self.P.forward(f["obs"], wpn)
+            _lib.check(lib.msacl_tanh_gauss_log_prob(M, self.A, logits.data_ptr(), f["act"].data_ptr(), self.lo.data_ptr(), self.hi.data_ptr(),
+                                                     self.min_ls, self.max_ls, logp.data_ptr(), self._st()))
+
+        def lya_forward():                    # one forward of V over [obs; obs2] (the reference's second V(obs) is identical)
+            xl[:M].copy_(f["obs"]); xl[M:].copy_(f["obs2"])
+            self.L.forward(xl, ws)
+
+        self._par(lya_forward, new_logp)
+        z, V = ws.y, ws.v
         dV = self._tmp("dV", 2 * M)
         c = alg.coef
         _lib.check(lib.msacl_lyapunov_risk(B, n, self.D, f["obs"].data_ptr(), f["obs2"].data_ptr(), logp.data_ptr(), f["logp"].data_ptr(),
@@ -384,18 +424,22 @@ class FusedLearner:
         new_act, new_logp = self._rsample(logits, eps, "new")
         xq = self._concat(f["obs"], new_act, "xqn")
         w1, w2 = self.Q1.workspace("dx", M, need_dx=True), self.Q2.workspace("dx", M, need_dx=True)
-        q1, q2 = self.Q1.forward(xq, w1), self.Q2.forward(xq, w2)
+        xl = self._tmp("xlp", B + M, self.D)
+        wl = self.L.workspace("nograd", B + M, sumsq=True)
+        r = {}
+
+        def advantage():      # stability advantage from V(obs_0) and V(obs2) (no gradient): one forward over [obs[:, 0]; obs2]
+            xl[:B].copy_(d["obs"][:, 0].reshape(B, self.D)); xl[B:].copy_(f["obs2"])
+            self.L.forward(xl, wl)
+            _, r["adv"] = tg.stability_advantage(wl.v[:B], wl.v[B:].view(B, n), alg.coef)
+
+        self._par(advantage, lambda: self.Q1.forward(xq, w1), lambda: self.Q2.forward(xq, w2))      # torch allocations stay on the main stream
+        q1, q2, adv = w1.y, w2.y, r["adv"]
         dq1, dq2 = self._tmp("pdq1", M), self._tmp("pdq2", M)
         _lib.check(lib.msacl_policy_q_route(M, q1.data_ptr(), q2.data_ptr(), new_logp.data_ptr(), la.data_ptr(), dq1.data_ptr(),
                                             dq2.data_ptr(), self.stats[8:].data_ptr(), st))
-        dx1 = self.Q1.backward(w1, dq1, wgrad=False, need_dx=True)
-        dx2 = self.Q2.backward(w2, dq2, wgrad=False, need_dx=True)
-        # stability advantage from V(obs_0) and V(obs2) (no gradient): one forward over [obs[:, 0]; obs2]
-        xl = self._tmp("xlp", B + M, self.D)
-        xl[:B].copy_(d["obs"][:, 0].reshape(B, self.D)); xl[B:].copy_(f["obs2"])
-        wl = self.L.workspace("nograd", B + M, sumsq=True)
-        self.L.forward(xl, wl)
-        _, adv = tg.stability_advantage(wl.v[:B], wl.v[B:].view(B, n), alg.coef)
+        self._par(lambda: self.Q1.backward(w1, dq1, wgrad=False, need_dx=True), lambda: self.Q2.backward(w2, dq2, wgrad=False, need_dx=True))
+        dx1, dx2 = w1.dx, w2.dx
         dlogits = self._tmp("dlogits", M, 2 * self.A)
         _lib.check(lib.msacl_policy_logits_grad(M, n, self.D, self.A, logits.data_ptr(), eps.data_ptr(), dx1.data_ptr(), dx2.data_ptr(),
                                                 la.data_ptr(), f["act"].data_ptr(), f["logp"].data_ptr(), adv.data_ptr(), float(alg.clip_coef),
