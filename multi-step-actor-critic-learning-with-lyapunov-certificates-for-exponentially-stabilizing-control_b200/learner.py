@@ -510,8 +510,18 @@ class FusedLearner:
             static_eps = [torch.empty(B, n, self.A, dtype=torch.float32, device=self.dev) if has_noise else None for _ in range(n_eps)]
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._sequence(static, do_target, do_policy, static_eps)
+            # no garbage collection while capturing: collecting an older learner's CUDAGraph objects (reference cycles
+            # alg <-> learner) would call cudaGraphExecDestroy mid-capture and invalidate it
+            import gc
+            gc.collect()
+            was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g):
+                    self._sequence(static, do_target, do_policy, static_eps)
+            finally:
+                if was_enabled:
+                    gc.enable()
             self._graphs[key] = (g, static, static_eps)
         g, static, static_eps = self._graphs[key]
         for k, v in static.items():
