@@ -522,6 +522,7 @@ def main():
                     help="also time a variant that copies EVERY transition of the chunk to pinned host memory")
     ap.add_argument("--engine", default="tc", choices=["tc", "ffma"],
                     help="actor engine: tcgen05 split-bf16 tensor cores (default) or FP32 FFMA")
+    ap.add_argument("--reserve-sms", type=int, default=2, help="N>1 e2e: SMs left free for the side-stream NCCL all-gather")
     ap.add_argument("--replay", default="indexed", choices=["indexed", "ring"],
                     help="e2e replay store: index-based windows over the transition store (default) or the reference-layout ring")
     args = ap.parse_args()
@@ -609,7 +610,7 @@ def main():
     # One packed buffer per rank carries the 7 batch fields + the statistics: the gather kernel writes the sampled windows
     # straight into it, N>1 all-gathers it on a side stream (consumed one step later), and ONE contiguous D2H copy brings
     # the [G, P] result into pinned host memory, where the learner-facing {field: [B, n, .]} dict is a set of views.
-    exch = mdist.BatchExchange(fields, Bq, n_step, dev)
+    exch = mdist.BatchExchange(fields, Bq, n_step, dev, depth=2 if world > 1 else 1)   # 2: a rank's step never waits for a straggler's
     host_packed = [torch.empty(world, exch.P, dtype=torch.float32).pin_memory() for _ in range(2)]
     host_ready = [None, None]
     d2h_bytes = host_packed[0].numel() * 4
@@ -636,6 +637,10 @@ def main():
             consumed[0] += float(hs[0]) + float(hb["rew"][0, 0])       # touch the data like a consumer would
         step_no[0] += 1
 
+    if world > 1 and args.engine == "tc":
+        # the side-stream all-gather needs an SM while the persistent rollout kernel runs: reserve NCCL's CTAs instead of
+        # letting them displace rollout CTAs (which stretched every launch by the collective's cross-rank wait: 0.6 ms)
+        ro.reserve_sms(args.reserve_sms)
     for _ in range(args.warmup):
         e2e_step()
     barrier()
@@ -646,6 +651,7 @@ def main():
     host_ready[(step_no[0] - 1) & 1].synchronize()       # the last step's batch has reached the host inside the timed region
     e1.record(stream)
     barrier()
+    ro.reserve_sms(0)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = steps_total / (e2e_ms * 1e-3)
     windows_kept = int(buf.size)

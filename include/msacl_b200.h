@@ -140,6 +140,11 @@ int msacl_rollout_fused(const msacl_env_state_t* st, const msacl_actor_t* actor,
  * relative (tolerances in tests/test_gpu_tc.py).  w1p / w2p are the operand images produced by
  * msacl_tc_pack_actor (sizes from msacl_tc_pack_bytes); repack after every weight update. */
 int msacl_tc_pack_bytes(int64_t* w1p_bytes, int64_t* w2p_bytes);
+/* Process-wide grid cap of the persistent tensor-core rollout kernel: 0 (default) = one CTA per SM (148); a smaller value
+ * leaves SMs free for a kernel that must run CONCURRENTLY with a rollout launch -- e.g. the NCCL all-gather of the replay
+ * sub-batches on a side stream, whose CTAs would otherwise displace rollout CTAs and stretch the launch by the collective's
+ * cross-rank wait.  Host call, takes effect at the next launch. */
+int msacl_rollout_tc_set_max_ctas(int32_t max_ctas);
 int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, void* w1p, void* w2p, void* stream);
 int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_actor_t* actor, const void* w1p, const void* w2p,
                            int32_t K, uint32_t step_base, int32_t n_step, float reward_scale, float cost_scale,

@@ -634,6 +634,14 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
 
 using namespace msacl;
 
+static int g_tc_max_ctas = 0;      // 0 = one persistent CTA per SM
+
+extern "C" int msacl_rollout_tc_set_max_ctas(int32_t max_ctas) {
+  if (max_ctas < 0 || max_ctas > kNumSMs) { set_error("rollout_tc_set_max_ctas: expected 0 (all SMs) .. %d", kNumSMs); return MSACL_ERR_BAD_ARG; }
+  g_tc_max_ctas = max_ctas;
+  return MSACL_OK;
+}
+
 extern "C" int msacl_tc_pack_bytes(int64_t* w1p_bytes, int64_t* w2p_bytes) {
   if (w1p_bytes) *w1p_bytes = W1P_BYTES;
   if (w2p_bytes) *w2p_bytes = W2P_BYTES;
@@ -662,7 +670,8 @@ extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_a
     constexpr int NS = MSACL_TC_NS(ID);      // tile slots in flight
     static_assert(sizeof(TcSmem<ID, NS>) + 128 <= 232448, "shared-memory layout exceeds the 227 KB per-CTA limit");
     const int64_t groups = (tiles + NS - 1) / NS;
-    const unsigned grid = (unsigned)(groups < kNumSMs ? groups : kNumSMs);
+    const int64_t cap = g_tc_max_ctas > 0 ? g_tc_max_ctas : kNumSMs;
+    const unsigned grid = (unsigned)(groups < cap ? groups : cap);
     const size_t smem = sizeof(TcSmem<ID, NS>) + 128;
     auto kern = rollout_tc_kernel<ID, NS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -70,12 +70,13 @@ class BatchExchange:
     One preallocated packed float32 buffer per rank holds the 7 batch fields ([B/G, n, .] each; `views()` hands them out
     so that the buffer's gather kernel writes the sampled windows straight into it -- no torch.cat) followed by the [8]
     float64 statistics bit-cast to 16 floats.  `exchange()` issues ONE all-gather of that buffer on a side stream and
-    returns the PREVIOUS call's gathered result: the learner's batch is one iteration stale (as it already is in the
+    returns the result of the call `depth` calls earlier (default 1: the PREVIOUS call): the learner's batch is one iteration stale (as it already is in the
     reference loop, where the batch is drawn before the current chunk's windows matter), so the collective's latency hides
     behind the next rollout launch instead of blocking it.  Buffers are double-buffered; the first call returns its own
     result.  On CPU tensors (gloo tests) the same protocol runs synchronously."""
 
-    def __init__(self, fields, sub_batch, n_step, device, group=None):
+    def __init__(self, fields, sub_batch, n_step, device, group=None, depth=1):
+        self.depth = max(1, int(depth))      # calls between issuing a gather and consuming it (1: next call; 2 absorbs rank skew)
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.group, self.device = group, torch.device(device)
         self.keys = sorted(fields)
@@ -88,15 +89,16 @@ class BatchExchange:
             self.offsets[k] = (off, numel)
             off += (numel + 3) // 4 * 4                 # keep every field 16-byte aligned
         self.stats_off, self.P = off, off + 16
-        self.send = [torch.zeros(self.P, dtype=torch.float32, device=self.device) for _ in range(2)]
-        self.recv = [torch.zeros(self.world, self.P, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.nbuf = self.depth + 1
+        self.send = [torch.zeros(self.P, dtype=torch.float32, device=self.device) for _ in range(self.nbuf)]
+        self.recv = [torch.zeros(self.world, self.P, dtype=torch.float32, device=self.device) for _ in range(self.nbuf)]
         self.side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
-        self.done = [None, None]
+        self.done = [None] * self.nbuf
         self.t = 0
 
     def views(self):
         """{field: [B/G, n, .]} views of the CURRENT send buffer: pass as `out=` to buffer.sample_batch."""
-        buf = self.send[self.t & 1]
+        buf = self.send[self.t % self.nbuf]
         return {k: buf[o:o + m].view(self.shapes[k]) for k, (o, m) in self.offsets.items()}
 
     def _unpack(self, recv):
@@ -111,7 +113,7 @@ class BatchExchange:
         """sub_batch: `views()` already filled by the gather kernel, or any {field: tensor} (copied in).  Returns the
         previous call's (global batch {field: [B, n, .]}, rank-summed statistics [8] float64) -- with unpack=False the raw
         gathered [G, P] buffer instead (one contiguous D2H copy; unpack on the host with `host_views`)."""
-        cur = self.t & 1
+        cur = self.t % self.nbuf
         mine = self.views()
         for k in self.keys:
             if sub_batch[k].data_ptr() != mine[k].data_ptr():
@@ -130,7 +132,7 @@ class BatchExchange:
                 ev = torch.cuda.Event()
                 ev.record()
             self.done[cur] = ev
-        take = cur if self.t == 0 else 1 - cur
+        take = (self.t - min(self.t, self.depth)) % self.nbuf      # the first `depth` calls return the oldest result there is
         if self.side is not None and self.done[take] is not None:
             torch.cuda.current_stream().wait_event(self.done[take])
         self.t += 1

@@ -215,6 +215,12 @@ class FusedRollout:
         self.stats = torch.zeros(32, dtype=torch.float64, device=self.state.device)   # [0:8) documented, rest diagnostic
         self.global_step = 0
 
+    @staticmethod
+    def reserve_sms(count):
+        """Leave `count` SMs free for kernels that run concurrently with the (persistent, one CTA per SM) tensor-core rollout
+        kernel, e.g. a side-stream NCCL collective.  0 restores the full grid."""
+        _lib.check(_lib.load().msacl_rollout_tc_set_max_ctas(0 if count <= 0 else 148 - int(count)))
+
     def run(self, actor: ActorWeights, eps=None, deterministic=False, write=True, engine=None, timing=None):
         """One K-step chunk.  eps: optional CUDA float32 [K, n, act_dim] explicit N(0,1) draws.
         engine: "ffma" (FP32 FFMA actor) or "tc" (tcgen05 split-bf16 actor); default self.engine.
