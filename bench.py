@@ -296,7 +296,7 @@ def make_policy(torch, D, A):
                                torch.nn.Linear(256, 2 * A))
 
 
-def time_rollout(cx, env, n, K, engine, steps, warmup, keep=False, clocks=False):
+def time_rollout(cx, env, n, K, engine, steps, warmup, keep=False, clocks=False, settle_s=0.0):
     """Device-resident throughput of the fused rollout: `steps` launches of K env steps over n envs per rank.
     Returns dict(value, total_ms, kern_ms [, ro, actor])."""
     torch, dist = cx.torch, cx.dist
@@ -311,6 +311,26 @@ def time_rollout(cx, env, n, K, engine, steps, warmup, keep=False, clocks=False)
     ro.state.reset()
     for _ in range(warmup):
         ro.run(actor)
+    burst = None
+    if settle_s > 0:
+        # (1) burst figure: the K launches right after the W warm-up launches, as round 1 measured it
+        cx.barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(cx.stream)
+        for _ in range(steps):
+            ro.run(actor)
+        b1.record(cx.stream)
+        cx.barrier()
+        burst = n * K * steps * cx.world / (cx.max_over_ranks(b0.elapsed_time(b1)) * 1e-3)
+        # (2) untimed settling launches: the part runs at its 1 kW power cap (sw_power_cap) and the SM clock of a cool GPU
+        # sags by 3-5 % over the first second of back-to-back launches.  `value` and `e2e` are both taken after the clocks
+        # have settled, so that they are comparable with each other (a burst `value` next to a settled `e2e` made the e2e
+        # path look 4 % slower than it is) and with the SUSTAINED tensor peak.
+        t_s = time.perf_counter()
+        while time.perf_counter() - t_s < settle_s:
+            for _ in range(4):
+                ro.run(actor)
+            torch.cuda.synchronize()
     cx.barrier()
     cs = None
     if clocks:
@@ -326,7 +346,8 @@ def time_rollout(cx, env, n, K, engine, steps, warmup, keep=False, clocks=False)
     clk = cs.stop() if cs else None
     total_ms = cx.max_over_ranks(t0.elapsed_time(t1))
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    out = {"value": n * K * steps * cx.world / (total_ms * 1e-3), "total_ms": total_ms, "kern_ms": kern_ms, "clocks": clk}
+    out = {"value": n * K * steps * cx.world / (total_ms * 1e-3), "total_ms": total_ms, "kern_ms": kern_ms, "clocks": clk,
+           "value_burst": burst}
     if keep:
         out.update(ro=ro, actor=actor, host_w=[p.detach().clone().pin_memory() for p in pol.parameters()])
     else:
@@ -522,7 +543,14 @@ def main():
                     help="also time a variant that copies EVERY transition of the chunk to pinned host memory")
     ap.add_argument("--engine", default="tc", choices=["tc", "ffma"],
                     help="actor engine: tcgen05 split-bf16 tensor cores (default) or FP32 FFMA")
-    ap.add_argument("--reserve-sms", type=int, default=2, help="N>1 e2e: SMs left free for the side-stream NCCL all-gather")
+    ap.add_argument("--settle", type=float, default=0.0,
+                    help="seconds of untimed back-to-back launches before the timed `value` region (sustained-clock figure; the burst "
+                         "figure is then reported as value_burst)")
+    ap.add_argument("--cooldown", type=float, default=2.0,
+                    help="idle seconds before the e2e region, so that it starts from the same thermal state as the `value` region")
+    ap.add_argument("--exchange", default="side", choices=["side", "main", "none"],
+                    help="N>1 e2e diagnosis: all-gather on a side stream (default), on the main stream, or skipped")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="N>1 e2e: SMs left free for the side-stream NCCL all-gather")
     ap.add_argument("--replay", default="indexed", choices=["indexed", "ring"],
                     help="e2e replay store: index-based windows over the transition store (default) or the reference-layout ring")
     args = ap.parse_args()
@@ -587,9 +615,10 @@ def main():
     D, A = spec.obs_dim, spec.act_dim
 
     # ---------------- device-resident throughput (`value`) + dominant-kernel timing
-    main_run = time_rollout(cx, args.env, n, K, args.engine, args.steps, args.warmup, keep=True, clocks=True)
+    main_run = time_rollout(cx, args.env, n, K, args.engine, args.steps, args.warmup, keep=True, clocks=True, settle_s=args.settle)
     ro, host_w = main_run["ro"], main_run["host_w"]
     value, total_ms, kern_ms, clk = main_run["value"], main_run["total_ms"], main_run["kern_ms"], main_run["clocks"]
+    main_run_burst = main_run["value_burst"]
     steps_total = n * K * args.steps * world
     h2d_bytes = sum(p.numel() * 4 for p in host_w)
 
@@ -611,19 +640,28 @@ def main():
     # straight into it, N>1 all-gathers it on a side stream (consumed one step later), and ONE contiguous D2H copy brings
     # the [G, P] result into pinned host memory, where the learner-facing {field: [B, n, .]} dict is a set of views.
     exch = mdist.BatchExchange(fields, Bq, n_step, dev, depth=2 if world > 1 else 1)   # 2: a rank's step never waits for a straggler's
+    if args.exchange == "main":
+        exch.side = None
     host_packed = [torch.empty(world, exch.P, dtype=torch.float32).pin_memory() for _ in range(2)]
     host_ready = [None, None]
     d2h_bytes = host_packed[0].numel() * 4
     step_no = [0]
     consumed = [0.0]
+    e2e_kernel_events = []
 
     def e2e_step():
         cur = step_no[0] & 1
         a = upload_actor()                               # H2D: the learner's current policy (pinned host memory)
-        batch = ro.run(a)                                # fused K-step rollout
+        kev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        e2e_kernel_events.append(kev)
+        batch = ro.run(a, timing=kev)                    # fused K-step rollout
         buf.add_batch(batch)                             # n-step windows -> device replay store
         sub = buf.sample_batch(Bq, out=exch.views())     # replay batch for the learner, gathered into the packed buffer
-        packed = exch.exchange(sub, ro.stats[:8], unpack=False)   # N>1: NCCL all-gather on a side stream, previous result back
+        if args.exchange == "none" and world > 1:
+            exch.send[0][exch.stats_off:].view(torch.float64).copy_(ro.stats[:8])
+            packed = exch.send[0][None].expand(world, -1)
+        else:
+            packed = exch.exchange(sub, ro.stats[:8], unpack=False)   # N>1: NCCL all-gather on a side stream, previous result back
         host_packed[cur].copy_(packed, non_blocking=True)         # D2H: the replay batch + episode statistics
         ev = torch.cuda.Event()
         ev.record(stream)
@@ -637,6 +675,11 @@ def main():
             consumed[0] += float(hs[0]) + float(hb["rew"][0, 0])       # touch the data like a consumer would
         step_no[0] += 1
 
+    # Same thermal state for both timed regions: the part runs at its 1 kW power cap and the SM clock of a cool GPU sags by
+    # 3-5 % over the first second of back-to-back launches, so an e2e region measured right after the `value` region looked
+    # 4 % slower than it is (round 1: e2e/value 0.96 at N = 8; skipping the NCCL exchange entirely changed nothing).
+    barrier()
+    time.sleep(args.cooldown)
     if world > 1 and args.engine == "tc":
         # the side-stream all-gather needs an SM while the persistent rollout kernel runs: reserve NCCL's CTAs instead of
         # letting them displace rollout CTAs (which stretched every launch by the collective's cross-rank wait: 0.6 ms)
@@ -653,6 +696,7 @@ def main():
     barrier()
     ro.reserve_sms(0)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_kernel_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in e2e_kernel_events[-args.steps:]]))
     e2e_value = steps_total / (e2e_ms * 1e-3)
     windows_kept = int(buf.size)
 
@@ -743,10 +787,11 @@ def main():
             "config": {"workload": f"{args.env} fused rollout (actor MLP + TanhGauss sample + env ODE step + reward/cost + autoreset), "
                                    f"{n} envs/GPU (BASELINE config 5 per-GPU share), {K} env steps per launch, transitions written to HBM",
                        "engine": args.engine, "envs_per_gpu": n, "inner_steps": K, "n_step": n_step, "l2": "inputs larger than L2 (state + transitions per launch >> 126 MB)",
+                       "settle_s": args.settle, "cooldown_before_e2e_s": args.cooldown,
                        "parallelism": f"env-sharded x{world}, no step-path collective"},
-            "clocks": clk, "gpu_launches": args.steps,
+            "value_burst": main_run_burst, "clocks": clk, "gpu_launches": args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / args.steps, "gpu_launches_per_step": 6, "replay": args.replay,
+                    "ms_per_step": e2e_ms / args.steps, "rollout_kernel_ms_inside_e2e": e2e_kernel_ms, "gpu_launches_per_step": 6, "replay": args.replay,
                     "replay_capacity_windows": cap, "replay_windows_resident_after_run": windows_kept,
                     "what": "per step: H2D actor weights (pinned) -> sampler rollout -> buffer.add_batch (device window index scatter) -> "
                             "buffer.sample_batch (n-step gather) -> [one packed NCCL all-gather of the sub-batches + statistics on a side "

@@ -232,23 +232,73 @@ window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_fl
 // ---- index-based window store: a window is the flat position of its newest transition in the
 // [T][n][.] transition store the rollout kernel already wrote; nothing is copied at append time (8 bytes per window
 // instead of 8 * n_step * (2D + A + 4)), and the n rows are gathered when a batch is sampled.
+// Blocks of 256 threads x 16 flags (one 16-byte load per thread when the flag slice is 16-byte aligned): 4096 flags per
+// block, so the single-CTA scan of the block counts has 16x fewer entries than with one flag per thread (2^25 flags:
+// 8192 counts = 8 scan passes instead of 128 -- the scan was 0.2 ms of the 0.43 ms e2e overhead per launch).
+constexpr int IPT = 16, IBF = WB * IPT;
+
+__device__ __forceinline__ uint32_t load_flag_mask16(const uint8_t* __restrict__ emit, int64_t f0, int64_t total, bool vec) {
+  uint32_t mask = 0;
+  if (f0 >= total) return 0;
+  if (vec && f0 + IPT <= total) {
+    const uint4 v = *reinterpret_cast<const uint4*>(emit + f0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if ((w[q] >> (8 * b)) & 0xFFu) mask |= 1u << (4 * q + b);
+  } else {
+    for (int j = 0; j < IPT && f0 + j < total; ++j)
+      if (emit[f0 + j]) mask |= 1u << j;
+  }
+  return mask;
+}
+
+__global__ void __launch_bounds__(WB) window_count16_kernel(const uint8_t* __restrict__ emit_new, int64_t total, int vec,
+                                                            int64_t* __restrict__ block_counts) {
+  __shared__ int warp_counts[WB / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int c = __popc(load_flag_mask16(emit_new, ((int64_t)blockIdx.x * WB + tid) * IPT, total, vec != 0));
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) warp_counts[warp] = c;
+  __syncthreads();
+  if (tid == 0) {
+    int s = 0;
+    for (int w = 0; w < WB / 32; ++w) s += warp_counts[w];
+    block_counts[blockIdx.x] = s;
+  }
+}
+
 __global__ void __launch_bounds__(WB)
-window_index_scatter_kernel(const uint8_t* __restrict__ emit_new, int64_t total_flags, int64_t base_pos,
+window_index_scatter_kernel(const uint8_t* __restrict__ emit_new, int64_t total_flags, int vec, int64_t base_pos,
                             int64_t* __restrict__ win_pos, int64_t max_size, const int64_t* __restrict__ block_offsets,
                             const int64_t* __restrict__ header) {
   __shared__ int warp_counts[WB / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t f = (int64_t)blockIdx.x * WB + tid;
-  const int flag = (f < total_flags && emit_new[f]) ? 1 : 0;
-  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
-  if (lane == 0) warp_counts[warp] = __popc(ballot);
+  const int64_t f0 = ((int64_t)blockIdx.x * WB + tid) * IPT;
+  uint32_t mask = load_flag_mask16(emit_new, f0, total_flags, vec != 0);
+  const int c = __popc(mask);
+  int incl = c;                                    // inclusive warp scan of the per-thread counts
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_counts[warp] = incl;
   __syncthreads();
-  if (!flag) return;
-  int before = 0;
+  if (!c) return;
+  int before = incl - c;
   for (int w = 0; w < warp; ++w) before += warp_counts[w];
-  const int64_t order = block_offsets[blockIdx.x] + before + __popc(ballot & ((1u << lane) - 1u));
+  int64_t order = block_offsets[blockIdx.x] + before;   // position of this thread's first window in the reference's append order
   const int64_t old_ptr = header[0], total = header[1];
-  if ((total - order) <= max_size) win_pos[(old_ptr + order) % max_size] = base_pos + f;     // last writer wins
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1;
+    if ((total - order) <= max_size) win_pos[(old_ptr + order) % max_size] = base_pos + f0 + j;     // last writer wins
+    ++order;
+  }
 }
 
 template <int W>
@@ -380,11 +430,12 @@ extern "C" int msacl_window_index_store(const uint8_t* emit_new, int32_t K, int6
     return MSACL_ERR_BAD_ARG;
   }
   const int64_t total = (int64_t)K * n;
-  const int64_t nb = (total + WB - 1) / WB;
+  const int64_t nb = (total + IBF - 1) / IBF;
+  const int vec = (reinterpret_cast<uintptr_t>(emit_new) & 15) == 0 ? 1 : 0;
   cudaStream_t s = (cudaStream_t)stream;
-  window_count_kernel<<<(unsigned)nb, WB, 0, s>>>(emit_new, total, scratch + 2);
+  window_count16_kernel<<<(unsigned)nb, WB, 0, s>>>(emit_new, total, vec, scratch + 2);
   window_scan_kernel<<<1, 1024, 0, s>>>(scratch + 2, nb, scratch, ptr_size, count_out, max_size);
-  window_index_scatter_kernel<<<(unsigned)nb, WB, 0, s>>>(emit_new, total, base_pos, win_pos, max_size, scratch + 2, scratch);
+  window_index_scatter_kernel<<<(unsigned)nb, WB, 0, s>>>(emit_new, total, vec, base_pos, win_pos, max_size, scratch + 2, scratch);
   return check_launch("window_index_store");
 }
 

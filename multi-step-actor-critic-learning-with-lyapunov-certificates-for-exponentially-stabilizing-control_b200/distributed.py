@@ -121,7 +121,7 @@ class BatchExchange:
         self.send[cur][self.stats_off:].view(torch.float64).copy_(stats.detach().to(torch.float64))
         if self.world == 1:
             self.recv[cur].copy_(self.send[cur][None])
-        elif self.side is None:
+        elif self.side is None:                       # CPU tensors (gloo), or in-stream on request
             dist.all_gather_into_tensor(self.recv[cur].view(-1), self.send[cur], group=self.group)
         else:
             ready = torch.cuda.Event()
