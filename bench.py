@@ -648,6 +648,7 @@ def main():
     step_no = [0]
     consumed = [0.0]
     e2e_kernel_events = []
+    copy_stream = torch.cuda.Stream(dev)
 
     def e2e_step():
         cur = step_no[0] & 1
@@ -662,9 +663,16 @@ def main():
             packed = exch.send[0][None].expand(world, -1)
         else:
             packed = exch.exchange(sub, ro.stats[:8], unpack=False)   # N>1: NCCL all-gather on a side stream, previous result back
-        host_packed[cur].copy_(packed, non_blocking=True)         # D2H: the replay batch + episode statistics
-        ev = torch.cuda.Event()
-        ev.record(stream)
+        # D2H of the replay batch + episode statistics on a copy stream: a copy engine moves it while the next rollout launch
+        # already runs (at N = 8 the gathered buffer is 5.2 MB = 0.2 ms of PCIe time that used to sit between two launches)
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        copy_stream.wait_event(ready)
+        with torch.cuda.stream(copy_stream):
+            host_packed[cur].copy_(packed, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        exch.guard_reuse(ev)
         host_ready[cur] = ev
         # the host (learner side) consumes the batch of the PREVIOUS step while this step's launches are in flight: the
         # learner's data is one iteration stale by design, so the per-step host wait never drains the GPU queue

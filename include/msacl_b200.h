@@ -263,8 +263,16 @@ typedef struct {
   float* row_sumsq;
   int32_t precision;   /* bf16 products per algorithmic product: 6 (or 0 = default; 3-term operand split, FP32-class ~2^-23)
                           or 3 (2-term split, ~1.5e-5 relative per product, half the tensor work) */
+  const void* b_packed; /* optional: the B operand pre-converted by msacl_gemm_pack_b (same b / strides / n / k / precision);
+                          used when the launch takes 256-wide column tiles (many row tiles): the B stages are then streamed
+                          by bulk copies instead of being re-converted from `b` in every CTA.  `b` must still be valid. */
 } msacl_gemm_t;
 int msacl_gemm_tc(const msacl_gemm_t* g, void* stream);
+/* Pre-convert the B operand described by g (b, b_row_stride, b_k_stride, n <= 256, k, precision) into the kernel's
+ * shared-memory stage images; `packed` = device buffer of msacl_gemm_packed_b_bytes(k, precision) bytes, 16-byte aligned.
+ * Repack whenever the weights change (tiny: one thread per 8 elements). */
+int64_t msacl_gemm_packed_b_bytes(int32_t k, int32_t precision);
+int msacl_gemm_pack_b(const msacl_gemm_t* g, void* packed, void* stream);
 
 /* out[z][c] = sum over the rows of split z (rows divided evenly over `splits`) of x[r*ld + c]; cols <= 256.  Bias gradients. */
 int msacl_colsum(const float* x, int64_t rows, int32_t cols, int64_t ld, int32_t splits, float* out, void* stream);

@@ -46,7 +46,7 @@ class Gemm(C.Structure):
                 ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
                 ("c", vp), ("ldc", C.c_int64), ("split_k", C.c_int32), ("c_split_stride", C.c_int64),
                 ("bias", vp), ("act", C.c_int32), ("mask_src", vp), ("mask_ld", C.c_int64), ("mask_act", C.c_int32),
-                ("row_sumsq", vp), ("precision", C.c_int32)]
+                ("row_sumsq", vp), ("precision", C.c_int32), ("b_packed", vp)]
 
 
 f32 = C.c_float
@@ -84,6 +84,8 @@ SIGNATURES = {
     "msacl_selftest_tc_gemm": (C.c_int, [vp, vp, vp, C.c_int32, vp]),
     "msacl_polyak_update": (C.c_int, [C.c_int32, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp]),
     "msacl_gemm_tc": (C.c_int, [C.POINTER(Gemm), vp]),
+    "msacl_gemm_packed_b_bytes": (C.c_int64, [i32, i32]),
+    "msacl_gemm_pack_b": (C.c_int, [C.POINTER(Gemm), vp, vp]),
     "msacl_colsum": (C.c_int, [vp, i64, i32, i64, i32, vp, vp]),
     "msacl_concat2": (C.c_int, [vp, i32, vp, i32, i64, vp, vp]),
     "msacl_reduce_splits": (C.c_int, [vp, i64, i32, vp, vp]),

@@ -134,6 +134,30 @@ __device__ __forceinline__ void g_load_row(unsigned char* img0, const float* __r
   }
 }
 
+// Pre-packed B operand (weights): the bf16 images of every 32-wide K stage, exactly as a CTA's shared-memory B stage holds
+// them ([NIMG][4 K blocks][256 rows][16 B], rows >= n and k >= k_total zero), so that a GEMM over many row tiles streams
+// them with one cp.async.bulk per stage instead of re-converting the same 256 x 256 weights in every CTA.
+template <int NIMG>
+__global__ void __launch_bounds__(256) gemm_pack_b_kernel(msacl_gemm_t g, unsigned char* __restrict__ packed) {
+  constexpr int GB_HALF = GN * GK * 2, GB_LBO = GN * 16;
+  const int stages = (g.k + GK - 1) / GK;
+  const int64_t total = (int64_t)stages * 4 * GN;            // one thread per (stage, K block, row)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i % GN), kb = (int)((i / GN) % 4), st = (int)(i / (4 * GN));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = st * GK + kb * 8 + j;
+      v[j] = (row < g.n && k < g.k) ? g.b[(int64_t)row * g.b_row_stride + (int64_t)k * g.b_k_stride] : 0.f;
+    }
+    uint4 img[NIMG];
+    g_split8<NIMG>(v, img);
+    unsigned char* dst = packed + (size_t)st * NIMG * GB_HALF + kb * GB_LBO + row * 16;
+#pragma unroll
+    for (int q = 0; q < NIMG; ++q) *reinterpret_cast<uint4*>(dst + q * GB_HALF) = img[q];
+  }
+}
+
 // BN = column tile (UMMA N <= BN), STAGES = shared-memory stages.  <*, 256, 2>: large row counts (one column tile covers a
 // 256-wide layer); <*, 64, 4>: small row counts -- 4x more CTAs and a deeper prefetch, so a GEMM over a few thousand rows
 // (the reference's replay batch: 256 windows x 20 steps) is not serialised behind one tile's load latency.
@@ -154,8 +178,10 @@ __global__ void __launch_bounds__(G_THREADS, (NIMG == 2 && BN == 256) ? 2 : 1) g
   const int n_rem = g.n - n0;
   const int n_mma = n_rem >= GN ? GN : ((n_rem + 15) / 16) * 16;        // UMMA N: multiple of 16, 16..256
 
+  // packed B (BN = 256 only): the B tile arrives by one bulk copy per stage (expect_tx arrival of the issuing thread)
+  const bool packed_b = BN == 256 && g.b_packed != nullptr;
   if (tid == 0) {
-    for (int s = 0; s < G_STAGES; ++s) { tc::mbar_init(&sm.full[s], G_LOADERS); tc::mbar_init(&sm.empty[s], 1); }
+    for (int s = 0; s < G_STAGES; ++s) { tc::mbar_init(&sm.full[s], packed_b ? 128 + 1 : G_LOADERS); tc::mbar_init(&sm.empty[s], 1); }
     tc::mbar_init(&sm.accfull, 1);
     tc::mbar_fence_init();
   }
@@ -179,6 +205,13 @@ __global__ void __launch_bounds__(G_THREADS, (NIMG == 2 && BN == 256) ? 2 : 1) g
       if (t < 128) {
         if (avec) g_load_tile_kcontig<GA_LBO, GA_HALF, NIMG, 128, GM>(sm.a[s], g.a, g.a_row_stride, m0, g.m, GM, k0, kend, t);
         else g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, m0 + t, m0 + t < g.m, k0, kend, t, false);
+      } else if (packed_b) {
+        if (t == 128) {
+          constexpr uint32_t bytes = NIMG * GB_HALF;
+          tc::mbar_expect_tx(&sm.full[s], bytes);
+          tc::tma_bulk_g2s(sm.b[s], static_cast<const unsigned char*>(g.b_packed) + (size_t)(k0 / GK) * bytes, bytes, &sm.full[s]);
+        }
+        continue;                                   // (the other B threads have nothing to do in this mode)
       } else {
         const int tb = t - 128;
         if (bvec) g_load_tile_kcontig<GB_LBO, GB_HALF, NIMG, 256, (GN >= 32 ? GN : 32)>(sm.b[s], g.b, g.b_row_stride, n0, g.n, n_mma, k0, kend, tb);
@@ -304,6 +337,24 @@ __global__ void __launch_bounds__(G_THREADS, (NIMG == 2 && BN == 256) ? 2 : 1) g
 
 using namespace msacl;
 
+extern "C" int64_t msacl_gemm_packed_b_bytes(int32_t k, int32_t precision) {
+  if (k <= 0) return 0;
+  const int nimg = precision == 3 ? 2 : 3;
+  return (int64_t)((k + GK - 1) / GK) * nimg * GN * GK * 2;
+}
+
+extern "C" int msacl_gemm_pack_b(const msacl_gemm_t* g, void* packed, void* stream) {
+  if (!g || !g->b || !packed || g->n <= 0 || g->n > GN || g->k <= 0 || (reinterpret_cast<uintptr_t>(packed) & 15)) {
+    set_error("gemm_pack_b: bad argument (needs n <= 256 and a 16-byte aligned destination)");
+    return MSACL_ERR_BAD_ARG;
+  }
+  const int stages = (g->k + GK - 1) / GK;
+  const unsigned grid = (unsigned)((stages * 4 * GN + 255) / 256);
+  if (g->precision == 3) gemm_pack_b_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(*g, (unsigned char*)packed);
+  else gemm_pack_b_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(*g, (unsigned char*)packed);
+  return check_launch("gemm_pack_b");
+}
+
 extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
   if (!g || !g->a || !g->b || !g->c || g->m <= 0 || g->n <= 0 || g->k <= 0 || g->split_k < 1 || g->ldc < 1) {
     set_error("gemm_tc: bad argument");
@@ -315,6 +366,10 @@ extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
   }
   if (g->split_k > 1 && (g->bias || g->act || g->mask_src || g->row_sumsq)) {
     set_error("gemm_tc: split-K partials take no epilogue (bias / act / mask / row_sumsq)");
+    return MSACL_ERR_BAD_ARG;
+  }
+  if (g->b_packed && (g->split_k != 1 || (reinterpret_cast<uintptr_t>(g->b_packed) & 15) || g->n > GN)) {
+    set_error("gemm_tc: b_packed needs split_k == 1, n <= 256 and 16-byte alignment");
     return MSACL_ERR_BAD_ARG;
   }
   if (g->row_sumsq && g->n > GN) { set_error("gemm_tc: row_sumsq needs n <= 256 (one column tile)"); return MSACL_ERR_BAD_ARG; }

@@ -89,11 +89,13 @@ class BatchExchange:
             self.offsets[k] = (off, numel)
             off += (numel + 3) // 4 * 4                 # keep every field 16-byte aligned
         self.stats_off, self.P = off, off + 16
-        self.nbuf = self.depth + 1
+        self.nbuf = self.depth + 2                # one spare: a consumer may still be copying a returned buffer to the host
         self.send = [torch.zeros(self.P, dtype=torch.float32, device=self.device) for _ in range(self.nbuf)]
         self.recv = [torch.zeros(self.world, self.P, dtype=torch.float32, device=self.device) for _ in range(self.nbuf)]
         self.side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self.done = [None] * self.nbuf
+        self.reuse_guard = [None] * self.nbuf     # events a consumer recorded after reading recv[i] on ANOTHER stream (see guard_reuse)
+        self.last_take = 0
         self.t = 0
 
     def views(self):
@@ -119,6 +121,9 @@ class BatchExchange:
             if sub_batch[k].data_ptr() != mine[k].data_ptr():
                 mine[k].copy_(sub_batch[k])
         self.send[cur][self.stats_off:].view(torch.float64).copy_(stats.detach().to(torch.float64))
+        guard, self.reuse_guard[cur] = self.reuse_guard[cur], None
+        if guard is not None:                         # recv[cur] is about to be overwritten: its last reader must be done
+            (self.side if (self.side is not None and self.world > 1) else torch.cuda.current_stream()).wait_event(guard)
         if self.world == 1:
             self.recv[cur].copy_(self.send[cur][None])
         elif self.side is None:                       # CPU tensors (gloo), or in-stream on request
@@ -136,7 +141,13 @@ class BatchExchange:
         if self.side is not None and self.done[take] is not None:
             torch.cuda.current_stream().wait_event(self.done[take])
         self.t += 1
+        self.last_take = take
         return self._unpack(self.recv[take]) if unpack else self.recv[take]
+
+    def guard_reuse(self, event):
+        """`event` (recorded on whatever stream reads the buffer the last exchange() returned, e.g. a D2H copy stream) must
+        complete before that buffer is gathered into again."""
+        self.reuse_guard[self.last_take] = event
 
     def host_views(self, host_packed):
         """Unpack a host copy [G, P] of a gathered buffer: ({field: [B, n, .]}, statistics [8] float64); the batch fields are

@@ -44,9 +44,9 @@ class _Launcher:
 
 
 def _desc(a, a_rs, a_ks, b, b_rs, b_ks, m, n, k, c, ldc, split_k=1, c_split_stride=0, bias=None, act=0, mask=None, mask_ld=0,
-          mask_act=0, row_sumsq=None, precision=0):
+          mask_act=0, row_sumsq=None, precision=0, b_packed=None):
     p = lambda t: None if t is None else (t if isinstance(t, int) else t.data_ptr())
-    return _lib.Gemm(a=p(a), a_row_stride=a_rs, a_k_stride=a_ks, b=p(b), b_row_stride=b_rs, b_k_stride=b_ks, m=m, n=n, k=k, c=p(c),
+    return _lib.Gemm(b_packed=p(b_packed), a=p(a), a_row_stride=a_rs, a_k_stride=a_ks, b=p(b), b_row_stride=b_rs, b_k_stride=b_ks, m=m, n=n, k=k, c=p(c),
                      ldc=ldc, split_k=split_k, c_split_stride=c_split_stride, bias=p(bias), act=act, mask_src=p(mask), mask_ld=mask_ld,
                      mask_act=mask_act, row_sumsq=p(row_sumsq), precision=precision)
 
@@ -65,16 +65,30 @@ class MLPWorkspace:
         self.h1, self.h2, self.y = f(M, HID), f(M, HID), f(M, Dout)
         self.v = f(M) if sumsq else None
         self.x = None
+        # Many row tiles (>= one per SM): the weight operands of the forward / dgrad GEMMs are pre-converted once per call
+        # (msacl_gemm_pack_b) and streamed by bulk copies, instead of being re-converted from FP32 in each of the CTAs.
+        self.packed = {}
+        pack_ok = (M + 127) // 128 >= 148
+
+        def packed(tag, k):
+            if not pack_ok:
+                return None
+            nbytes = int(mlp._l.lib.msacl_gemm_packed_b_bytes(k, mlp.precision))
+            t = self.packed[tag] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            return t
+
         # forward: H1 = act(X W1^T + b1), H2 = act(H1 W2^T + b2), Y = H2 W3^T + b3
         self.f1 = _desc(0, Din, 1, W1, Din, 1, M, HID, Din, self.h1, HID, bias=b1, act=a)
-        self.f2 = _desc(self.h1, HID, 1, W2, HID, 1, M, HID, HID, self.h2, HID, bias=b2, act=a)
-        self.f3 = _desc(self.h2, HID, 1, W3, HID, 1, M, Dout, HID, self.y, Dout, bias=b3, act=0, row_sumsq=self.v)
+        self.f2 = _desc(self.h1, HID, 1, W2, HID, 1, M, HID, HID, self.h2, HID, bias=b2, act=a, b_packed=packed("f2", HID))
+        self.f3 = _desc(self.h2, HID, 1, W3, HID, 1, M, Dout, HID, self.y, Dout, bias=b3, act=0, row_sumsq=self.v,
+                        b_packed=packed("f3", HID))
         if not (train or need_dx):
             return
         self.da2, self.da1 = f(M, HID), f(M, HID)
         # dgrad: dA2 = (dY W3) * act'(H2);  dA1 = (dA2 W2) * act'(H1);  dX = dA1 W1
         self.g3 = _desc(0, Dout, 1, W3, 1, HID, M, HID, Dout, self.da2, HID, mask=self.h2, mask_ld=HID, mask_act=a)
-        self.g2 = _desc(self.da2, HID, 1, W2, 1, HID, M, HID, HID, self.da1, HID, mask=self.h1, mask_ld=HID, mask_act=a)
+        self.g2 = _desc(self.da2, HID, 1, W2, 1, HID, M, HID, HID, self.da1, HID, mask=self.h1, mask_ld=HID, mask_act=a,
+                        b_packed=packed("g2", HID))
         self.dx = f(M, Din) if need_dx else None
         self.g1 = _desc(self.da1, HID, 1, W1, 1, Din, M, Din, HID, self.dx, Din) if need_dx else None
         if not train:
@@ -147,14 +161,21 @@ class FusedMLP:
         ws.x = x
         ws.f1.a = x.data_ptr()
         g = self._l.gemm
+        self._pack(ws, ("f2", ws.f2), ("f3", ws.f3))
         g(ws.f1); g(ws.f2); g(ws.f3)
         return ws.y
+
+    def _pack(self, ws, *descs):
+        for tag, d in descs:
+            if tag in ws.packed:
+                _lib.check(self._l.lib.msacl_gemm_pack_b(C.byref(d), ws.packed[tag].data_ptr(), _lib.current_stream()))
 
     def backward(self, ws, dy, wgrad=True, need_dx=False):
         """dy: [rows, dout] gradient w.r.t. ws.y.  Fills the weight / bias gradient partials (wgrad) and/or ws.dx."""
         assert dy.is_contiguous() and dy.numel() == ws.rows * self.dout
         lib, st, l = self._l.lib, _lib.current_stream(), self._l
         ws.g3.a = dy.data_ptr()
+        self._pack(ws, ("g2", ws.g2))
         l.gemm(ws.g3)
         l.gemm(ws.g2)
         if need_dx:

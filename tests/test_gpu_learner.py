@@ -51,6 +51,37 @@ def test_gemm_tc_forward_bias_act(m, n, k, prec, tol):
             np.testing.assert_allclose(ss.cpu().numpy(), (Cm.double() ** 2).sum(1).cpu().numpy(), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("prec", [6, 3])
+@pytest.mark.parametrize("transposed_b", [False, True])
+def test_gemm_tc_prepacked_weights_bit_identical(prec, transposed_b):
+    """Large row counts stream a pre-converted B operand (msacl_gemm_pack_b) with bulk copies: same bf16 images, so the result
+    is bit-identical to the path that converts B inside every CTA -- forward (B = W) and dgrad (B = W^T read strided)."""
+    import msacl_b200
+    from msacl_b200 import _lib
+    from msacl_b200.learner import _desc
+    lib = msacl_b200.load_library()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    m, n, k = 148 * 128 + 77, 256, 256
+    A = torch.randn(m, k, device="cuda", generator=g)
+    W = torch.randn(256, 256, device="cuda", generator=g) / 16
+    bias = torch.randn(n, device="cuda", generator=g)
+    b_rs, b_ks = (1, 256) if transposed_b else (256, 1)
+    out = []
+    for use_pack in (False, True):
+        Cm = torch.empty(m, n, device="cuda")
+        d = _desc(a=A, a_rs=k, a_ks=1, b=W, b_rs=b_rs, b_ks=b_ks, m=m, n=n, k=k, c=Cm, ldc=n, bias=bias, act=1, precision=prec)
+        if use_pack:
+            packed = torch.empty(int(lib.msacl_gemm_packed_b_bytes(k, prec)), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.msacl_gemm_pack_b(C.byref(d), packed.data_ptr(), _lib.current_stream()))
+            d.b_packed = packed.data_ptr()
+        _lib.check(lib.msacl_gemm_tc(C.byref(d), _lib.current_stream()))
+        out.append(Cm)
+    assert torch.equal(out[0], out[1])
+    Wm = W.t() if transposed_b else W
+    want = torch.relu(A.double() @ Wm.double().t() + bias.double())
+    assert _rel(out[1], want) < (4e-6 if prec == 6 else 5e-5)
+
+
 def test_gemm_tc_strided_operands_dgrad_mask_and_splitk_wgrad():
     """dgrad (B read transposed, activation-derivative mask in the epilogue) and wgrad (A and B read transposed, K = rows
     split over CTAs, partials reduced in order) vs float64."""

@@ -27,9 +27,16 @@ cases = {
     "dgrad    [rows,256]x[256,256]   *relu'": lambda p: _desc(a=X, a_rs=256, a_ks=1, b=W, b_rs=1, b_ks=256, m=rows, n=256, k=256, c=Y, ldc=256, mask=X, mask_ld=256, mask_act=1, precision=p),
     "wgrad    [256,rows]x[rows,256]  split-K 74": lambda p: _desc(a=X, a_rs=1, a_ks=256, b=X, b_rs=1, b_ks=256, m=256, n=256, k=rows, c=parts, ldc=256, split_k=S, c_split_stride=65536, precision=p),
 }
-for name, mk in cases.items():
+packed_cases = {k + "  [weights pre-packed]": v for k, v in cases.items() if "wgrad" not in k}
+for name, mk in list(cases.items()) + list(packed_cases.items()):
     for prec in (6, 3):
         d = mk(prec)
+        if "pre-packed" in name:
+            if (rows + 127) // 128 < 148:
+                continue
+            pk = torch.empty(int(lib.msacl_gemm_packed_b_bytes(256, prec)), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.msacl_gemm_pack_b(C.byref(d), pk.data_ptr(), _lib.current_stream()))
+            d.b_packed = pk.data_ptr()
         for _ in range(3):
             _lib.check(lib.msacl_gemm_tc(C.byref(d), _lib.current_stream()))
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
