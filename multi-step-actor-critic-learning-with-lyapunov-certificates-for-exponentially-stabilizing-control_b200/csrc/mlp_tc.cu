@@ -33,7 +33,8 @@ template <int NIMG, int BN, int STAGES>
 struct GemmSmem {
   alignas(128) unsigned char a[STAGES][NIMG * GA_HALF];
   alignas(128) unsigned char b[STAGES][NIMG * BN * GK * 2];
-  unsigned long long full[STAGES], empty[STAGES], accfull;
+  alignas(16) float bias[BN];
+  unsigned long long full[STAGES], empty[STAGES], accfull[2], accfree[2];
   uint32_t tmem_slot;
 };
 
@@ -158,31 +159,50 @@ __global__ void __launch_bounds__(256) gemm_pack_b_kernel(msacl_gemm_t g, unsign
   }
 }
 
-// BN = column tile (UMMA N <= BN), STAGES = shared-memory stages.  <*, 256, 2>: large row counts (one column tile covers a
-// 256-wide layer); <*, 64, 4>: small row counts -- 4x more CTAs and a deeper prefetch, so a GEMM over a few thousand rows
-// (the reference's replay batch: 256 windows x 20 steps) is not serialised behind one tile's load latency.
+// BN = column tile (UMMA N <= BN), STAGES = shared-memory stages.  Persistent CTAs (one per SM) walk the output tiles with a
+// static stride; the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM -> bias /
+// activation -> global) overlaps the loads and UMMAs of tile i + 1 -- ncu had the epilogue at ~2/3 of a tile's lifetime
+// with every other warp idle at the teardown barrier.  <*, 256, *>: large row counts (one column tile covers a 256-wide
+// layer); <*, 128, *> / <*, 64, *>: small row counts -- more CTAs in the single wave, so a GEMM over a few thousand rows (the
+// reference's replay batch: 256 windows x 20 steps) is not serialised behind one tile's load latency.
+struct GemmTile {
+  int m0, n0, z, kbeg, kend, nk, n_rem, n_mma;
+};
+
+template <int BN>
+__device__ __forceinline__ GemmTile gemm_tile(const msacl_gemm_t& g, int64_t tile, int mtiles, int ntiles) {
+  GemmTile t;
+  const int64_t per_z = (int64_t)mtiles * ntiles;
+  t.z = (int)(tile / per_z);
+  const int64_t rem = tile - (int64_t)t.z * per_z;
+  const int y = (int)(rem / mtiles);
+  t.m0 = (int)(rem - (int64_t)y * mtiles) * GM;
+  t.n0 = y * BN;
+  const int kper = ((g.k + g.split_k - 1) / g.split_k + GK - 1) / GK * GK;     // K range of a split: multiples of the stage width
+  t.kbeg = t.z * kper;
+  t.kend = min(g.k, t.kbeg + kper);
+  t.nk = t.kend > t.kbeg ? (t.kend - t.kbeg + GK - 1) / GK : 0;
+  t.n_rem = g.n - t.n0;
+  t.n_mma = t.n_rem >= BN ? BN : ((t.n_rem + 15) / 16) * 16;                   // UMMA N: multiple of 16, 16..256
+  return t;
+}
+
 template <int NIMG, int BN, int STAGES>
-__global__ void __launch_bounds__(G_THREADS, (NIMG == 2 && BN == 256) ? 2 : 1) gemm_tc_kernel(msacl_gemm_t g) {
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
   constexpr int G_STAGES = STAGES;
   constexpr int GN = BN, GB_HALF = BN * GK * 2, GB_LBO = BN * 16;
-  constexpr uint32_t TMEM_COLS = BN >= 256 ? 256 : (BN >= 128 ? 128 : 64);
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator buffers (512 / 256 / 128 columns)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GemmSmem<NIMG, BN, STAGES>& sm = *reinterpret_cast<GemmSmem<NIMG, BN, STAGES>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
-  // K range of this split (multiples of the stage width)
-  const int kper = ((g.k + g.split_k - 1) / g.split_k + GK - 1) / GK * GK;
-  const int kbeg = blockIdx.z * kper;
-  const int kend = min(g.k, kbeg + kper);
-  const int nk = kend > kbeg ? (kend - kbeg + GK - 1) / GK : 0;
-  const int n_rem = g.n - n0;
-  const int n_mma = n_rem >= GN ? GN : ((n_rem + 15) / 16) * 16;        // UMMA N: multiple of 16, 16..256
+  const int mtiles = (g.m + GM - 1) / GM, ntiles = (g.n + BN - 1) / BN;
+  const int64_t total_tiles = (int64_t)mtiles * ntiles * g.split_k;
 
   // packed B (BN = 256 only): the B tile arrives by one bulk copy per stage (expect_tx arrival of the issuing thread)
   const bool packed_b = BN == 256 && g.b_packed != nullptr;
   if (tid == 0) {
     for (int s = 0; s < G_STAGES; ++s) { tc::mbar_init(&sm.full[s], packed_b ? 128 + 1 : G_LOADERS); tc::mbar_init(&sm.empty[s], 1); }
-    tc::mbar_init(&sm.accfull, 1);
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&sm.accfull[b], 1); tc::mbar_init(&sm.accfree[b], 128); }
     tc::mbar_fence_init();
   }
   if (warp == G_MMA_WARP) tc::tmem_alloc(&sm.tmem_slot, TMEM_COLS);
@@ -198,134 +218,158 @@ __global__ void __launch_bounds__(G_THREADS, (NIMG == 2 && BN == 256) ? 2 : 1) g
     const int t = tid - 128;
     const bool avec = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0;
     const bool bvec = g.b_k_stride == 1 && (g.b_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0;
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % G_STAGES;
-      if (it >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((it / G_STAGES - 1) & 1));
-      const int k0 = kbeg + it * GK;
-      if (t < 128) {
-        if (avec) g_load_tile_kcontig<GA_LBO, GA_HALF, NIMG, 128, GM>(sm.a[s], g.a, g.a_row_stride, m0, g.m, GM, k0, kend, t);
-        else g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, m0 + t, m0 + t < g.m, k0, kend, t, false);
-      } else if (packed_b) {
-        if (t == 128) {
-          constexpr uint32_t bytes = NIMG * GB_HALF;
-          tc::mbar_expect_tx(&sm.full[s], bytes);
-          tc::tma_bulk_g2s(sm.b[s], static_cast<const unsigned char*>(g.b_packed) + (size_t)(k0 / GK) * bytes, bytes, &sm.full[s]);
+    uint32_t gs = 0;                                     // stage counter over all tiles of this CTA
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const GemmTile tl = gemm_tile<BN>(g, tile, mtiles, ntiles);
+      for (int it = 0; it < tl.nk; ++it, ++gs) {
+        const int s = gs % G_STAGES;
+        if (gs >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((gs / G_STAGES - 1) & 1));
+        const int k0 = tl.kbeg + it * GK;
+        if (t < 128) {
+          if (avec) g_load_tile_kcontig<GA_LBO, GA_HALF, NIMG, 128, GM>(sm.a[s], g.a, g.a_row_stride, tl.m0, g.m, GM, k0, tl.kend, t);
+          else g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, tl.m0 + t, tl.m0 + t < g.m, k0, tl.kend, t, false);
+        } else if (packed_b) {
+          if (t == 128) {
+            constexpr uint32_t bytes = NIMG * GB_HALF;
+            tc::mbar_expect_tx(&sm.full[s], bytes);
+            tc::tma_bulk_g2s(sm.b[s], static_cast<const unsigned char*>(g.b_packed) + (size_t)(k0 / GK) * bytes, bytes, &sm.full[s]);
+          }
+          continue;                                   // (the other B threads have nothing to do in this mode)
+        } else {
+          const int tb = t - 128;
+          if (bvec) g_load_tile_kcontig<GB_LBO, GB_HALF, NIMG, 256, (GN >= 32 ? GN : 32)>(sm.b[s], g.b, g.b_row_stride, tl.n0, g.n, tl.n_mma, k0, tl.kend, tb);
+          else if (tb < tl.n_mma) g_load_row<GB_LBO, GB_HALF, NIMG>(sm.b[s], g.b, g.b_row_stride, g.b_k_stride, tl.n0 + tb, tl.n0 + tb < g.n, k0, tl.kend, tb, false);
         }
-        continue;                                   // (the other B threads have nothing to do in this mode)
-      } else {
-        const int tb = t - 128;
-        if (bvec) g_load_tile_kcontig<GB_LBO, GB_HALF, NIMG, 256, (GN >= 32 ? GN : 32)>(sm.b[s], g.b, g.b_row_stride, n0, g.n, n_mma, k0, kend, tb);
-        else if (tb < n_mma) g_load_row<GB_LBO, GB_HALF, NIMG>(sm.b[s], g.b, g.b_row_stride, g.b_k_stride, n0 + tb, n0 + tb < g.n, k0, kend, tb, false);
+        tc::fence_async_smem();
+        tc::mbar_arrive(&sm.full[s]);
       }
-      tc::fence_async_smem();
-      tc::mbar_arrive(&sm.full[s]);
     }
   } else if (warp == G_MMA_WARP) {
     // =========================== MMA issuer ===========================
     if (tc::elect_one()) {
-      const uint32_t idesc = tc::make_idesc_bf16(GM, n_mma);
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % G_STAGES;
-        tc::mbar_wait(&sm.full[s], (uint32_t)((it / G_STAGES) & 1));
+      uint32_t gs = 0, li = 0;                            // stage counter, local tile counter
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+        const GemmTile tl = gemm_tile<BN>(g, tile, mtiles, ntiles);
+        const uint32_t buf = li & 1u;
+        if (li >= 2) tc::mbar_wait(&sm.accfree[buf], (uint32_t)(((li >> 1) - 1) & 1));     // epilogue of tile li - 2 has drained this buffer
         tc::tc_fence_after();
-        const uint32_t ab = tc::smem_u32(sm.a[s]), bb = tc::smem_u32(sm.b[s]);
+        const uint32_t tacc = tmem + buf * (uint32_t)BN;
+        const uint32_t idesc = tc::make_idesc_bf16(GM, tl.n_mma);
+        for (int it = 0; it < tl.nk; ++it, ++gs) {
+          const int s = gs % G_STAGES;
+          tc::mbar_wait(&sm.full[s], (uint32_t)((gs / G_STAGES) & 1));
+          tc::tc_fence_after();
+          const uint32_t ab = tc::smem_u32(sm.a[s]), bb = tc::smem_u32(sm.b[s]);
 #pragma unroll
-        for (int j = 0; j < GK / 16; ++j) {
-          uint64_t da[NIMG], db[NIMG];
+          for (int j = 0; j < GK / 16; ++j) {
+            uint64_t da[NIMG], db[NIMG];
 #pragma unroll
-          for (int i = 0; i < NIMG; ++i) {
-            da[i] = tc::make_smem_desc(ab + i * GA_HALF + j * 2 * GA_LBO, GA_LBO, G_SBO);
-            db[i] = tc::make_smem_desc(bb + i * GB_HALF + j * 2 * GB_LBO, GB_LBO, G_SBO);
+            for (int i = 0; i < NIMG; ++i) {
+              da[i] = tc::make_smem_desc(ab + i * GA_HALF + j * 2 * GA_LBO, GA_LBO, G_SBO);
+              db[i] = tc::make_smem_desc(bb + i * GB_HALF + j * 2 * GB_LBO, GB_LBO, G_SBO);
+            }
+            tc::umma_bf16(tacc, da[0], db[0], idesc, (it > 0 || j > 0) ? 1u : 0u);
+            tc::umma_bf16(tacc, da[0], db[1], idesc, 1u);
+            tc::umma_bf16(tacc, da[1], db[0], idesc, 1u);
+            if constexpr (NIMG == 3) {
+              tc::umma_bf16(tacc, da[1], db[1], idesc, 1u);
+              tc::umma_bf16(tacc, da[0], db[2], idesc, 1u);
+              tc::umma_bf16(tacc, da[2], db[0], idesc, 1u);
+            }
           }
-          // smallest cross terms first would be ideal for the FP32 accumulator; the order below keeps the accumulate flag simple
-          tc::umma_bf16(tmem, da[0], db[0], idesc, (it > 0 || j > 0) ? 1u : 0u);
-          tc::umma_bf16(tmem, da[0], db[1], idesc, 1u);
-          tc::umma_bf16(tmem, da[1], db[0], idesc, 1u);
-          if constexpr (NIMG == 3) {
-            tc::umma_bf16(tmem, da[1], db[1], idesc, 1u);
-            tc::umma_bf16(tmem, da[0], db[2], idesc, 1u);
-            tc::umma_bf16(tmem, da[2], db[0], idesc, 1u);
-          }
+          tc::umma_commit(&sm.empty[s]);
         }
-        tc::umma_commit(&sm.empty[s]);
+        tc::umma_commit(&sm.accfull[buf]);
       }
-      tc::umma_commit(&sm.accfull);
     }
   } else {
     // =========================== epilogue: TMEM -> bias / activation / mask -> global ===========================
-    const int row = m0 + warp * 32 + lane;
-    const bool row_ok = row < g.m;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    float* crow = g.c + (int64_t)blockIdx.z * g.c_split_stride + (int64_t)row * g.ldc + n0;
-    const float* mrow = g.mask_src ? g.mask_src + (int64_t)row * g.mask_ld + n0 : nullptr;
     const bool cvec = (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(g.c) & 15) == 0 && (g.c_split_stride & 3) == 0;
-    const bool mvec = mrow && (g.mask_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask_src) & 15) == 0;
-    float ss = 0.f;
-    if (nk > 0) {
-      tc::mbar_wait(&sm.accfull, 0u);
+    const bool mvec = g.mask_src && (g.mask_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask_src) & 15) == 0;
+    uint32_t li = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+      const GemmTile tl = gemm_tile<BN>(g, tile, mtiles, ntiles);
+      const uint32_t buf = li & 1u;
+      const uint32_t tacc = tmem + buf * (uint32_t)BN;
+      const int row = tl.m0 + warp * 32 + lane;
+      const bool row_ok = row < g.m;
+      float* crow = g.c + (int64_t)tl.z * g.c_split_stride + (int64_t)row * g.ldc + tl.n0;
+      const float* mrow = g.mask_src ? g.mask_src + (int64_t)row * g.mask_ld + tl.n0 : nullptr;
+      // bias of this column tile -> shared memory (the per-column global loads were most of the epilogue's stall time)
+      asm volatile("bar.sync 1, 128;" ::: "memory");             // every epilogue warp is done with the previous tile's bias
+      if (g.bias)
+        for (int c = tid; c < BN; c += 128) sm.bias[c] = (c < tl.n_rem) ? g.bias[tl.n0 + c] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float ss = 0.f;
+      tc::mbar_wait(&sm.accfull[buf], (uint32_t)((li >> 1) & 1));
       tc::tc_fence_after();
-    }
-    for (int c = 0; c < n_mma; c += 32) {
-      uint32_t v[32];
-      if (nk == 0) {
+      for (int c = 0; c < tl.n_mma; c += 32) {
+        uint32_t v[32];
+        if (tl.nk == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      } else if (n_mma - c >= 32) {
-        tc::tmem_ld32(tmem + lane_addr + (uint32_t)c, v);
-        tc::tmem_ld_wait();
-      } else {
-        uint32_t w[16];
-        tc::tmem_ld16(tmem + lane_addr + (uint32_t)c, w);
-        tc::tmem_ld_wait();
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        } else if (tl.n_mma - c >= 32) {
+          tc::tmem_ld32(tacc + lane_addr + (uint32_t)c, v);
+          tc::tmem_ld_wait();
+        } else {
+          uint32_t w[16];
+          tc::tmem_ld16(tacc + lane_addr + (uint32_t)c, w);
+          tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
-      }
-      if (!row_ok) continue;
-#pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        const int col = c + j4;                 // tile-local column
-        if (col >= n_rem) break;
-        float x[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = __uint_as_float(v[j4 + j]);
-        const bool full4 = col + 3 < n_rem;
-        if (g.bias) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (col + j < n_rem) x[j] += g.bias[n0 + col + j];
+          for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
         }
-        if (g.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
-        } else if (g.act == 2) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+        if (c + 32 >= tl.n_mma) {                       // last accumulator read of this tile: hand the buffer back to the MMA thread
+          tc::tc_fence_before();
+          tc::mbar_arrive(&sm.accfree[buf]);
         }
-        if (mrow) {
-          float hsrc[4];
-          if (mvec && full4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(mrow + col);
-            hsrc[0] = t4.x; hsrc[1] = t4.y; hsrc[2] = t4.z; hsrc[3] = t4.w;
+        if (!row_ok) continue;
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const int col = c + j4;                 // tile-local column
+          if (col >= tl.n_rem) break;
+          float x[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = __uint_as_float(v[j4 + j]);
+          const bool full4 = col + 3 < tl.n_rem;
+          if (g.bias) {
+            const float4 bb = *reinterpret_cast<const float4*>(&sm.bias[col]);
+            x[0] += bb.x; x[1] += bb.y; x[2] += bb.z; x[3] += bb.w;
+          }
+          if (g.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
+          } else if (g.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+          }
+          if (mrow) {
+            float hsrc[4];
+            if (mvec && full4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(mrow + col);
+              hsrc[0] = t4.x; hsrc[1] = t4.y; hsrc[2] = t4.z; hsrc[3] = t4.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) hsrc[j] = (col + j < tl.n_rem) ? mrow[col + j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (g.mask_act == 1) x[j] = hsrc[j] > 0.f ? x[j] : 0.f;                       // relu'(pre) = [post > 0]
+              else if (g.mask_act == 2) x[j] = x[j] * (1.0f - hsrc[j] * hsrc[j]);           // tanh'(pre) = 1 - post^2
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (col + j < tl.n_rem) ss = __fmaf_rn(x[j], x[j], ss);
+          if (cvec && full4) {
+            *reinterpret_cast<float4*>(crow + col) = make_float4(x[0], x[1], x[2], x[3]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) hsrc[j] = (col + j < n_rem) ? mrow[col + j] : 0.f;
+            for (int j = 0; j < 4; ++j) if (col + j < tl.n_rem) crow[col + j] = x[j];
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (g.mask_act == 1) x[j] = hsrc[j] > 0.f ? x[j] : 0.f;                       // relu'(pre) = [post > 0]
-            else if (g.mask_act == 2) x[j] = x[j] * (1.0f - hsrc[j] * hsrc[j]);           // tanh'(pre) = 1 - post^2
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (col + j < n_rem) ss = __fmaf_rn(x[j], x[j], ss);
-        if (cvec && full4) {
-          *reinterpret_cast<float4*>(crow + col) = make_float4(x[0], x[1], x[2], x[3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (col + j < n_rem) crow[col + j] = x[j];
         }
       }
+      if (g.row_sumsq && row_ok) g.row_sumsq[row] = ss;
     }
-    if (g.row_sumsq && row_ok) g.row_sumsq[row] = ss;
   }
   // ---- teardown
   tc::tc_fence_before();
@@ -388,12 +432,13 @@ extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
       if (best_waves < 0 || waves < best_waves) { best_waves = waves; bn = cand; }
     }
   }
-  const dim3 grid((unsigned)mt, (unsigned)((g->n + bn - 1) / bn), (unsigned)g->split_k);
+  const int64_t tiles = mt * ((g->n + bn - 1) / bn) * g->split_k;
+  const dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));          // persistent: one CTA per SM
   static bool attr_set = false;
   auto set_attr = [&](auto kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
   };
-#define MSACL_GEMM_VARIANTS(X) X(2, 256, 2) X(3, 256, 2) X(2, 128, 3) X(3, 128, 3) X(2, 64, 4) X(3, 64, 4)
+#define MSACL_GEMM_VARIANTS(X) X(2, 256, 4) X(3, 256, 3) X(2, 128, 4) X(3, 128, 4) X(2, 64, 4) X(3, 64, 4)
   if (!attr_set) {
     bool ok = true;
 #define X(NI, BN_, ST) ok = ok && set_attr(gemm_tc_kernel<NI, BN_, ST>, sizeof(GemmSmem<NI, BN_, ST>) + 128);
