@@ -26,14 +26,17 @@ constexpr int GM = 128, GN = 256, GK = 32;  // GN = widest column tile (template
 constexpr int GA_HALF = GM * GK * 2;       // 8 KB: one bf16 image of an A stage
 constexpr int GA_LBO = GM * 16, G_SBO = 128;
 constexpr int G_LOADERS = 384;             // 12 loader warps: threads 0..127 own the A tile, 128..383 the B tile
-constexpr int G_MMA_WARP = 4 + G_LOADERS / 32;
-constexpr int G_THREADS = 32 * (G_MMA_WARP + 1);   // warps 0-3 epilogue (TMEM lane quadrant = warp), 4-15 loaders, 16 MMA issuer
+constexpr int G_EPI_WARPS = 8;             // two per TMEM lane quadrant (quadrant = warp & 3), each owning half of the columns
+constexpr int G_EPI_THREADS = 32 * G_EPI_WARPS;
+constexpr int G_MMA_WARP = G_EPI_WARPS + G_LOADERS / 32;
+constexpr int G_THREADS = 32 * (G_MMA_WARP + 1);   // warps 0-7 epilogue, 8-19 loaders, 20 MMA issuer
 
 template <int NIMG, int BN, int STAGES>
 struct GemmSmem {
   alignas(128) unsigned char a[STAGES][NIMG * GA_HALF];
   alignas(128) unsigned char b[STAGES][NIMG * BN * GK * 2];
   alignas(16) float bias[BN];
+  float ss_part[GM];
   unsigned long long full[STAGES], empty[STAGES], accfull[2], accfree[2];
   uint32_t tmem_slot;
 };
@@ -66,13 +69,11 @@ __device__ __forceinline__ void g_split8(const float (&v)[8], uint4 (&img)[NIMG]
 // consecutive lanes on consecutive chunks (a warp instruction covers 4 whole 128-byte rows: fully coalesced, 4 L1 tags
 // instead of 32).  Thread t keeps chunk c = t % 8 (K block c / 2, half c % 2) of rows t / 8 + j * GSZ / 8; each chunk becomes one
 // 8-byte store per image (4-way bank conflict among the 4 K blocks of a row group, ~1k cycles per stage).
-template <int LBO, int HALF, int NIMG, int GSZ, int ROWS>
-__device__ __forceinline__ void g_load_tile_kcontig(unsigned char* img0, const float* __restrict__ src, int64_t rs, int64_t row0,
-                                                    int64_t row_limit, int rows_used, int k0, int kend, int t) {
+template <int GSZ, int ROWS>
+__device__ __forceinline__ void g_kcontig_load(float4 (&v)[ROWS * 8 / GSZ], const float* __restrict__ src, int64_t rs, int64_t row0,
+                                               int64_t row_limit, int rows_used, int k0, int kend, int t) {
   constexpr int NIT = ROWS * 8 / GSZ;
-  const int c = t & 7;
-  const int kk = k0 + c * 4;
-  float4 v[NIT];
+  const int kk = k0 + (t & 7) * 4;
 #pragma unroll
   for (int j = 0; j < NIT; ++j) {
     const int rl = (t >> 3) + j * (GSZ / 8);
@@ -88,6 +89,12 @@ __device__ __forceinline__ void g_load_tile_kcontig(unsigned char* img0, const f
       }
     }
   }
+}
+
+template <int LBO, int HALF, int NIMG, int GSZ, int ROWS>
+__device__ __forceinline__ void g_kcontig_store(unsigned char* img0, const float4 (&v)[ROWS * 8 / GSZ], int rows_used, int t) {
+  constexpr int NIT = ROWS * 8 / GSZ;
+  const int c = t & 7;
 #pragma unroll
   for (int j = 0; j < NIT; ++j) {
     const int rl = (t >> 3) + j * (GSZ / 8);
@@ -102,6 +109,14 @@ __device__ __forceinline__ void g_load_tile_kcontig(unsigned char* img0, const f
       *reinterpret_cast<uint2*>(dst + i * HALF) = make_uint2(h0, h1);
     }
   }
+}
+
+template <int LBO, int HALF, int NIMG, int GSZ, int ROWS>
+__device__ __forceinline__ void g_load_tile_kcontig(unsigned char* img0, const float* __restrict__ src, int64_t rs, int64_t row0,
+                                                    int64_t row_limit, int rows_used, int k0, int kend, int t) {
+  float4 v[ROWS * 8 / GSZ];
+  g_kcontig_load<GSZ, ROWS>(v, src, rs, row0, row_limit, rows_used, k0, kend, t);
+  g_kcontig_store<LBO, HALF, NIMG, GSZ, ROWS>(img0, v, rows_used, t);
 }
 
 // One operand row (local index rl, global row index `row`) of a 32-wide K stage -> 4 K blocks of 8 into the hi / lo images.
@@ -200,9 +215,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
 
   // packed B (BN = 256 only): the B tile arrives by one bulk copy per stage (expect_tx arrival of the issuing thread)
   const bool packed_b = BN == 256 && g.b_packed != nullptr;
+  const bool avec0 = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0;
+  // loader roles (t = thread index within the 384 loader threads): A tile by threads [0, a_threads) -- 256 of them when the B
+  // tile needs no conversion (packed) and A is k-contiguous, else 128; B tile by threads [128, 384), or by ONE bulk-copy issuer
+  const int a_threads = (packed_b && avec0) ? 256 : 128;
+  const int b_issuer = a_threads;                      // packed mode: the thread right after the A group issues the bulk copies
   if (tid == 0) {
-    for (int s = 0; s < G_STAGES; ++s) { tc::mbar_init(&sm.full[s], packed_b ? 128 + 1 : G_LOADERS); tc::mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&sm.accfull[b], 1); tc::mbar_init(&sm.accfree[b], 128); }
+    for (int s = 0; s < G_STAGES; ++s) { tc::mbar_init(&sm.full[s], packed_b ? a_threads + 1 : G_LOADERS); tc::mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&sm.accfull[b], 1); tc::mbar_init(&sm.accfree[b], G_EPI_THREADS); }
     tc::mbar_fence_init();
   }
   if (warp == G_MMA_WARP) tc::tmem_alloc(&sm.tmem_slot, TMEM_COLS);
@@ -211,37 +231,90 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
   tc::tc_fence_after();
   const uint32_t tmem = sm.tmem_slot;
 
-  if (warp >= 4 && warp < G_MMA_WARP) {
+  if (warp >= G_EPI_WARPS && warp < G_MMA_WARP) {
     // =========================== loaders: FP32 global -> split-bf16 operand images ===========================
     // threads 0..127 of the loader group own the A tile (128 rows), threads 128..383 the B tile (<= 256 rows): one row (or
     // 8 coalesced float4 chunks) per thread per stage, so a stage costs one global round trip.
-    const int t = tid - 128;
+    const int t = tid - G_EPI_THREADS;
     const bool avec = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0;
     const bool bvec = g.b_k_stride == 1 && (g.b_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0;
-    uint32_t gs = 0;                                     // stage counter over all tiles of this CTA
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const GemmTile tl = gemm_tile<BN>(g, tile, mtiles, ntiles);
-      for (int it = 0; it < tl.nk; ++it, ++gs) {
+    if (avec && packed_b && t < a_threads) {
+      // ---- A tile, k-contiguous, many row tiles (packed B): software-pipelined -- the global loads of stage i + 1 (possibly the next tile's first
+      //      stage) are in flight while stage i is converted and stored, so a stage no longer costs a full DRAM round trip
+      //      per loader thread (ncu: 74 % of the loader samples were long-scoreboard stalls)
+      int64_t tile = blockIdx.x, ntile = tile;
+      GemmTile tl, ntl;
+      int it = 0, nit = 0;
+      bool have = false, nhave = false;
+      auto fetch = [&](int64_t& tl_id, GemmTile& c, int& i_, bool& ok, int64_t from_tile, int from_it, const GemmTile& from, bool first) {
+        // position after (from_tile, from_it), or the first position if `first`
+        tl_id = from_tile; c = from; i_ = first ? 0 : from_it + 1;
+        if (first) c = tl_id < total_tiles ? gemm_tile<BN>(g, tl_id, mtiles, ntiles) : c;
+        while (tl_id < total_tiles && i_ >= c.nk) {
+          tl_id += gridDim.x; i_ = 0;
+          if (tl_id < total_tiles) c = gemm_tile<BN>(g, tl_id, mtiles, ntiles);
+        }
+        ok = tl_id < total_tiles;
+      };
+      fetch(tile, tl, it, have, (int64_t)blockIdx.x, 0, tl, true);
+      float4 cur[8], nxt[8];
+      auto load = [&](float4 (&v)[8], const GemmTile& c, int i_) {
+        if (a_threads == 256) {
+          float4 w[4];
+          g_kcontig_load<256, GM>(w, g.a, g.a_row_stride, c.m0, g.m, GM, c.kbeg + i_ * GK, c.kend, t);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = w[q];
+        } else {
+          g_kcontig_load<128, GM>(v, g.a, g.a_row_stride, c.m0, g.m, GM, c.kbeg + i_ * GK, c.kend, t);
+        }
+      };
+      if (have) load(cur, tl, it);
+      uint32_t gs = 0;
+      while (have) {
+        fetch(ntile, ntl, nit, nhave, tile, it, tl, false);
+        if (nhave) load(nxt, ntl, nit);
         const int s = gs % G_STAGES;
         if (gs >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((gs / G_STAGES - 1) & 1));
-        const int k0 = tl.kbeg + it * GK;
-        if (t < 128) {
-          if (avec) g_load_tile_kcontig<GA_LBO, GA_HALF, NIMG, 128, GM>(sm.a[s], g.a, g.a_row_stride, tl.m0, g.m, GM, k0, tl.kend, t);
-          else g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, tl.m0 + t, tl.m0 + t < g.m, k0, tl.kend, t, false);
-        } else if (packed_b) {
-          if (t == 128) {
-            constexpr uint32_t bytes = NIMG * GB_HALF;
-            tc::mbar_expect_tx(&sm.full[s], bytes);
-            tc::tma_bulk_g2s(sm.b[s], static_cast<const unsigned char*>(g.b_packed) + (size_t)(k0 / GK) * bytes, bytes, &sm.full[s]);
-          }
-          continue;                                   // (the other B threads have nothing to do in this mode)
+        if (a_threads == 256) {
+          float4 w[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[q] = cur[q];
+          g_kcontig_store<GA_LBO, GA_HALF, NIMG, 256, GM>(sm.a[s], w, GM, t);
         } else {
-          const int tb = t - 128;
-          if (bvec) g_load_tile_kcontig<GB_LBO, GB_HALF, NIMG, 256, (GN >= 32 ? GN : 32)>(sm.b[s], g.b, g.b_row_stride, tl.n0, g.n, tl.n_mma, k0, tl.kend, tb);
-          else if (tb < tl.n_mma) g_load_row<GB_LBO, GB_HALF, NIMG>(sm.b[s], g.b, g.b_row_stride, g.b_k_stride, tl.n0 + tb, tl.n0 + tb < g.n, k0, tl.kend, tb, false);
+          g_kcontig_store<GA_LBO, GA_HALF, NIMG, 128, GM>(sm.a[s], cur, GM, t);
         }
         tc::fence_async_smem();
         tc::mbar_arrive(&sm.full[s]);
+        ++gs;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+        tile = ntile; tl = ntl; it = nit; have = nhave;
+      }
+    } else if (t < 128 || (!packed_b && t >= 128) || (packed_b && t == b_issuer)) {
+      const bool a_role = t < 128;                    // A tile: one row (or 8 coalesced chunks) per thread
+      uint32_t gs = 0;                                     // stage counter over all tiles of this CTA
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const GemmTile tl = gemm_tile<BN>(g, tile, mtiles, ntiles);
+        for (int it = 0; it < tl.nk; ++it, ++gs) {
+          const int s = gs % G_STAGES;
+          if (gs >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((gs / G_STAGES - 1) & 1));
+          const int k0 = tl.kbeg + it * GK;
+          if (a_role) {
+            if (avec) g_load_tile_kcontig<GA_LBO, GA_HALF, NIMG, 128, GM>(sm.a[s], g.a, g.a_row_stride, tl.m0, g.m, GM, k0, tl.kend, t);
+            else g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, tl.m0 + t, tl.m0 + t < g.m, k0, tl.kend, t, false);
+          } else if (packed_b) {
+            constexpr uint32_t bytes = NIMG * GB_HALF;
+            tc::mbar_expect_tx(&sm.full[s], bytes);
+            tc::tma_bulk_g2s(sm.b[s], static_cast<const unsigned char*>(g.b_packed) + (size_t)(k0 / GK) * bytes, bytes, &sm.full[s]);
+            continue;                                 // (the expect_tx above is this thread's arrival)
+          } else {
+            const int tb = t - 128;
+            if (bvec) g_load_tile_kcontig<GB_LBO, GB_HALF, NIMG, 256, (GN >= 32 ? GN : 32)>(sm.b[s], g.b, g.b_row_stride, tl.n0, g.n, tl.n_mma, k0, tl.kend, tb);
+            else if (tb < tl.n_mma) g_load_row<GB_LBO, GB_HALF, NIMG>(sm.b[s], g.b, g.b_row_stride, g.b_k_stride, tl.n0 + tb, tl.n0 + tb < g.n, k0, tl.kend, tb, false);
+          }
+          tc::fence_async_smem();
+          tc::mbar_arrive(&sm.full[s]);
+        }
       }
     }
   } else if (warp == G_MMA_WARP) {
@@ -284,7 +357,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
     }
   } else {
     // =========================== epilogue: TMEM -> bias / activation / mask -> global ===========================
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const int q = warp & 3, half = warp >> 2;          // TMEM lane quadrant (rows 32 q ..), column half
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const bool cvec = (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(g.c) & 15) == 0 && (g.c_split_stride & 3) == 0;
     const bool mvec = g.mask_src && (g.mask_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask_src) & 15) == 0;
     uint32_t li = 0;
@@ -292,19 +366,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
       const GemmTile tl = gemm_tile<BN>(g, tile, mtiles, ntiles);
       const uint32_t buf = li & 1u;
       const uint32_t tacc = tmem + buf * (uint32_t)BN;
-      const int row = tl.m0 + warp * 32 + lane;
+      const int row = tl.m0 + q * 32 + lane;
       const bool row_ok = row < g.m;
+      const int nchunks = (tl.n_mma + 31) / 32, c_lo = half == 0 ? 0 : (nchunks + 1) / 2, c_hi = half == 0 ? (nchunks + 1) / 2 : nchunks;
       float* crow = g.c + (int64_t)tl.z * g.c_split_stride + (int64_t)row * g.ldc + tl.n0;
       const float* mrow = g.mask_src ? g.mask_src + (int64_t)row * g.mask_ld + tl.n0 : nullptr;
       // bias of this column tile -> shared memory (the per-column global loads were most of the epilogue's stall time)
-      asm volatile("bar.sync 1, 128;" ::: "memory");             // every epilogue warp is done with the previous tile's bias
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // every epilogue warp is done with the previous tile's bias
       if (g.bias)
-        for (int c = tid; c < BN; c += 128) sm.bias[c] = (c < tl.n_rem) ? g.bias[tl.n0 + c] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = tid; c < BN; c += G_EPI_THREADS) sm.bias[c] = (c < tl.n_rem) ? g.bias[tl.n0 + c] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       float ss = 0.f;
       tc::mbar_wait(&sm.accfull[buf], (uint32_t)((li >> 1) & 1));
       tc::tc_fence_after();
-      for (int c = 0; c < tl.n_mma; c += 32) {
+      if (c_lo >= c_hi) {                               // (narrow tiles: the second half has no columns)
+        tc::tc_fence_before();
+        tc::mbar_arrive(&sm.accfree[buf]);
+      }
+      for (int c = c_lo * 32; c < c_hi * 32; c += 32) {
         uint32_t v[32];
         if (tl.nk == 0) {
 #pragma unroll
@@ -319,7 +398,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0u; }
         }
-        if (c + 32 >= tl.n_mma) {                       // last accumulator read of this tile: hand the buffer back to the MMA thread
+        if (c + 32 >= c_hi * 32) {                      // last accumulator read of this warp: hand the buffer back to the MMA thread
           tc::tc_fence_before();
           tc::mbar_arrive(&sm.accfree[buf]);
         }
@@ -368,7 +447,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
           }
         }
       }
-      if (g.row_sumsq && row_ok) g.row_sumsq[row] = ss;
+      if (g.row_sumsq) {                                // combine the two column halves of a row
+        if (half == 1) sm.ss_part[q * 32 + lane] = ss;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && row_ok) g.row_sumsq[row] = ss + sm.ss_part[q * 32 + lane];
+      }
     }
   }
   // ---- teardown
