@@ -67,6 +67,22 @@ __device__ __forceinline__ void wd_wait(void* bar, uint32_t parity, int site, ui
 #ifndef MSACL_TC_NS
 #define MSACL_TC_NS(ID) 3
 #endif
+// Tiles per env warpgroup (TPW).  1: a warpgroup owns one tile and keeps its env state in registers for all K steps.
+// 2: a warpgroup alternates between two tiles -- while the MLP of one runs it integrates the other -- with the env
+// state parked in its global arrays between steps (L2-resident: the tiles in flight of all CTAs are ~30 MB) and the
+// logits handed over through a per-CTA global scratch area (no shared memory left for 2 NS tiles).  The quadrotor is
+// bound by slots x (env-phase latency + MLP latency), not by any pipe; doubling the tiles in flight without doubling
+// the env threads' registers is what TPW = 2 buys.
+// Measured (round 2, QuadTracking, 2^21 envs x 16 steps): TPW = 2 is NOT faster (16.2 ms vs 15.4 ms per launch).  With the
+// warpgroups free-running, three copies of the ~50 KB env phase stream through the 32 KB instruction cache at once (ncu:
+// icc hit rate 78 %, gcc instruction requests 93 % of peak, 33 % of the env-phase samples `no_instruction`); with the
+// batch wait below the fetches are shared (icc 96 %, gcc 50 %) but the twelve env warps then contend for issue slots and
+// the FP64 pipe (math-pipe throttle 1.8 warps per issue): every arrangement tried -- (NS, TPW) = (3,1) (3,2) (2,2) (2,3)
+// (4,1) -- lands within 5 % of 14 k cycles per tile-step, the SM's instruction throughput for this mix (~7.5 k useful
+// warp-instructions per sub-partition per tile-step at ~0.55 IPC).  Kept as a build option (MSACL_TC_TPW=2); default 1.
+#ifndef MSACL_TC_TPW
+#define MSACL_TC_TPW(ID) 1
+#endif
 constexpr int TCM = 128;            // envs per tile
 constexpr int TC_HID = 256;
 constexpr int KC2 = 32;             // K per A stage
@@ -89,9 +105,18 @@ template <> struct TcCfg<3> { static constexpr int THREADS = 768, ENV_REGS = 112
 template <> struct TcCfg<4> { static constexpr int THREADS = 896, ENV_REGS = 88, EPI_REGS = 56, MISC_REGS = 40, NB = 2; };    // launch 72*28 = 2016 = 16*88 + 8*56 + 4*40; the 4th slot's 8 KB come out of the W2 ring
 constexpr int W2P_BYTES = NCHB * 2 * B_HALF;   // 256 KB packed W2 (hi/lo k-step images)
 constexpr int W1P_BYTES = 2 * W1_HALF;
+// per-CTA global scratch behind the packed W2 image (TPW > 1): partial logits [tile slot][column half][8][128]
+constexpr int SCR_TILES = 8;
+constexpr int SCR_PER_TILE = 2 * 8 * TCM;
+constexpr int SCR_PER_CTA = SCR_TILES * SCR_PER_TILE;                  // 16384 floats = 64 KB
+constexpr bool tc_any_parked() {
+  return MSACL_TC_TPW(kVanderPol) > 1 || MSACL_TC_TPW(kPendulum) > 1 || MSACL_TC_TPW(kDuctedFan) > 1 || MSACL_TC_TPW(kTwoLink) > 1 ||
+         MSACL_TC_TPW(kSingleTrackCar) > 1 || MSACL_TC_TPW(kQuadTracking) > 1;
+}
+constexpr int64_t TC_SCRATCH_BYTES = tc_any_parked() ? (int64_t)kNumSMs * SCR_PER_CTA * 4 : 0;   // default build: none
 
 struct TcBars {
-  unsigned long long xfull[4], logits[4];
+  unsigned long long xfull[4], xfree[4], logits[8];
   unsigned long long h1full[2], h1free[2], h2full[2], h2free[2];   // per TMEM buffer
   unsigned long long afull[NCH], afree[NCH], bfull[NB_MAX], bfree[NB_MAX];
   uint32_t tmem_slot;
@@ -114,7 +139,7 @@ struct TcSmem {
   alignas(128) unsigned char bstage[NB][2 * B_HALF];     //  48 KB (box envs: 64 KB)
   alignas(128) unsigned char astage[NCH][2 * A_HALF];    // 128 KB
   alignas(128) unsigned char w1p[2 * W1H];               //  16 KB (box envs: 8 KB)
-  alignas(128) unsigned char xop[NS][2 * XH];            //   8 KB (4 KB) per slot; doubles as the slot's logits / partial sums
+  alignas(128) unsigned char xop[NS][2 * XH];            //   8 KB (4 KB) per env warpgroup; TPW == 1: doubles as the slot's logits
   alignas(128) unsigned char zeros[X2 ? 128 : W1_HALF / 2];   // shared all-zero second K block (box envs)
   alignas(16) float w3t[TC_HID * tc_w3_stride<ID>()];   // layer-3 weights transposed: [unit n][output j] (zero padded)
   alignas(16) float b2[TC_HID];
@@ -181,25 +206,36 @@ __global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, unsigned char* 
   }
 }
 
-template <int ID, int NS>
+template <int ID, int NS, int TPW>
 __global__ void __launch_bounds__(TcCfg<NS>::THREADS, 1)
 rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char* __restrict__ w1p_g,
-                  const unsigned char* __restrict__ w2p_g, int K, uint32_t step_base, int n_step, float reward_scale,
-                  float cost_scale, const float* __restrict__ eps, int deterministic, msacl_transitions_t out, double* stats) {
+                  const unsigned char* __restrict__ w2p_g, float* __restrict__ scratch, int K, uint32_t step_base, int n_step,
+                  float reward_scale, float cost_scale, const float* __restrict__ eps, int deterministic, msacl_transitions_t out,
+                  double* stats) {
   using E = Env<ID>;
   using S = TcSmem<ID, NS>;
   using CFG = TcCfg<NS>;
   constexpr int D = E::D, A = E::A, A2 = 2 * A;
+  constexpr int NT = NS * TPW;                 // tiles in flight per CTA ("group"); tile slot s belongs to warpgroup s % NS
+#ifdef MSACL_TC_FORCE_PARK
+  constexpr bool PARK = true;                  // (experiment: TPW = 1 scheduling with the TPW = 2 hand-overs)
+#else
+  constexpr bool PARK = TPW > 1;
+#endif
+  // env state parked in global memory between steps, logits through global scratch
+  static_assert(NT <= SCR_TILES && A2 <= 8, "scratch layout");
   constexpr int TC_THREADS = CFG::THREADS, NB = S::NB, XH = S::XH, W1H = S::W1H, W3S = tc_w3_stride<ID>();
   constexpr bool X2 = S::X2;
   constexpr int W_EPI1 = 4 * NS, W_MMA = 4 * NS + 8, W_TMA = 4 * NS + 9;
   static_assert(D < 16, "layer-1 K block holds obs + bias column");
-  static_assert(A2 * TCM * 4 <= XH && ((A2 + 1) / 2) * 2 * TCM * 4 <= XH, "logits and partial sums alias the two halves of the X-operand region");
+  static_assert(A2 * TCM * 4 <= XH && ((A2 + 1) / 2) * 2 * TCM * 4 <= XH, "logits and partial sums alias the two halves of the X-operand region (TPW == 1)");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  auto logits_of = [&](int s) { return reinterpret_cast<float*>(sm.xop[s]); };              // [2A][128] f32, first half of the region
-  auto partial_of = [&](int s) { return reinterpret_cast<float*>(sm.xop[s] + XH); };       // epilogue-2 partial sums, second half
+  // TPW == 1: a slot's logits live in its X-operand region (free between layer 1 and the next write_xop);
+  // TPW > 1: in this CTA's global scratch (the X region is shared by the warpgroup's tiles)
+  float* const scr = PARK ? scratch + (size_t)blockIdx.x * SCR_PER_CTA : nullptr;
+  auto logits_of = [&](int s) { return PARK ? scr + s * SCR_PER_TILE : reinterpret_cast<float*>(sm.xop[s]); };   // [2A][128] f32
 
   // ---- one-time setup
   // W1|b1 images: the packed global buffer always holds both K blocks per image; box envs keep only the first
@@ -213,7 +249,8 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   if (tid < 8) sm.b3[tid] = tid < A2 ? actor.b3[tid] : 0.f;
   if (tid == 0) {
     TcBars& b = sm.bars;
-    for (int s = 0; s < NS; ++s) { tc::mbar_init(&b.xfull[s], TCM); tc::mbar_init(&b.logits[s], TCM); }
+    for (int s = 0; s < NS; ++s) { tc::mbar_init(&b.xfull[s], TCM); tc::mbar_init(&b.xfree[s], 1); }
+    for (int s = 0; s < NT; ++s) tc::mbar_init(&b.logits[s], PARK ? 2 * TCM : TCM);   // PARK: both column halves deliver
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&b.h1full[i], 1); tc::mbar_init(&b.h1free[i], 2 * TCM);     // drained by all 8 epilogue warps
       tc::mbar_init(&b.h2full[i], 1); tc::mbar_init(&b.h2free[i], 2 * TCM);
@@ -230,42 +267,65 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   const uint32_t tmem = sm.bars.tmem_slot;     // buffer b of tile-step t (b = t & 1) = columns [256 b, 256 b + 256)
 
   const int64_t num_tiles = (st.n + TCM - 1) / TCM;
-  const int64_t num_pairs = (num_tiles + NS - 1) / NS;      // "pair" = group of NS tiles in flight
-  auto tiles_in_pair = [&](int64_t pair) { return (int)((num_tiles - NS * pair) < NS ? (num_tiles - NS * pair) : NS); };
+  const int64_t num_pairs = (num_tiles + NT - 1) / NT;      // "pair" = group of NT tiles in flight
+  auto tiles_in_pair = [&](int64_t pair) { return (int)((num_tiles - NT * pair) < NT ? (num_tiles - NT * pair) : NT); };
+  // X operands are written per warpgroup: group pi (all but the last are full), step k, tile slot s -> running index
+  auto tiles_of_wg = [&](int w, int nt) { return nt > w ? (nt - w - 1) / NS + 1 : 0; };
+  auto x_index = [&](uint32_t pi, int k, int s, int nt) { return pi * (uint32_t)(TPW * K) + (uint32_t)(k * tiles_of_wg(s % NS, nt) + s / NS); };
 
   if (warp < W_EPI1) {
     // =========================== env warps ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CFG::ENV_REGS));
-    const int s = warp >> 2;                 // tile slot of this env warpgroup
+#ifdef MSACL_TC_COLOC
+    // (experiment) NS == 4: the four warps of an env warpgroup share one SM sub-partition (warp % 4), so they run the
+    // same instruction stream through the same L0 instruction cache
+    const int w = NS == 4 ? (warp & 3) : (warp >> 2);
+    const int r = NS == 4 ? ((warp >> 2) * 32 + lane) : (tid & (TCM - 1));
+#else
+    const int w = warp >> 2;                 // env warpgroup: tile slots w, w + NS, ...
     const int r = tid & (TCM - 1);
-    uint32_t lcount = 0;
+#endif
+    uint32_t xcount = 0;                     // X operands this warpgroup has written
+    uint32_t lcount = 0;                     // logits deliveries each of its tile slots has consumed
     float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_term = 0.f, st_trunc = 0.f;
     auto write_xop = [&](const float* obs, bool valid) {
       float v[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] = (k < D) ? (valid ? obs[k < D ? k : 0] : 0.f) : (k == D ? 1.f : 0.f);
+      // (TPW > 1) the region is shared by the warpgroup's tiles: layer 1 of the previous X operand must have read it
+      if (PARK && xcount > 0) TC_WAIT(&sm.bars.xfree[w], (xcount - 1) & 1, 14, xcount);
+      ++xcount;
 #pragma unroll
       for (int kb = 0; kb < (X2 ? 2 : 1); ++kb) {
-        float w[8];
+        float wv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = v[kb * 8 + j];
+        for (int j = 0; j < 8; ++j) wv[j] = v[kb * 8 + j];
         uint4 hi, lo;
-        split8(w, hi, lo);
-        *reinterpret_cast<uint4*>(sm.xop[s] + kb * A_LBO + r * 16) = hi;
-        *reinterpret_cast<uint4*>(sm.xop[s] + XH + kb * A_LBO + r * 16) = lo;
+        split8(wv, hi, lo);
+        *reinterpret_cast<uint4*>(sm.xop[w] + kb * A_LBO + r * 16) = hi;
+        *reinterpret_cast<uint4*>(sm.xop[w] + XH + kb * A_LBO + r * 16) = lo;
       }
       tc::fence_async_smem();
-      tc::mbar_arrive(&sm.bars.xfull[s]);
+      tc::mbar_arrive(&sm.bars.xfull[w]);
     };
     for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-      const int64_t tile = NS * pair + s;
-      if (tile >= num_tiles) break;
-      const int64_t gi = tile * TCM + r;
-      const bool owner = gi < st.n;
+      const int nt = tiles_in_pair(pair);
+      if (w >= nt) break;
       EnvRegs<ID> e;
-      if (owner) e.load(st, gi);
-      write_xop(e.obs(), owner);
+      // first observations of this group's tiles
+#pragma unroll 1
+      for (int s = w; s < nt; s += NS) {
+        const int64_t gi = (NT * pair + s) * TCM + r;
+        const bool owner = gi < st.n;
+        if (owner) e.load(st, gi);
+        write_xop(e.obs(), owner);
+      }
       for (int k = 0; k < K; ++k) {
+#pragma unroll 1
+        for (int s = w; s < nt; s += NS) {
+        const int64_t gi = (NT * pair + s) * TCM + r;
+        const bool owner = gi < st.n;
+        if (PARK && owner) e.load(st, gi);     // issued in front of the logits wait: the L2 round trip hides behind it
         // the action noise of this step does not depend on the logits: draw it while the tile's MLP is still running
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (owner && !deterministic) {
@@ -279,15 +339,31 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
 #ifdef MSACL_TC_TIMING
         const long long t_w0 = clock64();
 #endif
-        TC_WAIT(&sm.bars.logits[s], lcount & 1, 1, lcount);
-        ++lcount;
-        // the logits of this slot were written into its X-operand region (free between layer 1 and the next
-        // write_xop): take them into registers, then a slot-wide barrier so that no thread of the slot can overwrite
-        // them with its next observation before every thread has read its own
-        float lg[A2];
+        if constexpr (PARK) {
+          // wait for the logits of ALL tiles of this batch (slots sub*NS .. sub*NS + NS - 1), so that the env warpgroups run
+          // the (long, straight-line) env phase in step and share its instruction-cache lines: one warpgroup per tile
+          // streaming ~50 KB of code on its own saturates the GPC-level instruction cache (ncu: gcc instruction
+          // requests 81-93 % of peak, icc hit rate = the 75 % that the four warps of one warpgroup share)
+          const int s0 = s - w;
 #pragma unroll
-        for (int j = 0; j < A2; ++j) lg[j] = logits_of(s)[j * TCM + r];
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory");
+          for (int j = 0; j < NS; ++j)
+            if (s0 + j < nt) TC_WAIT(&sm.bars.logits[s0 + j], lcount & 1, 1, lcount);
+        } else {
+          TC_WAIT(&sm.bars.logits[s], lcount & 1, 1, lcount);
+        }
+        float lg[A2];
+        if constexpr (PARK) {
+          // written with st.global.cg by the epilogue warps of this CTA before their (release) arrive on the barrier
+#pragma unroll
+          for (int j = 0; j < A2; ++j) lg[j] = __ldcg(logits_of(s) + j * TCM + r) + __ldcg(logits_of(s) + SCR_PER_TILE / 2 + j * TCM + r);
+        } else {
+          // the logits of this slot were written into its X-operand region (free between layer 1 and the next
+          // write_xop): take them into registers, then a slot-wide barrier so that no thread of the slot can overwrite
+          // them with its next observation before every thread has read its own
+#pragma unroll
+          for (int j = 0; j < A2; ++j) lg[j] = logits_of(s)[j * TCM + r];
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
+        }
 #ifdef MSACL_TC_TIMING
         const long long t_w1 = clock64();
 #endif
@@ -358,6 +434,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           if (out.done) out.done[row] = done ? 1 : 0;
           if (out.logp) out.logp[row] = logp;
           if (out.emit) out.emit[row] = emit ? 1 : 0;
+          if (PARK) e.store(st, gi);
         } else if (k + 1 < K) {
           write_xop(e.obs(), false);
         }
@@ -369,8 +446,13 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           atomicAdd(&stats[7], 1.0);
         }
 #endif
+        }
+        ++lcount;
       }
-      if (owner) e.store(st, gi);
+      if constexpr (!PARK) {
+        const int64_t gi = (NT * pair + w) * TCM + r;
+        if (gi < st.n) e.store(st, gi);
+      }
     }
     if (stats) {
       float v[5] = {st_ep, st_ret, st_len, st_term, st_trunc};
@@ -470,26 +552,42 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         }
       }
       // combine the two column halves: rows of quadrant q are shared by warps (q, half 0) and (q, half 1)
-      float* part = partial_of(s);
-      if (h == 1) {
+      // combine the two column halves: rows of quadrant q are shared by warps (q, half 0) and (q, half 1)
+      if constexpr (PARK) {
+        // both halves hand their partial logits to the slot's env warps through this CTA's global scratch (L2-only stores,
+        // ordered by the release-arrive below); the env thread adds them (half 0 + half 1, the order of the TPW == 1 path)
+        float* lgs = logits_of(s) + h * (SCR_PER_TILE / 2);
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
           float lo, hi;
           unpack2(acc[p], lo, hi);
-          part[(2 * p) * TCM + r] = lo;
-          part[(2 * p + 1) * TCM + r] = hi;
-        }
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(4 + q) : "memory");
-      if (h == 0) {
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          float lo, hi;
-          unpack2(acc[p], lo, hi);
-          logits_of(s)[(2 * p) * TCM + r] = lo + part[(2 * p) * TCM + r];
-          if (2 * p + 1 < A2) logits_of(s)[(2 * p + 1) * TCM + r] = hi + part[(2 * p + 1) * TCM + r];
+          __stcg(&lgs[(2 * p) * TCM + r], lo);
+          if (2 * p + 1 < A2) __stcg(&lgs[(2 * p + 1) * TCM + r], hi);
         }
         tc::mbar_arrive(&sm.bars.logits[s]);
+      } else {
+        float* part = reinterpret_cast<float*>(sm.xop[s] + XH);      // second half of the slot's X-operand region
+        float* lgs = logits_of(s);
+        if (h == 1) {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            float lo, hi;
+            unpack2(acc[p], lo, hi);
+            part[(2 * p) * TCM + r] = lo;
+            part[(2 * p + 1) * TCM + r] = hi;
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(4 + q) : "memory");
+        if (h == 0) {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            float lo, hi;
+            unpack2(acc[p], lo, hi);
+            lgs[(2 * p) * TCM + r] = lo + part[(2 * p) * TCM + r];
+            if (2 * p + 1 < A2) lgs[(2 * p + 1) * TCM + r] = hi + part[(2 * p + 1) * TCM + r];
+          }
+          tc::mbar_arrive(&sm.bars.logits[s]);
+        }
       }
       if (timer) TC_ACC(12, t_b);                     // epi2: compute
     };
@@ -500,7 +598,11 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         for (int s = 0; s < nt; ++s, ++ts) {
           if (ts == 0) epi1(0u);
           const bool has_next = !(s + 1 == nt && k + 1 == K && pair + (int64_t)gridDim.x >= num_pairs);
-          if (nt > 1) {
+          // PARK: the env warpgroups wait for the logits of a whole batch of NS tiles, so the X operand of the successor
+          // depends on THIS tile-step's logits when the group has a single batch, and at the last tile-step of a group
+          // (the first X operand of the next group is written after the warpgroup's last env step)
+          const bool epi2_first = PARK ? (nt <= NS || (s + 1 == nt && k + 1 == K)) : (nt <= 1);
+          if (!epi2_first) {
             if (has_next) epi1(ts + 1);
             epi2(ts, s);
           } else {
@@ -532,12 +634,12 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         if (t1 >= 2) TC_WAIT(&sm.bars.h2free[t1 & 1], ((t1 >> 1) - 1) & 1, 10, t1);   // epilogue 2 of tile-step t1-2 has drained the buffer
         TC_ACC(17, t_h);                              // MMA: wait for a free TMEM buffer
         TC_T0(t_x);
-        TC_WAIT(&sm.bars.xfull[s], xn & 1, 7, t1);
+        TC_WAIT(&sm.bars.xfull[s % NS], xn & 1, 7, t1);
         TC_ACC(13, t_x);                              // MMA: wait for X
         tc::tc_fence_after();
         const uint32_t tmem_b = tmem + (t1 & 1u) * 256u;
         // K-block stride: the next 8 K columns follow in place (quadrotor) or are the shared zero block (box envs)
-        const uint32_t xbase = tc::smem_u32(sm.xop[s]), zbase = tc::smem_u32(sm.zeros);
+        const uint32_t xbase = tc::smem_u32(sm.xop[s % NS]), zbase = tc::smem_u32(sm.zeros);
         const uint64_t dw1 = tc::make_smem_desc(w1base, X2 ? B_LBO : zbase - w1base, SBO);
         const uint64_t dw2 = tc::make_smem_desc(w1base + W1H, X2 ? B_LBO : zbase - (w1base + W1H), SBO);
         const uint64_t dx1 = tc::make_smem_desc(xbase, X2 ? A_LBO : zbase - xbase, SBO);
@@ -546,6 +648,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         tc::umma_bf16(tmem_b, dx1, dw2, idesc, 1u);
         tc::umma_bf16(tmem_b, dx2, dw1, idesc, 1u);
         tc::umma_commit(&sm.bars.h1full[t1 & 1]);
+        if (PARK) tc::umma_commit(&sm.bars.xfree[s % NS]);     // the warpgroup may write its next X operand
       };
       uint32_t ts = 0, pi = 0;                        // tile-step counter, local group counter
       for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++pi) {
@@ -561,11 +664,11 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
             int64_t pair2 = pair;
             uint32_t pi2 = pi;
             if (s2 == nt) { s2 = 0; if (++k2 == K) { k2 = 0; pair2 += gridDim.x; ++pi2; } }
-            const uint32_t xn2 = pi2 * (uint32_t)K + (uint32_t)k2, t2 = ts + 1;
             bool next_pending = pair2 < num_pairs;
+            const uint32_t xn2 = x_index(pi2, k2, s2, (pair2 == pair || !next_pending) ? nt : tiles_in_pair(pair2)), t2 = ts + 1;
             auto try_next = [&]() {
               if (next_pending && (t2 < 2 || tc::mbar_test(&sm.bars.h2free[t2 & 1], ((t2 >> 1) - 1) & 1)) &&
-                  tc::mbar_test(&sm.bars.xfull[s2], xn2 & 1)) {
+                  tc::mbar_test(&sm.bars.xfull[s2 % NS], xn2 & 1)) {
                 issue_l1(s2, xn2, t2);
                 next_pending = false;
               }
@@ -644,7 +747,7 @@ extern "C" int msacl_rollout_tc_set_max_ctas(int32_t max_ctas) {
 
 extern "C" int msacl_tc_pack_bytes(int64_t* w1p_bytes, int64_t* w2p_bytes) {
   if (w1p_bytes) *w1p_bytes = W1P_BYTES;
-  if (w2p_bytes) *w2p_bytes = W2P_BYTES;
+  if (w2p_bytes) *w2p_bytes = W2P_BYTES + TC_SCRATCH_BYTES;     // packed W2 images + the rollout kernel's per-CTA scratch
   return MSACL_OK;
 }
 
@@ -667,16 +770,20 @@ extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_a
       set_error("rollout_fused_tc: transition obs/obs2/act rows must be aligned to their vector width (16 B if the row length is a multiple of 4 floats, 8 B if even)");
       return MSACL_ERR_BAD_ARG;
     }
-    constexpr int NS = MSACL_TC_NS(ID);      // tile slots in flight
+    constexpr int NS = MSACL_TC_NS(ID);      // env warpgroups
+    constexpr int TPW = MSACL_TC_TPW(ID);    // tiles per warpgroup: NS * TPW tiles in flight per CTA
     static_assert(sizeof(TcSmem<ID, NS>) + 128 <= 232448, "shared-memory layout exceeds the 227 KB per-CTA limit");
-    const int64_t groups = (tiles + NS - 1) / NS;
+    const int64_t groups = (tiles + NS * TPW - 1) / (NS * TPW);
     const int64_t cap = g_tc_max_ctas > 0 ? g_tc_max_ctas : kNumSMs;
     const unsigned grid = (unsigned)(groups < cap ? groups : cap);
     const size_t smem = sizeof(TcSmem<ID, NS>) + 128;
-    auto kern = rollout_tc_kernel<ID, NS>;
+    auto kern = rollout_tc_kernel<ID, NS, TPW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("rollout_fused_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
-    kern<<<grid, TcCfg<NS>::THREADS, smem, (cudaStream_t)stream>>>(*st, *actor, (const unsigned char*)w1p, (const unsigned char*)w2p, K,
+    // the scratch area behind the W2 images is written by the kernel (the ABI hands the buffer over as const because the
+    // images are; one launch at a time may use a given buffer)
+    float* scratch = reinterpret_cast<float*>(const_cast<unsigned char*>((const unsigned char*)w2p) + W2P_BYTES);
+    kern<<<grid, TcCfg<NS>::THREADS, smem, (cudaStream_t)stream>>>(*st, *actor, (const unsigned char*)w1p, (const unsigned char*)w2p, scratch, K,
                                                                   step_base, n_step, reward_scale, cost_scale, eps, deterministic, *out, stats);
   });
   return check_launch("rollout_fused_tc");

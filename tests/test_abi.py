@@ -74,4 +74,4 @@ def test_error_codes_without_gpu_work():
     assert b"n_step must be <= 32" in lib.msacl_last_error()
     assert lib.msacl_action_noise(0, 0, 8, 5, 0, None, None) == -2
     n1, n2 = C.c_int64(0), C.c_int64(0)
-    assert lib.msacl_tc_pack_bytes(C.byref(n1), C.byref(n2)) == 0 and (n1.value, n2.value) == (16384, 262144)
+    assert lib.msacl_tc_pack_bytes(C.byref(n1), C.byref(n2)) == 0 and n1.value == 16384 and n2.value in (262144, 262144 + 148 * 65536)   # + scratch in MSACL_TC_TPW=2 builds
