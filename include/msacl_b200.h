@@ -154,6 +154,18 @@ int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_actor_t* act
                            const float* eps, int32_t deterministic, const msacl_transitions_t* out, double* stats,
                            void* stream);
 
+/* One BaseSampler._n_step (RL/trainer/sampler/base.py:118-163,220) for policy outputs computed by the caller: the rollout
+ * path for policies the fused kernels are not specialised for (the reference builds MLPs of any depth, width and
+ * activation, RL/apprfunc/mlp.py:18-33; the layers are then msacl_gemm_tc calls).
+ *   logits [n][2*act_dim] = mean || log_std of StochaPolicy.forward (mlp.py:132-136, before the clamp / exp)
+ *   step   = global step index (keys the Philox action-noise stream, like step_base + k of the fused kernels)
+ *   out    = pointers to the [n][.] slices of THIS step; eps [n][act_dim] optional explicit N(0,1) draws
+ * Sampling, clip, env step, reward / cost scaling, same-step autoreset, episode statistics and n-step run / emit
+ * bookkeeping are those of msacl_rollout_fused (same arithmetic, same random streams). */
+int msacl_rollout_step(const msacl_env_state_t* st, const float* logits, float min_log_std, float max_log_std, uint32_t step,
+                       int32_t n_step, float reward_scale, float cost_scale, const float* eps, int32_t deterministic,
+                       const msacl_transitions_t* out, double* stats, void* stream);
+
 /* Diagnostic: out[i] = NormalizeOrientMatrix(in[i]) for n row-major 3x3 float32 matrices through the device polar
  * routine of the QuadTracking step (RL/env/QuadTracking.py:308-315), including its det < 0 branch (:312-314), which the
  * dynamics cannot reach.  theta2 = (h |Omega|)^2 hint (>= 0.02 -> a third Newton sweep). */

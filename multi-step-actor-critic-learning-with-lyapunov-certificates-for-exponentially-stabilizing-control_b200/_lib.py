@@ -68,6 +68,8 @@ SIGNATURES = {
     "msacl_tc_pack_actor": (C.c_int, [C.POINTER(Actor), C.c_int32, vp, vp, vp]),
     "msacl_rollout_fused_tc": (C.c_int, [C.POINTER(EnvState), C.POINTER(Actor), vp, vp, C.c_int32, C.c_uint32, C.c_int32,
                                          C.c_float, C.c_float, vp, C.c_int32, C.POINTER(Transitions), vp, vp]),
+    "msacl_rollout_step": (C.c_int, [C.POINTER(EnvState), vp, C.c_float, C.c_float, C.c_uint32, C.c_int32, C.c_float, C.c_float, vp,
+                                     C.c_int32, C.POINTER(Transitions), vp, vp]),
     "msacl_action_noise": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32, vp, vp]),
     "msacl_window_store_scratch_elems": (C.c_int64, [C.c_int32, C.c_int64]),
     "msacl_selftest_quad_polar": (C.c_int, [vp, vp, C.c_int64, C.c_float, vp]),

@@ -25,11 +25,15 @@ namespace msacl {
 constexpr int GM = 128, GN = 256, GK = 32;  // GN = widest column tile (template BN: 256, or 64 for small row counts)
 constexpr int GA_HALF = GM * GK * 2;       // 8 KB: one bf16 image of an A stage
 constexpr int GA_LBO = GM * 16, G_SBO = 128;
-constexpr int G_LOADERS = 384;             // 12 loader warps: threads 0..127 own the A tile, 128..383 the B tile
-constexpr int G_EPI_WARPS = 8;             // two per TMEM lane quadrant (quadrant = warp & 3), each owning half of the columns
-constexpr int G_EPI_THREADS = 32 * G_EPI_WARPS;
-constexpr int G_MMA_WARP = G_EPI_WARPS + G_LOADERS / 32;
-constexpr int G_THREADS = 32 * (G_MMA_WARP + 1);   // warps 0-7 epilogue, 8-19 loaders, 20 MMA issuer
+// 17 warps (five per SM sub-partition at most: 96 registers per thread).  Warp 16 issues the UMMAs; the other sixteen are
+// split by operand mode:
+//   streamed weights (pre-packed B by bulk copies, k-contiguous A):  warps 0-7 epilogue (two per TMEM lane quadrant, each
+//       owning half of the columns), warps 8-15 convert the A tile (256 threads, software-pipelined);
+//   converted B (weight gradient, un-packed weights):                warps 0-3 epilogue, warps 4-15 loaders (threads
+//       0..127 of the group own the A tile, 128..383 the B tile).
+constexpr int G_LOADERS = 384;
+constexpr int G_MMA_WARP = 16;
+constexpr int G_THREADS = 32 * (G_MMA_WARP + 1);
 
 template <int NIMG, int BN, int STAGES>
 struct GemmSmem {
@@ -202,7 +206,9 @@ __device__ __forceinline__ GemmTile gemm_tile(const msacl_gemm_t& g, int64_t til
   return t;
 }
 
-template <int NIMG, int BN, int STAGES>
+// STREAMED (BN = 256 only): the host found a pre-packed B operand behind a k-contiguous A -- its own instantiation, so that
+// the software-pipelined A loader does not share a register allocation with the converting loaders of the other mode.
+template <int NIMG, int BN, int STAGES, bool STREAMED>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
   constexpr int G_STAGES = STAGES;
   constexpr int GN = BN, GB_HALF = BN * GK * 2, GB_LBO = BN * 16;
@@ -214,15 +220,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
   const int64_t total_tiles = (int64_t)mtiles * ntiles * g.split_k;
 
   // packed B (BN = 256 only): the B tile arrives by one bulk copy per stage (expect_tx arrival of the issuing thread)
-  const bool packed_b = BN == 256 && g.b_packed != nullptr;
-  const bool avec0 = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0;
-  // loader roles (t = thread index within the 384 loader threads): A tile by threads [0, a_threads) -- 256 of them when the B
-  // tile needs no conversion (packed) and A is k-contiguous, else 128; B tile by threads [128, 384), or by ONE bulk-copy issuer
-  const int a_threads = (packed_b && avec0) ? 256 : 128;
-  const int b_issuer = a_threads;                      // packed mode: the thread right after the A group issues the bulk copies
+  const bool packed_b = STREAMED || (BN == 256 && g.b_packed != nullptr);
+  constexpr bool streamed = STREAMED;                  // role split (see G_THREADS)
+  const int epi_warps = streamed ? 8 : 4, epi_threads = 32 * epi_warps;
+  // arrivals per full stage: streamed -- 256 A threads + the bulk-copy expect_tx of A thread 0; packed B behind a strided A --
+  // 128 A threads + the issuer; else all 384 loaders
   if (tid == 0) {
-    for (int s = 0; s < G_STAGES; ++s) { tc::mbar_init(&sm.full[s], packed_b ? a_threads + 1 : G_LOADERS); tc::mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&sm.accfull[b], 1); tc::mbar_init(&sm.accfree[b], G_EPI_THREADS); }
+    for (int s = 0; s < G_STAGES; ++s) { tc::mbar_init(&sm.full[s], streamed ? 256 + 1 : (packed_b ? 128 + 1 : G_LOADERS)); tc::mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&sm.accfull[b], 1); tc::mbar_init(&sm.accfree[b], epi_threads); }
     tc::mbar_fence_init();
   }
   if (warp == G_MMA_WARP) tc::tmem_alloc(&sm.tmem_slot, TMEM_COLS);
@@ -231,14 +236,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
   tc::tc_fence_after();
   const uint32_t tmem = sm.tmem_slot;
 
-  if (warp >= G_EPI_WARPS && warp < G_MMA_WARP) {
+  if (warp >= epi_warps && warp < G_MMA_WARP) {
     // =========================== loaders: FP32 global -> split-bf16 operand images ===========================
     // threads 0..127 of the loader group own the A tile (128 rows), threads 128..383 the B tile (<= 256 rows): one row (or
     // 8 coalesced float4 chunks) per thread per stage, so a stage costs one global round trip.
-    const int t = tid - G_EPI_THREADS;
-    const bool avec = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0;
-    const bool bvec = g.b_k_stride == 1 && (g.b_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0;
-    if (avec && packed_b && t < a_threads) {
+    const int t = tid - epi_threads;
+    if constexpr (streamed) {
       // ---- A tile, k-contiguous, many row tiles (packed B): software-pipelined -- the global loads of stage i + 1 (possibly the next tile's first
       //      stage) are in flight while stage i is converted and stored, so a stage no longer costs a full DRAM round trip
       //      per loader thread (ncu: 74 % of the loader samples were long-scoreboard stalls)
@@ -257,16 +260,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
         ok = tl_id < total_tiles;
       };
       fetch(tile, tl, it, have, (int64_t)blockIdx.x, 0, tl, true);
-      float4 cur[8], nxt[8];
-      auto load = [&](float4 (&v)[8], const GemmTile& c, int i_) {
-        if (a_threads == 256) {
-          float4 w[4];
-          g_kcontig_load<256, GM>(w, g.a, g.a_row_stride, c.m0, g.m, GM, c.kbeg + i_ * GK, c.kend, t);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) v[q] = w[q];
-        } else {
-          g_kcontig_load<128, GM>(v, g.a, g.a_row_stride, c.m0, g.m, GM, c.kbeg + i_ * GK, c.kend, t);
-        }
+      float4 cur[4], nxt[4];
+      auto load = [&](float4 (&v)[4], const GemmTile& c, int i_) {
+        g_kcontig_load<256, GM>(v, g.a, g.a_row_stride, c.m0, g.m, GM, c.kbeg + i_ * GK, c.kend, t);
       };
       if (have) load(cur, tl, it);
       uint32_t gs = 0;
@@ -275,22 +271,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
         if (nhave) load(nxt, ntl, nit);
         const int s = gs % G_STAGES;
         if (gs >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((gs / G_STAGES - 1) & 1));
-        if (a_threads == 256) {
-          float4 w[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) w[q] = cur[q];
-          g_kcontig_store<GA_LBO, GA_HALF, NIMG, 256, GM>(sm.a[s], w, GM, t);
-        } else {
-          g_kcontig_store<GA_LBO, GA_HALF, NIMG, 128, GM>(sm.a[s], cur, GM, t);
+        if (t == 0) {                                   // the stage's B tile: one bulk copy of the pre-packed images
+          constexpr uint32_t bytes = NIMG * GB_HALF;
+          tc::mbar_expect_tx(&sm.full[s], bytes);
+          tc::tma_bulk_g2s(sm.b[s], static_cast<const unsigned char*>(g.b_packed) + (size_t)((tl.kbeg + it * GK) / GK) * bytes, bytes, &sm.full[s]);
         }
+        g_kcontig_store<GA_LBO, GA_HALF, NIMG, 256, GM>(sm.a[s], cur, GM, t);
         tc::fence_async_smem();
         tc::mbar_arrive(&sm.full[s]);
         ++gs;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
         tile = ntile; tl = ntl; it = nit; have = nhave;
       }
-    } else if (t < 128 || (!packed_b && t >= 128) || (packed_b && t == b_issuer)) {
+    } else if (t < 128 || !packed_b || t == 128) {    // (packed B behind a strided A: thread 128 issues the bulk copies)
+      const bool avec = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0;
+      const bool bvec = g.b_k_stride == 1 && (g.b_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0;
       const bool a_role = t < 128;                    // A tile: one row (or 8 coalesced chunks) per thread
       uint32_t gs = 0;                                     // stage counter over all tiles of this CTA
       for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -357,7 +353,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
     }
   } else {
     // =========================== epilogue: TMEM -> bias / activation / mask -> global ===========================
-    const int q = warp & 3, half = warp >> 2;          // TMEM lane quadrant (rows 32 q ..), column half
+    const int q = warp & 3, half = warp >> 2;          // TMEM lane quadrant (rows 32 q ..), column half (streamed mode: two halves)
+    const bool two_halves = epi_warps == 8;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const bool cvec = (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(g.c) & 15) == 0 && (g.c_split_stride & 3) == 0;
     const bool mvec = g.mask_src && (g.mask_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask_src) & 15) == 0;
@@ -368,14 +365,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
       const uint32_t tacc = tmem + buf * (uint32_t)BN;
       const int row = tl.m0 + q * 32 + lane;
       const bool row_ok = row < g.m;
-      const int nchunks = (tl.n_mma + 31) / 32, c_lo = half == 0 ? 0 : (nchunks + 1) / 2, c_hi = half == 0 ? (nchunks + 1) / 2 : nchunks;
+      const int nchunks = (tl.n_mma + 31) / 32, c_mid = two_halves ? (nchunks + 1) / 2 : nchunks;
+      const int c_lo = half == 0 ? 0 : c_mid, c_hi = half == 0 ? c_mid : nchunks;
       float* crow = g.c + (int64_t)tl.z * g.c_split_stride + (int64_t)row * g.ldc + tl.n0;
       const float* mrow = g.mask_src ? g.mask_src + (int64_t)row * g.mask_ld + tl.n0 : nullptr;
       // bias of this column tile -> shared memory (the per-column global loads were most of the epilogue's stall time)
-      asm volatile("bar.sync 1, 256;" ::: "memory");             // every epilogue warp is done with the previous tile's bias
+      asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");   // every epilogue warp is done with the previous tile's bias
       if (g.bias)
-        for (int c = tid; c < BN; c += G_EPI_THREADS) sm.bias[c] = (c < tl.n_rem) ? g.bias[tl.n0 + c] : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = tid; c < BN; c += epi_threads) sm.bias[c] = (c < tl.n_rem) ? g.bias[tl.n0 + c] : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
       float ss = 0.f;
       tc::mbar_wait(&sm.accfull[buf], (uint32_t)((li >> 1) & 1));
       tc::tc_fence_after();
@@ -447,10 +445,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
           }
         }
       }
-      if (g.row_sumsq) {                                // combine the two column halves of a row
-        if (half == 1) sm.ss_part[q * 32 + lane] = ss;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0 && row_ok) g.row_sumsq[row] = ss + sm.ss_part[q * 32 + lane];
+      if (g.row_sumsq) {
+        if (two_halves) {                               // combine the two column halves of a row
+          if (half == 1) sm.ss_part[q * 32 + lane] = ss;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (half == 0 && row_ok) g.row_sumsq[row] = ss + sm.ss_part[q * 32 + lane];
+        } else if (row_ok) {
+          g.row_sumsq[row] = ss;
+        }
       }
     }
   }
@@ -521,10 +523,11 @@ extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
   auto set_attr = [&](auto kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
   };
-#define MSACL_GEMM_VARIANTS(X) X(2, 256, 4) X(3, 256, 3) X(2, 128, 4) X(3, 128, 4) X(2, 64, 4) X(3, 64, 4)
+#define MSACL_GEMM_VARIANTS(X) X(2, 256, 4, false) X(3, 256, 3, false) X(2, 256, 4, true) X(3, 256, 3, true) X(2, 128, 4, false) X(3, 128, 4, false) \
+  X(2, 64, 4, false) X(3, 64, 4, false)
   if (!attr_set) {
     bool ok = true;
-#define X(NI, BN_, ST) ok = ok && set_attr(gemm_tc_kernel<NI, BN_, ST>, sizeof(GemmSmem<NI, BN_, ST>) + 128);
+#define X(NI, BN_, ST, SM_) ok = ok && set_attr(gemm_tc_kernel<NI, BN_, ST, SM_>, sizeof(GemmSmem<NI, BN_, ST>) + 128);
     MSACL_GEMM_VARIANTS(X)
 #undef X
     if (!ok) { set_error("gemm_tc: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"); return MSACL_ERR_CUDA; }
@@ -532,8 +535,10 @@ extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int nimg = g->precision == 3 ? 2 : 3;
-#define X(NI, BN_, ST) \
-  if (nimg == NI && bn == BN_) gemm_tc_kernel<NI, BN_, ST><<<grid, G_THREADS, sizeof(GemmSmem<NI, BN_, ST>) + 128, st>>>(*g);
+  // streamed mode: pre-packed weights (BN = 256) behind a k-contiguous, 16-byte aligned A operand
+  const bool streamed = bn == 256 && g->b_packed && g->a_k_stride == 1 && (g->a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g->a) & 15) == 0;
+#define X(NI, BN_, ST, SM_) \
+  if (nimg == NI && bn == BN_ && streamed == SM_) gemm_tc_kernel<NI, BN_, ST, SM_><<<grid, G_THREADS, sizeof(GemmSmem<NI, BN_, ST>) + 128, st>>>(*g);
   MSACL_GEMM_VARIANTS(X)
 #undef X
 #undef MSACL_GEMM_VARIANTS

@@ -4,6 +4,8 @@
 //   advantage :392-400.  One warp per window: lane k owns step k (n <= 32), the clipped
 //   importance-ratio cumprod is a warp scan and the lambda-weighted sums are warp reductions.
 // HBM-bound: algorithmic bytes per window = 4*n*(2D + 4) read + 4*n*2 written (risk).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace msacl {
@@ -109,6 +111,150 @@ lyapunov_risk_kernel(int64_t B, int n, int D_rt, const float* __restrict__ obs, 
       g_obs2[e] = w;
       if (is_clip_out) is_clip_out[e] = c;
       if (esl_out) esl_out[e] = esl;
+    }
+  }
+  p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
+  if (lane == 0) { s_part[0][warp] = p0; s_part[1][warp] = p1; s_part[2][warp] = p2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int w = 0; w < WPB; ++w) s += (double)s_part[threadIdx.x][w];
+    atomicAdd(&loss_parts[threadIdx.x], s);
+  }
+}
+
+#ifndef MSACL_LYA_MINB
+#define MSACL_LYA_MINB 2
+#endif
+// All-lanes-live variant: a warp walks tiles of 32 P consecutive (window, step) elements, P = n / gcd(n, 32), so that a tile
+// holds whole windows (n = 20: 160 elements = 8 windows in 5 passes; n = 16: 2 windows in 1 pass).  Lane l of pass p owns
+// element 32 p + l of the tile -- coalesced loads, every lane busy (the warp-per-window kernel above keeps only n of 32
+// lanes busy and is instruction-issue bound at ~0.47 of the HBM peak for n = 20).  A window spans at most two passes
+// (n <= 32), so the clipped-ratio cumprod is a segmented warp scan plus one carry from the previous pass, the window
+// head's (||o_0||, V(o_0)) come from this or the previous pass by one shuffle each, and the head's back-propagated sum is
+// a segmented suffix sum plus the continuation at lane 0 of the next pass.  Same arithmetic per element as the kernel above; only the association of the cumprod / window sums
+// differs for windows that straddle two passes.
+template <int WPB, int P, int DT>
+__global__ void __launch_bounds__(WPB * 32, MSACL_LYA_MINB)
+lyapunov_risk_striped_kernel(int64_t B, int n, const float* __restrict__ obs, const float* __restrict__ obs2,
+                             const float* __restrict__ logp_new, const float* __restrict__ logp_old,
+                             const float* __restrict__ lya_obs, const float* __restrict__ lya_obs2,
+                             const float* __restrict__ coef_son, const float* __restrict__ coef_diff,
+                             const float* __restrict__ coef_sl, float alpha1, float alpha2, float diff_scale, float pos_scale,
+                             double* __restrict__ loss_parts, float* __restrict__ g_obs, float* __restrict__ g_obs2,
+                             float* __restrict__ is_clip_out, float* __restrict__ esl_out) {
+  static_assert(DT > 0, "compile-time obs_dim");
+  __shared__ float s_part[3][WPB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int T = 32 * P;
+  const int64_t total = B * (int64_t)n;
+  const float inv_bn = pos_scale / (float)((double)B * n);
+  const float w_scale = diff_scale / (float)B;
+  // tile-relative step index of this lane's element in every pass, and the coefficients of that step
+  int kk[P];
+  float son[P], dif[P], sl[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    kk[p] = (32 * p + lane) % n;
+    son[p] = coef_son[kk[p]]; dif[p] = coef_diff[kk[p]]; sl[p] = coef_sl[kk[p]];
+  }
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+  const int64_t tiles = (total + T - 1) / T;
+  for (int64_t tile = (int64_t)blockIdx.x * WPB + warp; tile < tiles; tile += (int64_t)gridDim.x * WPB) {
+    const int64_t e0 = tile * T + lane;
+    float ratio[P], v1[P], v2[P], op[P], op2[P];
+    // ---- loads, pass by pass (measured: hoisting all P passes' loads in front of the first use -- 30 loads in flight per
+    //      lane -- is slower, 0.54 vs 0.59 of the HBM peak: the compute of pass p no longer overlaps the loads of pass p + 1)
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int64_t e = e0 + 32 * p;
+      ratio[p] = 1.f; v1[p] = 0.f; v2[p] = 0.f; op[p] = 0.f; op2[p] = 0.f;
+      if (e < total) {
+        const float ln = logp_new[e], lo_ = logp_old[e];
+        v1[p] = lya_obs[e]; v2[p] = lya_obs2[e];
+        const float* o = obs + e * DT;
+        const float* q = obs2 + e * DT;
+        float a[DT], c[DT];
+        if constexpr (DT % 4 == 0) {
+#pragma unroll
+          for (int d = 0; d < DT / 4; ++d) {
+            const float4 x = reinterpret_cast<const float4*>(o)[d], y = reinterpret_cast<const float4*>(q)[d];
+            a[4 * d] = x.x; a[4 * d + 1] = x.y; a[4 * d + 2] = x.z; a[4 * d + 3] = x.w;
+            c[4 * d] = y.x; c[4 * d + 1] = y.y; c[4 * d + 2] = y.z; c[4 * d + 3] = y.w;
+          }
+        } else if constexpr (DT % 2 == 0) {
+#pragma unroll
+          for (int d = 0; d < DT / 2; ++d) {
+            const float2 x = reinterpret_cast<const float2*>(o)[d], y = reinterpret_cast<const float2*>(q)[d];
+            a[2 * d] = x.x; a[2 * d + 1] = x.y; c[2 * d] = y.x; c[2 * d + 1] = y.y;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < DT; ++d) { a[d] = o[d]; c[d] = q[d]; }
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int d = 0; d < DT; ++d) { s1 = __fmaf_rn(a[d], a[d], s1); s2 = __fmaf_rn(c[d], c[d], s2); }
+        op[p] = s1; op2[p] = s2;
+        ratio[p] = fminf(fmaxf(expf(ln - lo_), 0.f), 1.f);   // clamp(ratio, 0, 1) :284-285
+      }
+    }
+    // ---- per pass: segmented cumprod (:286), window-head values, hinge terms
+    float cp[P], wv[P], g1[P], es[P], sfx[P];
+    float carry = 1.f;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int k = kk[p];
+      float c = ratio[p];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float y = __shfl_up_sync(0xffffffffu, c, o);
+        if (lane >= o && k >= o) c *= y;
+      }
+      if (k > lane) c *= carry;                     // the window began in the previous pass
+      carry = __shfl_sync(0xffffffffu, c, 31);
+      cp[p] = c;
+      const int src = (lane - k) & 31;              // lane of the window head, in this pass (k <= lane) or the previous one
+      float h_op = __shfl_sync(0xffffffffu, op[p], src), h_v1 = __shfl_sync(0xffffffffu, v1[p], src);
+      if (p > 0) {
+        const float q_op = __shfl_sync(0xffffffffu, op[p > 0 ? p - 1 : 0], src), q_v1 = __shfl_sync(0xffffffffu, v1[p > 0 ? p - 1 : 0], src);
+        if (k > lane) { h_op = q_op; h_v1 = q_v1; }
+      }
+      const bool live = e0 + 32 * p < total;
+      const float lo = alpha1 * op[p] - v1[p], up = v1[p] - alpha2 * op[p];           // boundedness hinge :291-301
+      const float start_norm = sqrtf(h_op);                                              // ||o_0|| :306-307
+      const float esl = (start_norm * son[p] - sqrtf(op2[p])) >= 0.f ? 1.f : -1.f;      // :308-312
+      const float inner = esl * (v2[p] - h_v1 * sl[p]);                                  // :318-323
+      const float term = c * fmaxf(inner, 0.f);
+      const float w = (live && inner > 0.f) ? dif[p] * c * esl * w_scale : 0.f;
+      wv[p] = w; es[p] = esl;
+      // suffix sum of w * sl inside the window, within this pass
+      float sx = w * sl[p];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float y = __shfl_down_sync(0xffffffffu, sx, o);
+        if (lane + o < 32 && k + o < n) sx += y;
+      }
+      sfx[p] = sx;
+      g1[p] = ((lo > 0.f) ? -inv_bn : 0.f) + ((up > 0.f) ? inv_bn : 0.f);
+      if (live) {
+        p0 += fmaxf(lo, 0.f);
+        p1 += fmaxf(up, 0.f);
+        p2 += dif[p] * term;
+      }
+    }
+    // ---- window heads take the back-propagated sum (continued at lane 0 of the next pass when the window straddles)
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float next0 = __shfl_sync(0xffffffffu, sfx[p + 1 < P ? p + 1 : p], 0);
+      if (kk[p] == 0) g1[p] -= sfx[p] + ((p + 1 < P && lane + n > 32) ? next0 : 0.f);
+      const int64_t e = e0 + 32 * p;
+      if (e < total) {
+        g_obs[e] = g1[p];
+        g_obs2[e] = wv[p];
+        if (is_clip_out) is_clip_out[e] = cp[p];
+        if (esl_out) esl_out[e] = es[p];
+      }
     }
   }
   p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
@@ -335,6 +481,25 @@ extern "C" int msacl_lyapunov_risk(int64_t B, int32_t n, int32_t D, const float*
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(loss_parts, 0, 3 * sizeof(double), s);
   constexpr int WPB = 8;
+  // all-lanes-live kernel: tiles of 32 P elements hold whole windows when P = n / gcd(n, 32); instantiated for P = 1, 3, 5
+  // (n = 32, 16, 8, 4, 2, 1 / 24, 12, 6, 3 / 20, 10, 5 -- the reference default is n = 20) and the six envs' obs_dim
+  {
+    int g = n, r = 32;
+    while (r) { const int t = g % r; g = r; r = t; }
+    const int P = n / g;
+    const int64_t tiles = (B * (int64_t)n + 32 * P - 1) / (32 * P);
+#define MSACL_LYA_STRIPED(P_, DT)                                                                                            \
+    if (P == P_ && D == DT) {                                                                                                \
+      lyapunov_risk_striped_kernel<WPB, P_, DT><<<grid_for(tiles, WPB), WPB * 32, 0, s>>>(                                    \
+          B, n, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale,   \
+          pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);                                                  \
+      return check_launch("lyapunov_risk");                                                                                   \
+    }
+#define MSACL_LYA_STRIPED_D(P_) MSACL_LYA_STRIPED(P_, 2) MSACL_LYA_STRIPED(P_, 4) MSACL_LYA_STRIPED(P_, 6) MSACL_LYA_STRIPED(P_, 7) MSACL_LYA_STRIPED(P_, 12)
+    if (n > 1 && !getenv("MSACL_LYA_WARP_PER_WINDOW")) { MSACL_LYA_STRIPED_D(1) MSACL_LYA_STRIPED_D(3) MSACL_LYA_STRIPED_D(5) }
+#undef MSACL_LYA_STRIPED_D
+#undef MSACL_LYA_STRIPED
+  }
 #define MSACL_LYA_LAUNCH(DT)                                                                                              \
   lyapunov_risk_kernel<WPB, DT><<<grid_for(B, WPB), WPB * 32, 0, s>>>(B, n, D, obs, obs2, logp_new, logp_old, lya_obs,    \
                                                                       lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, \

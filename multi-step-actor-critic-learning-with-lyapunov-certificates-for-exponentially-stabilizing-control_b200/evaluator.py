@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 from . import distributed as mdist
-from .sampler import ActorWeights, FusedRollout
+from .sampler import ActorWeights, FusedRollout, actor_from_policy
 
 
 class B200Evaluator:
@@ -32,7 +32,7 @@ class B200Evaluator:
         self.networks.load_state_dict(state_dict)
 
     def run_parallel_episodes(self, actor: ActorWeights = None, state_init=None):
-        actor = actor or ActorWeights.from_policy(self.networks.policy, device=self.device)
+        actor = actor or actor_from_policy(self.networks.policy, device=self.device)
         lo, hi = 0, self.num_eval_episode
         sharded = self.distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if sharded:

@@ -87,6 +87,78 @@ class ActorWeights:
         return tuple((p.data_ptr(), p._version) for p in policy.parameters())
 
 
+class GeneralActor:
+    """Any StochaPolicy MLP (RL/apprfunc/mlp.py:18-33,111-136): Linear / activation pairs of arbitrary depth, width and
+    activation -- the policies `ActorWeights` (the fused rollout kernels: two hidden layers of 256 ReLU units) cannot take.
+    A forward pass is one `msacl_gemm_tc` per layer (split-bf16 tcgen05 GEMM at FP32-class precision; bias and ReLU / Tanh
+    fused into the epilogue, any other activation module applied in place to the GEMM output); layer 1 reads the
+    observations straight out of the structure-of-arrays env state (row stride 1, k stride = env pitch)."""
+
+    _FUSED_ACT = {torch.nn.ReLU: 1, torch.nn.Tanh: 2, torch.nn.Identity: 0}
+
+    def __init__(self, layers, activations, device="cuda", min_log_std=-20.0, max_log_std=1.0, precision=6):
+        dev = torch.device(device)
+        t = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a.detach(), dtype=torch.float32).to(dev).contiguous()
+        self.layers = [(t(w), t(b)) for w, b in layers]
+        self.activations = list(activations)
+        if len(self.activations) != len(self.layers):
+            raise ValueError("one activation module per Linear layer (Identity for the output layer)")
+        for (w0, _), (w1, _) in zip(self.layers[:-1], self.layers[1:]):
+            if w1.shape[1] != w0.shape[0]:
+                raise ValueError("layer widths do not chain")
+        self.obs_dim = self.layers[0][0].shape[1]
+        self.act_dim = self.layers[-1][0].shape[0] // 2
+        self.min_log_std, self.max_log_std = float(min_log_std), float(max_log_std)
+        self.precision = int(precision)
+        self.device = dev
+        self._ws = {}
+
+    @classmethod
+    def from_policy(cls, policy, device="cuda"):
+        seq = policy.policy if hasattr(policy, "policy") else policy
+        mods = list(seq)
+        lin = [m for m in mods if isinstance(m, torch.nn.Linear)]
+        acts = [m for m in mods if not isinstance(m, torch.nn.Linear)]
+        if not lin or len(acts) != len(lin):
+            raise ValueError("expected Linear / activation pairs (RL/apprfunc/mlp.py:18-33)")
+        return cls([(l.weight, l.bias) for l in lin], acts, device=device,
+                   min_log_std=getattr(policy, "min_log_std", -20.0), max_log_std=getattr(policy, "max_log_std", 1.0))
+
+    def _workspace(self, n):
+        if n not in self._ws:
+            self._ws[n] = [torch.empty(n, w.shape[0], dtype=torch.float32, device=self.device) for w, _ in self.layers]
+        return self._ws[n]
+
+    def forward_state(self, state):
+        """logits [n, 2*act_dim] for the current observations of an `EnvStateBuffers`."""
+        from .learner import _desc
+        lib = _lib.load()
+        n, spec = state.n, state.spec
+        outs = self._workspace(n)
+        a_ptr, a_rs, a_ks = state.sf.data_ptr() + 4 * spec.obs_off * n, 1, n       # SoA: obs[r][k] = sf[obs_off + k][r]
+        for (w, b), act, y in zip(self.layers, self.activations, outs):
+            code = self._FUSED_ACT.get(type(act))
+            g = _desc(a_ptr, a_rs, a_ks, w, w.shape[1], 1, n, w.shape[0], w.shape[1], y, w.shape[0], bias=b,
+                      act=code or 0, precision=self.precision)
+            _lib.check(lib.msacl_gemm_tc(C.byref(g), _lib.current_stream()))
+            if code is None:                    # gelu / elu / selu / sigmoid ...: the module itself, on the device
+                with torch.no_grad():
+                    y.copy_(act(y))
+            a_ptr, a_rs, a_ks = y.data_ptr(), w.shape[0], 1
+        return outs[-1]
+
+
+def actor_from_policy(policy, device="cuda", strict=False):
+    """The packed actor the rollout engines take: `ActorWeights` for the [256, 256] ReLU policy the fused kernels are
+    specialised for, else (unless `strict`) a `GeneralActor` driving per-layer GEMMs + msacl_rollout_step."""
+    try:
+        return ActorWeights.from_policy(policy, device=device)
+    except ValueError:
+        if strict:
+            raise
+        return GeneralActor.from_policy(policy, device=device)
+
+
 class TransitionBuffers:
     """Transition store of one rollout: for every field a `[H + M*K, n, .]` array, H = n_step - 1 history slices.
 
@@ -272,11 +344,31 @@ class FusedRollout:
         common = (self.K, self.global_step & 0xFFFFFFFF, self.n_step, self.reward_scale, self.cost_scale,
                   None if eps is None else eps.data_ptr(), 1 if deterministic else 0, C.byref(out), self.stats.data_ptr(),
                   _lib.current_stream())
+        if isinstance(actor, GeneralActor):
+            engine = "general"
+        elif engine == "general":
+            raise ValueError("rollout engine 'general' takes a GeneralActor")
         if engine == "tc":
             w1p, w2p = actor.tc_images()
         if timing is not None:
             timing[0].record()
-        if engine == "tc":
+        if engine == "general":
+            # per step: policy forward (one GEMM launch per layer) + one msacl_rollout_step launch (sample, env step,
+            # transition record, n-step bookkeeping) -- the unfused form of what the rollout kernels do in one launch
+            lib = _lib.load()
+            for k in range(self.K):
+                logits = actor.forward_state(self.state)
+                if write:
+                    full = tr.desc(tr.H + k, join=False)
+                    if tr.logits is not None:
+                        full.logits = tr.logits[k].data_ptr()
+                else:
+                    full = _lib.Transitions()
+                _lib.check(lib.msacl_rollout_step(C.byref(self.state.desc), logits.data_ptr(), actor.min_log_std, actor.max_log_std,
+                                                  (self.global_step + k) & 0xFFFFFFFF, self.n_step, self.reward_scale, self.cost_scale,
+                                                  None if eps is None else eps[k].data_ptr(), 1 if deterministic else 0,
+                                                  C.byref(full), self.stats.data_ptr(), _lib.current_stream()))
+        elif engine == "tc":
             _lib.check(_lib.load().msacl_rollout_fused_tc(C.byref(self.state.desc), C.byref(actor.desc), w1p.data_ptr(),
                                                          w2p.data_ptr(), *common))
         elif engine == "ffma":
@@ -326,6 +418,7 @@ class B200NstepOffSampler:
         self.rollout = FusedRollout(self.env_id, self.num_envs, self.horizon, self.n_step, self.reward_scale, self.cost_scale,
                                     device=self.device, state=self.envs.state, engine=kwargs.get("rollout_engine", "tc"),
                                     history_chunks=chunks)
+        self._explicit_engine = kwargs.get("rollout_engine") in ("tc", "ffma")     # then an unsupported policy is an error
         self.envs.state.reset()        # base.py:98  envs.reset(seed=None)
         self._actor = None
         self._actor_cache = None
@@ -353,7 +446,9 @@ class B200NstepOffSampler:
         pol = self.networks.policy
         ver = (id(pol), ActorWeights.policy_version(pol))
         if self._actor_cache is None or self._actor_cache[0] != ver:
-            self._actor_cache = (ver, ActorWeights.from_policy(pol, device=self.device))
+            # (a policy the fused kernels are not specialised for runs as per-layer GEMMs + msacl_rollout_step, unless the
+            #  caller asked for a fused engine by name)
+            self._actor_cache = (ver, actor_from_policy(pol, device=self.device, strict=self._explicit_engine))
         return self._actor_cache[1]
 
     def _sample(self):

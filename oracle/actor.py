@@ -29,9 +29,10 @@ def mlp_forward(weights, x, hidden_act=relu):
     return h
 
 
-def policy_forward(weights, obs, min_log_std=-20.0, max_log_std=1.0):
-    """mlp.py:132-136 -> (mean [N,A], std [N,A])."""
-    logits = mlp_forward(weights, obs)
+def policy_forward(weights, obs, min_log_std=-20.0, max_log_std=1.0, hidden_act=relu):
+    """mlp.py:132-136 -> (mean [N,A], std [N,A]).  `weights` may hold any number of layers and `hidden_act` any
+    activation (mlp.py:18-33 builds Linear / activation pairs from `hidden_sizes` / `hidden_activation`)."""
+    logits = mlp_forward(weights, obs, hidden_act)
     a = logits.shape[-1] // 2
     mean, log_std = logits[..., :a], logits[..., a:]
     std = np.exp(np.clip(log_std, f32(min_log_std), f32(max_log_std))).astype(f32)

@@ -76,11 +76,11 @@ class VectorEnv:
         return new["obs"].copy(), reward, term, trunc, final_obs, stats
 
 
-def sampler_step(venv: VectorEnv, weights, eps, reward_scale=100.0, cost_scale=100.0):
+def sampler_step(venv: VectorEnv, weights, eps, reward_scale=100.0, cost_scale=100.0, hidden_act=actor.relu):
     """base.py:124-163 for one vector step; returns the transition dict (all f32 / bool)."""
     spec = venv.spec
     obs = venv.obs.astype(f32).copy()
-    mean, std = actor.policy_forward(weights, obs)
+    mean, std = actor.policy_forward(weights, obs, hidden_act=hidden_act)
     act, logp, _ = actor.tanh_gauss_sample(mean, std, eps, spec.act_low, spec.act_high)
     act_clip = np.clip(act, spec.act_low, spec.act_high).astype(f32)
     next_obs, reward, term, trunc, final_obs, stats = venv.step(act_clip)

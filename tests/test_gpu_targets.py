@@ -25,7 +25,10 @@ def test_q_backup_vs_oracle_and_golden():
     np.testing.assert_allclose(loss, g["loss_q"], rtol=1e-5)
 
 
-@pytest.mark.parametrize("B,n,D", [(48, 20, 4), (1000, 20, 12), (7, 5, 2), (300, 32, 7)])
+# (all-lanes-live kernel: n = 20 / 5 / 10 -> 5 passes per tile, 24 / 12 / 3 -> 3, 32 / 16 / 8 / 2 -> 1; warp-per-window kernel:
+#  n = 1, 7, 18 and obs_dim 3)
+@pytest.mark.parametrize("B,n,D", [(48, 20, 4), (1000, 20, 12), (7, 5, 2), (300, 32, 7), (1001, 16, 4), (333, 24, 6), (50, 12, 2),
+                                   (129, 10, 7), (77, 8, 12), (64, 3, 4), (90, 2, 2), (40, 1, 4), (65, 7, 4), (33, 18, 6), (21, 20, 3)])
 def test_lyapunov_risk_vs_oracle(B, n, D):
     from msacl_b200 import targets as tg
     rng = np.random.default_rng(B)
