@@ -162,6 +162,19 @@ class B200MSACL:
             self._fused = FusedLearner(self)
         return self._fused
 
+    def _select_engine(self):
+        """The fused learner covers the reference's network family with two hidden layers of any width and ReLU / Tanh
+        activations (mlp.py:18-33 defaults); deeper networks, other activations or a Lyapunov head wider than one 256-column
+        tile run on the autograd engine instead of failing at the first update."""
+        if self.engine_name == "fused" and self._fused is None:
+            try:
+                self._fused_learner()
+            except ValueError as e:
+                import warnings
+                warnings.warn(f"msacl_b200: network shapes outside the fused learner ({e}); using learner_engine='torch'")
+                self.engine_name = "torch"
+        return self.engine_name
+
     def _get_alpha(self, requires_grad=False):
         a = self.networks.log_alpha.exp()
         return a if requires_grad else a.item()
@@ -174,7 +187,7 @@ class B200MSACL:
         noise = iter(noise) if noise is not None else None
         nxt = (lambda: next(noise)) if noise is not None else (lambda: None)
         data = {k: v.to(self.device, non_blocking=True) for k, v in data.items()}
-        if self.engine_name == "fused":
+        if self._select_engine() == "fused":
             return self._model_update_fused(data, global_iteration, nxt, noise is not None, start)
         loss_q, q1_mean, q2_mean = self._q_update(data, nxt())
         if global_iteration % self.target_network_frequency == 0:

@@ -24,22 +24,25 @@ __device__ __forceinline__ float block_sum_to_double(float v, double* dst) {
 }
 
 // ---- bias gradients: out[z][c] = sum over the rows of split z of x[r][c]
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld,
+// (blockIdx.y = 256-column chunk: layers wider than 256 units take several chunks)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t rows, int cols_total, int64_t ld,
                                                      float* __restrict__ out) {
   __shared__ float part[256];
-  const int rpp = 256 / cols;                       // rows per pass (cols <= 256)
+  const int c0 = blockIdx.y * 256;
+  const int cols = min(256, cols_total - c0);       // columns of this chunk
+  const int rpp = 256 / cols;                       // rows per pass
   const int rsub = threadIdx.x / cols, c = threadIdx.x - rsub * cols;
   const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(rows, r0 + per);
   float s = 0.f;
   if (rsub < rpp)
-    for (int64_t r = r0 + rsub; r < r1; r += rpp) s += x[r * ld + c];
+    for (int64_t r = r0 + rsub; r < r1; r += rpp) s += x[r * ld + c0 + c];
   part[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x < cols) {
     float t = 0.f;
     for (int j = 0; j < rpp; ++j) t += part[j * cols + threadIdx.x];
-    out[(int64_t)blockIdx.x * cols + threadIdx.x] = t;
+    out[(int64_t)blockIdx.x * cols_total + c0 + threadIdx.x] = t;
   }
 }
 
@@ -339,8 +342,8 @@ using namespace msacl;
 extern "C" {
 
 int msacl_colsum(const float* x, int64_t rows, int32_t cols, int64_t ld, int32_t splits, float* out, void* stream) {
-  LCHECK(x && out && rows > 0 && cols > 0 && cols <= 256 && ld >= cols && splits >= 1, "colsum");
-  colsum_kernel<<<(unsigned)splits, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, out);
+  LCHECK(x && out && rows > 0 && cols > 0 && ld >= cols && splits >= 1, "colsum");
+  colsum_kernel<<<dim3((unsigned)splits, (unsigned)((cols + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, out);
   return check_launch("colsum");
 }
 

@@ -59,10 +59,11 @@ class MLPWorkspace:
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         self.rows, self.train = rows, train
         M, Din, Dout, a = rows, mlp.din, mlp.dout, mlp.act
+        H1, H2 = mlp.h1, mlp.h2                       # hidden widths (reference default 256, 256; any width is accepted)
         (W1, b1), (W2, b2), (W3, b3) = mlp.layers
         import functools
         _desc = functools.partial(globals()["_desc"], precision=mlp.precision)
-        self.h1, self.h2, self.y = f(M, HID), f(M, HID), f(M, Dout)
+        self.h1, self.h2, self.y = f(M, H1), f(M, H2), f(M, Dout)
         self.v = f(M) if sumsq else None
         self.x = None
         # Many row tiles (>= one per SM): the weight operands of the forward / dgrad GEMMs are pre-converted once per call
@@ -70,38 +71,38 @@ class MLPWorkspace:
         self.packed = {}
         pack_ok = (M + 127) // 128 >= 148
 
-        def packed(tag, k):
-            if not pack_ok:
+        def packed(tag, k, n):
+            if not pack_ok or n > 256:               # a pre-packed operand covers one 256-wide column tile
                 return None
             nbytes = int(mlp._l.lib.msacl_gemm_packed_b_bytes(k, mlp.precision))
             t = self.packed[tag] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             return t
 
         # forward: H1 = act(X W1^T + b1), H2 = act(H1 W2^T + b2), Y = H2 W3^T + b3
-        self.f1 = _desc(0, Din, 1, W1, Din, 1, M, HID, Din, self.h1, HID, bias=b1, act=a)
-        self.f2 = _desc(self.h1, HID, 1, W2, HID, 1, M, HID, HID, self.h2, HID, bias=b2, act=a, b_packed=packed("f2", HID))
-        self.f3 = _desc(self.h2, HID, 1, W3, HID, 1, M, Dout, HID, self.y, Dout, bias=b3, act=0, row_sumsq=self.v,
-                        b_packed=packed("f3", HID))
+        self.f1 = _desc(0, Din, 1, W1, Din, 1, M, H1, Din, self.h1, H1, bias=b1, act=a)
+        self.f2 = _desc(self.h1, H1, 1, W2, H1, 1, M, H2, H1, self.h2, H2, bias=b2, act=a, b_packed=packed("f2", H1, H2))
+        self.f3 = _desc(self.h2, H2, 1, W3, H2, 1, M, Dout, H2, self.y, Dout, bias=b3, act=0, row_sumsq=self.v,
+                        b_packed=packed("f3", H2, Dout))
         if not (train or need_dx):
             return
-        self.da2, self.da1 = f(M, HID), f(M, HID)
+        self.da2, self.da1 = f(M, H2), f(M, H1)
         # dgrad: dA2 = (dY W3) * act'(H2);  dA1 = (dA2 W2) * act'(H1);  dX = dA1 W1
-        self.g3 = _desc(0, Dout, 1, W3, 1, HID, M, HID, Dout, self.da2, HID, mask=self.h2, mask_ld=HID, mask_act=a)
-        self.g2 = _desc(self.da2, HID, 1, W2, 1, HID, M, HID, HID, self.da1, HID, mask=self.h1, mask_ld=HID, mask_act=a,
-                        b_packed=packed("g2", HID))
+        self.g3 = _desc(0, Dout, 1, W3, 1, H2, M, H2, Dout, self.da2, H2, mask=self.h2, mask_ld=H2, mask_act=a)
+        self.g2 = _desc(self.da2, H2, 1, W2, 1, H1, M, H1, H2, self.da1, H1, mask=self.h1, mask_ld=H1, mask_act=a,
+                        b_packed=packed("g2", H2, H1))
         self.dx = f(M, Din) if need_dx else None
-        self.g1 = _desc(self.da1, HID, 1, W1, 1, Din, M, Din, HID, self.dx, Din) if need_dx else None
+        self.g1 = _desc(self.da1, H1, 1, W1, 1, Din, M, Din, H1, self.dx, Din) if need_dx else None
         if not train:
             return
         # wgrad (K = rows, split over CTAs; partials summed by the Adam kernel): dW = dY^T X, db = column sums of dY
         S = self.S = _splits(M)
         Sb = self.Sb = max(1, min(1184, -(-M // 64)))       # bias gradients: many short row blocks (memory-level parallelism)
-        self.gw1, self.gb1 = f(S, HID, Din), f(Sb, HID)
-        self.gw2, self.gb2 = f(S, HID, HID), f(Sb, HID)
-        self.gw3, self.gb3 = f(S, Dout, HID), f(Sb, Dout)
-        self.w3 = _desc(0, 1, Dout, self.h2, 1, HID, Dout, HID, M, self.gw3, HID, split_k=S, c_split_stride=Dout * HID)
-        self.w2 = _desc(self.da2, 1, HID, self.h1, 1, HID, HID, HID, M, self.gw2, HID, split_k=S, c_split_stride=HID * HID)
-        self.w1 = _desc(self.da1, 1, HID, 0, 1, Din, HID, Din, M, self.gw1, Din, split_k=S, c_split_stride=HID * Din)
+        self.gw1, self.gb1 = f(S, H1, Din), f(Sb, H1)
+        self.gw2, self.gb2 = f(S, H2, H1), f(Sb, H2)
+        self.gw3, self.gb3 = f(S, Dout, H2), f(Sb, Dout)
+        self.w3 = _desc(0, 1, Dout, self.h2, 1, H2, Dout, H2, M, self.gw3, H2, split_k=S, c_split_stride=Dout * H2)
+        self.w2 = _desc(self.da2, 1, H2, self.h1, 1, H1, H2, H1, M, self.gw2, H1, split_k=S, c_split_stride=H2 * H1)
+        self.w1 = _desc(self.da1, 1, H1, 0, 1, Din, H1, Din, M, self.gw1, Din, split_k=S, c_split_stride=H1 * Din)
 
     def grads(self):
         """[(partials tensor, nsplit)] in nn.Module.parameters() order: W1, b1, W2, b2, W3, b3."""
@@ -109,17 +110,20 @@ class MLPWorkspace:
 
 
 class FusedMLP:
-    """A reference-style 3-layer MLP (mlp.py:18-33: Linear-act-Linear-act-Linear-Identity, hidden width 256) driven by
+    """A reference-style 3-layer MLP (mlp.py:18-33: Linear-act-Linear-act-Linear-Identity, any hidden widths) driven by
     msacl_gemm_tc.  `seq` is the nn.Sequential whose parameters stay the single source of truth."""
 
-    def __init__(self, seq, device, precision=6):
+    def __init__(self, seq, device, precision=6, sumsq_head=False):
         if precision not in (3, 6):
             raise ValueError("precision: 6 (bf16x6, FP32-class) or 3 (bf16x3)")
         self.precision = precision
         lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
         other = [m for m in seq if not isinstance(m, torch.nn.Linear)]
-        if len(lin) != 3 or lin[0].out_features != HID or lin[1].in_features != HID or lin[1].out_features != HID or lin[2].in_features != HID:
-            raise ValueError("FusedMLP: the fused learner is specialised for hidden sizes [256, 256]")
+        if len(lin) != 3 or lin[1].in_features != lin[0].out_features or lin[2].in_features != lin[1].out_features:
+            raise ValueError("FusedMLP: the fused learner takes two hidden layers (any widths; reference default [256, 256])")
+        self.h1, self.h2 = lin[0].out_features, lin[1].out_features
+        if sumsq_head and lin[2].out_features > 256:
+            raise ValueError("FusedMLP: the fused sum-of-squares head covers one 256-wide column tile (lyapunov_output_dim <= 256)")
         if type(other[0]) not in ACT_CODE or type(other[0]) is torch.nn.Identity or type(other[1]) is not type(other[0]) or \
                 not isinstance(other[2], torch.nn.Identity):
             raise ValueError(f"FusedMLP: unsupported activations {[type(m).__name__ for m in other]} (relu / tanh hidden, linear output)")
@@ -185,8 +189,8 @@ class FusedMLP:
             ws.w1.b = ws.x.data_ptr()
             l.gemm(ws.w3); l.gemm(ws.w2); l.gemm(ws.w1)
             _lib.check(lib.msacl_colsum(dy.data_ptr(), ws.rows, self.dout, self.dout, ws.Sb, ws.gb3.data_ptr(), st))
-            _lib.check(lib.msacl_colsum(ws.da2.data_ptr(), ws.rows, HID, HID, ws.Sb, ws.gb2.data_ptr(), st))
-            _lib.check(lib.msacl_colsum(ws.da1.data_ptr(), ws.rows, HID, HID, ws.Sb, ws.gb1.data_ptr(), st))
+            _lib.check(lib.msacl_colsum(ws.da2.data_ptr(), ws.rows, self.h2, self.h2, ws.Sb, ws.gb2.data_ptr(), st))
+            _lib.check(lib.msacl_colsum(ws.da1.data_ptr(), ws.rows, self.h1, self.h1, ws.Sb, ws.gb1.data_ptr(), st))
         return ws.dx
 
     def reduced_grads(self, ws):
@@ -277,7 +281,7 @@ class FusedLearner:
         self.P = FusedMLP(net.policy.policy, dev, pr)
         self.Q1, self.Q2 = FusedMLP(net.q1.q, dev, pr), FusedMLP(net.q2.q, dev, pr)
         self.Q1t, self.Q2t = FusedMLP(net.q1_target.q, dev, pr), FusedMLP(net.q2_target.q, dev, pr)
-        self.L = FusedMLP(net.lyapunov.lya, dev, pr)
+        self.L = FusedMLP(net.lyapunov.lya, dev, pr, sumsq_head=True)
         if self.P.act != 1 or self.Q1.act != 1:
             pass      # any supported activation works for the learner; the ROLLOUT kernels additionally require ReLU policies
         self.D, self.A = self.P.din, self.P.dout // 2

@@ -118,13 +118,17 @@ def test_gemm_tc_strided_operands_dgrad_mask_and_splitk_wgrad():
     np.testing.assert_allclose(cs.sum(0).cpu().numpy(), dY.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-4)
 
 
-@pytest.mark.parametrize("din,dout,act,rows", [(6, 1, "relu", 5120), (4, 4, "relu", 777), (4, 256, "tanh", 2 * 640), (16, 1, "relu", 130)])
-def test_fused_mlp_forward_backward_vs_autograd(din, dout, act, rows):
-    """FusedMLP (three msacl_gemm_tc layers forward, dgrad + split-K wgrad backward) vs torch autograd on the same nn.Sequential."""
+@pytest.mark.parametrize("din,dout,act,rows,hidden", [(6, 1, "relu", 5120, (256, 256)), (4, 4, "relu", 777, (256, 256)),
+                                                      (4, 256, "tanh", 2 * 640, (256, 256)), (16, 1, "relu", 130, (256, 256)),
+                                                      (7, 2, "relu", 1500, (64, 128)), (12, 256, "tanh", 900, (300, 40)),
+                                                      (3, 1, "relu", 20000, (512, 32))])
+def test_fused_mlp_forward_backward_vs_autograd(din, dout, act, rows, hidden):
+    """FusedMLP (three msacl_gemm_tc layers forward, dgrad + split-K wgrad backward) vs torch autograd on the same nn.Sequential;
+    hidden widths are arbitrary (the reference builds them from `*_hidden_sizes`, mlp.py:18-33)."""
     from msacl_b200.algorithm import mlp
     from msacl_b200.learner import FusedMLP
     torch.manual_seed(rows)
-    seq = mlp([din, 256, 256, dout], {"relu": torch.nn.ReLU, "tanh": torch.nn.Tanh}[act]).cuda()
+    seq = mlp([din, *hidden, dout], {"relu": torch.nn.ReLU, "tanh": torch.nn.Tanh}[act]).cuda()
     x = torch.randn(rows, din, device="cuda")
     dy = torch.randn(rows, dout, device="cuda") / rows
     fm = FusedMLP(seq, "cuda")
@@ -216,8 +220,28 @@ def test_adam_multi_matches_torch_adam():
     np.testing.assert_allclose(oa.state[pa[2]]["exp_avg_sq"].cpu().numpy(), ob.state[pb[2]]["exp_avg_sq"].cpu().numpy(), rtol=2e-6, atol=1e-12)
 
 
-@pytest.mark.parametrize("env,B", [("TwoLink", 48), ("QuadTracking", 20), ("DuctedFan", 33)])
-def test_fused_learner_matches_torch_engine(env, B):
+def test_learner_engine_falls_back_for_networks_outside_the_fused_family():
+    """Three hidden layers / GELU: the default learner_engine switches to the autograd engine (with a warning) instead of
+    failing at the first update; the reference accepts any `*_hidden_sizes` / `*_hidden_activation`."""
+    import msacl_b200
+    from msacl_b200.specs import get_spec
+    spec = get_spec("VanderPol")
+    D, A, n, B = spec.obs_dim, spec.act_dim, 5, 16
+    alg = msacl_b200.create_alg(algorithm="msacl", env_name="VanderPol", obs_dim=D, act_dim=A, n_step=n, action_low_limit=spec.act_low,
+                                action_high_limit=spec.act_high, q_learning_rate=1e-3, lyapunov_learning_rate=1e-3, policy_learning_rate=3e-4,
+                                alpha_learning_rate=1e-3, value_hidden_sizes=[32, 32, 32], policy_hidden_activation="gelu")
+    r = lambda *s: torch.randn(*s, device="cuda")
+    data = dict(obs=r(B, n, D) * 0.3, obs2=r(B, n, D) * 0.3, act=torch.zeros(B, n, A, device="cuda"), rew=-torch.rand(B, n, device="cuda"),
+                cost=torch.rand(B, n, device="cuda"), done=torch.zeros(B, n, device="cuda"), logp=r(B, n) - 1.0)
+    with pytest.warns(UserWarning, match="learner_engine='torch'"):
+        info = alg.model_update(data, 2)
+    assert alg.engine_name == "torch" and info is not None and np.isfinite(list(info.values())).all()
+
+
+@pytest.mark.parametrize("env,B,sizes", [("TwoLink", 48, None), ("QuadTracking", 20, None), ("DuctedFan", 33, None),
+                                         ("SingleTrackCar", 24, dict(value_hidden_sizes=[128, 64], lyapunov_hidden_sizes=[64, 96],
+                                                                     lyapunov_output_dim=32, policy_hidden_sizes=[96, 320]))])
+def test_fused_learner_matches_torch_engine(env, B, sizes):
     """Two iterations (q + Lyapunov + 2 policy + alpha updates) of the fused learner vs the autograd engine from identical
     state, batch and rsample noise: same losses (2e-4) and the same parameters after the Adam steps."""
     import msacl_b200
@@ -225,7 +249,8 @@ def test_fused_learner_matches_torch_engine(env, B):
     spec = get_spec(env)
     D, A, n = spec.obs_dim, spec.act_dim, 20
     kw = dict(algorithm="msacl", env_name=env, obs_dim=D, act_dim=A, n_step=n, action_low_limit=spec.act_low, action_high_limit=spec.act_high,
-              q_learning_rate=1e-3, lyapunov_learning_rate=1e-3, policy_learning_rate=3e-4, alpha_learning_rate=1e-3, lya_diff_scale=10.0)
+              q_learning_rate=1e-3, lyapunov_learning_rate=1e-3, policy_learning_rate=3e-4, alpha_learning_rate=1e-3, lya_diff_scale=10.0,
+              **(sizes or {}))
     torch.manual_seed(1)
     a = msacl_b200.create_alg(learner_engine="torch", **kw)
     b = msacl_b200.create_alg(learner_engine="fused", **kw)
