@@ -356,6 +356,36 @@ def time_rollout(cx, env, n, K, engine, steps, warmup, keep=False, clocks=False,
     return out
 
 
+def time_general_rollout(cx, env="TwoLink", n=1 << 18, K=16, hidden=(64, 64), steps=3, warmup=2):
+    """The general rollout engine (a policy the fused kernels are not specialised for: per-layer tcgen05 GEMMs +
+    msacl_rollout_step, launches per env step instead of one per K steps)."""
+    torch = cx.torch
+    from msacl_b200.sampler import FusedRollout, GeneralActor
+    from msacl_b200.specs import get_spec
+    spec = get_spec(env)
+    torch.manual_seed(0)
+    sizes = [spec.obs_dim, *hidden, 2 * spec.act_dim]
+    lin = [torch.nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:])]
+    actor = GeneralActor([(l.weight, l.bias) for l in lin], [torch.nn.Tanh() for _ in hidden] + [torch.nn.Identity()], device=cx.dev)
+    ro = FusedRollout(env, n, K, n_step=20, seed=0, env_base=cx.rank * n, device=cx.dev, history_chunks=1)
+    ro.state.reset()
+    for _ in range(warmup):
+        ro.run(actor)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record(cx.stream)
+    for _ in range(steps):
+        ro.run(actor)
+    t1.record(cx.stream)
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    del ro, actor
+    torch.cuda.empty_cache()
+    return {"env": env, "envs_per_gpu": n, "inner_steps": K, "engine": "general", "policy_hidden_sizes": list(hidden),
+            "policy_hidden_activation": "tanh", "value": n * K / (ms * 1e-3), "unit": UNIT, "ms_per_launch_of_K_steps": ms,
+            "gpu_launches_per_env_step": len(hidden) + 2}
+
+
 def rollout_roofline(cx, env, n, K, engine, kern_ms, ffma_peak):
     from msacl_b200.specs import get_spec
     spec = get_spec(env)
@@ -773,6 +803,10 @@ def main():
                 c3["learner_model_update"] = {"error": repr(e)}
             configs["3_twolink_1M_envs_msacl_targets"] = c3
             configs["5_quadtracking_fp32_ffma_engine"] = rollout_cfg(args.env, n, K, "ffma" if args.engine == "tc" else "tc")
+            try:
+                configs["general_engine_twolink_hidden_64x64_tanh"] = time_general_rollout(cx)
+            except Exception as e:
+                configs["general_engine_twolink_hidden_64x64_tanh"] = {"error": repr(e)}
             try:
                 configs["1_vanderpol_training_reference_defaults"] = time_training_loop(cx)
             except Exception as e:
