@@ -351,7 +351,11 @@ int msacl_adam_tick(int32_t* step, float* dyn, double lr, double beta1, double b
  * mode 0: independent FFMA chains with immediate operands (pipe peak);
  * mode 1: register-resident 8x8 outer-product accumulation, i.e. a register-tiled SGEMM inner
  *         loop with no memory traffic (three-register FFMA ceiling);
- * mode 2: the same outer product with packed FFMA2 (fma.rn.f32x2).
+ * mode 2: the same outer product with packed FFMA2 (fma.rn.f32x2);
+ * mode 3: FP64 DFMA throughput at full occupancy;
+ * modes 4-6: separate DMUL / DADD issued by ONE warp per SM sub-partition with 8 / 2 / 1 independent chains per thread
+ *         (*flops then returns the FP64 instructions issued per warp): the FP64 issue rate the fused rollout's env phase sees;
+ * mode 7: float32 <-> float64 round trips (two conversions + one DMUL each; *flops = round trips per warp).
  * sink: device float[128] (sink[64..128) is read as operand source in mode 1).
  * Returns the FLOPs issued in *flops (host). */
 int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, void* stream);

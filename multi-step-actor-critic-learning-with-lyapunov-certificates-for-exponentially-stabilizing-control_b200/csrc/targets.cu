@@ -449,6 +449,46 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, float* sink)
   if (s == 123.456) sink[0] = (float)s;
 }
 
+// modes 4-6: FP64 issue rate seen by ONE warp per SM sub-partition (the env phase of the fused rollout kernel: one env warp
+// per sub-partition, separate DMUL / DADD because the dynamics round like NumPy): CH independent chains per thread of
+// alternating DMUL, DADD.  4: CH = 8 (throughput of a lone warp), 5: CH = 2, 6: CH = 1 (dependent latency).
+template <int CH>
+__global__ void __launch_bounds__(128) dmul_dadd_probe_kernel(int iters, float* sink) {
+  double a[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) a[j] = (double)(threadIdx.x + j) * 1e-3;
+  const double x = (double)sink[64] * 1e-9 + 1.0, y = (double)sink[65] * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 32 / CH; ++u)
+#pragma unroll
+      for (int j = 0; j < CH; ++j) a[j] = __dadd_rn(__dmul_rn(a[j], x), y);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < CH; ++j) s += a[j];
+  if (s == 123.456) sink[0] = (float)s;
+}
+
+// mode 7: float32 <-> float64 round trips (F2F.F32.F64, F2F.F64.F32) plus one DMUL per round trip, 8 chains, one warp per
+// sub-partition: the conversion cost of the reference's mixed-precision dtype flow
+__global__ void __launch_bounds__(128) f2f_probe_kernel(int iters, float* sink) {
+  double a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = (double)(threadIdx.x + j) * 1e-3 + 1.0;
+  const double x = (double)sink[64] * 1e-9 + 1.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = __dmul_rn((double)__double2float_rn(a[j]), x);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == 123.456) sink[0] = (float)s;
+}
+
 }  // namespace msacl
 
 using namespace msacl;
@@ -547,7 +587,15 @@ extern "C" int msacl_polyak_update(int32_t count, const float* const* src, float
 }
 
 extern "C" int msacl_ffma_probe(int32_t mode, int32_t iters, float* sink, double* flops, void* stream) {
-  if (iters <= 0 || !sink || mode < 0 || mode > 3) { set_error("ffma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
+  if (iters <= 0 || !sink || mode < 0 || mode > 7) { set_error("ffma_probe: bad argument"); return MSACL_ERR_BAD_ARG; }
+  if (mode >= 4) {          // one warp per sub-partition: 148 blocks x 128 threads; *flops = FP64 instructions per warp
+    if (mode == 4) dmul_dadd_probe_kernel<8><<<kNumSMs, 128, 0, (cudaStream_t)stream>>>(iters, sink);
+    else if (mode == 5) dmul_dadd_probe_kernel<2><<<kNumSMs, 128, 0, (cudaStream_t)stream>>>(iters, sink);
+    else if (mode == 6) dmul_dadd_probe_kernel<1><<<kNumSMs, 128, 0, (cudaStream_t)stream>>>(iters, sink);
+    else f2f_probe_kernel<<<kNumSMs, 128, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (flops) *flops = (mode == 7 ? 32.0 : 64.0) * (double)iters;     // mode 7: round trips (2 conversions + 1 DMUL each)
+    return check_launch("ffma_probe");
+  }
   const unsigned grid = 2 * kNumSMs * 4;
   if (mode == 0) {
     ffma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
