@@ -32,18 +32,34 @@ constexpr int GA_LBO = GM * 16, G_SBO = 128;
 //   converted B (weight gradient, un-packed weights):                warps 0-3 epilogue, warps 4-15 loaders (threads
 //       0..127 of the group own the A tile, 128..383 the B tile).
 constexpr int G_LOADERS = 384;
+#ifndef MSACL_GEMM_LOOKAHEAD
+#define MSACL_GEMM_LOOKAHEAD 3
+#endif
 constexpr int G_MMA_WARP = 16;
 constexpr int G_THREADS = 32 * (G_MMA_WARP + 1);
 
-template <int NIMG, int BN, int STAGES>
+// streamed mode: the K blocks of an A image are 32 bytes further apart (LBO = 128 * 16 + 32), so that the loader's 16-byte
+// stores -- a quarter-warp holds the 4 K blocks of 2 adjacent rows -- fall into 8 different 16-byte bank groups
+constexpr int GA_LBO_S = GM * 16 + 32, GA_HALF_S = 4 * GA_LBO_S;
+template <int NIMG, int BN, int STAGES, bool STREAMED = false>
 struct GemmSmem {
-  alignas(128) unsigned char a[STAGES][NIMG * GA_HALF];
+  alignas(128) unsigned char a[STAGES][NIMG * (STREAMED ? GA_HALF_S : GA_HALF)];
   alignas(128) unsigned char b[STAGES][NIMG * BN * GK * 2];
   alignas(16) float bias[BN];
   float ss_part[GM];
   unsigned long long full[STAGES], empty[STAGES], accfull[2], accfree[2];
   uint32_t tmem_slot;
 };
+
+// 256-bit global accesses (sm_100: LDG / STG .ENL2.256); the address must be 32-byte aligned
+__device__ __forceinline__ void g_stg256(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void g_ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]),
+               "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
 
 __device__ __forceinline__ uint32_t g_pack_bf16x2_rn(float lo, float hi) {   // {hi:lo} packed, RNE
   uint32_t r;
@@ -112,6 +128,40 @@ __device__ __forceinline__ void g_kcontig_store(unsigned char* img0, const float
       r[2] -= __uint_as_float(h1 << 16); r[3] -= __uint_as_float(h1 & 0xFFFF0000u);
       *reinterpret_cast<uint2*>(dst + i * HALF) = make_uint2(h0, h1);
     }
+  }
+}
+
+// Streamed mode, 256 loader threads, a 128 x 32 A stage: thread t owns K block kb = t & 3 (8 consecutive k = 32 bytes, one
+// 256-bit load) of rows (t >> 2) + 64 j, j = 0, 1 -- a warp instruction covers 8 whole 128-byte rows -- and turns each into ONE
+// 16-byte store per image.  Needs 32-byte aligned rows (row stride % 8 == 0); the host checks.
+__device__ __forceinline__ void g_k8_load(float (&v)[2][8], const float* __restrict__ src, int64_t rs, int64_t row0, int64_t row_limit,
+                                          int k0, int kend, int t) {
+  const int kk = k0 + (t & 3) * 8;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int64_t row = row0 + (t >> 2) + 64 * j;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+    if (row < row_limit) {
+      const float* p = src + row * rs + kk;
+      if (kk + 7 < kend) g_ldg256(p, v[j]);
+      else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (kk + e < kend) v[j][e] = p[e];
+      }
+    }
+  }
+}
+
+template <int LBO, int HALF, int NIMG>
+__device__ __forceinline__ void g_k8_store(unsigned char* img0, const float (&v)[2][8], int t) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint4 img[NIMG];
+    g_split8<NIMG>(v[j], img);
+    unsigned char* dst = img0 + (t & 3) * LBO + ((t >> 2) + 64 * j) * 16;
+#pragma unroll
+    for (int i = 0; i < NIMG; ++i) *reinterpret_cast<uint4*>(dst + i * HALF) = img[i];
   }
 }
 
@@ -214,7 +264,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
   constexpr int GN = BN, GB_HALF = BN * GK * 2, GB_LBO = BN * 16;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator buffers (512 / 256 / 128 columns)
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  GemmSmem<NIMG, BN, STAGES>& sm = *reinterpret_cast<GemmSmem<NIMG, BN, STAGES>*>(smem_raw);
+  GemmSmem<NIMG, BN, STAGES, STREAMED>& sm = *reinterpret_cast<GemmSmem<NIMG, BN, STAGES, STREAMED>*>(smem_raw);
+  constexpr int A_LBO = STREAMED ? GA_LBO_S : GA_LBO, A_HALF = STREAMED ? GA_HALF_S : GA_HALF;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int mtiles = (g.m + GM - 1) / GM, ntiles = (g.n + BN - 1) / BN;
   const int64_t total_tiles = (int64_t)mtiles * ntiles * g.split_k;
@@ -242,47 +293,65 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
     // 8 coalesced float4 chunks) per thread per stage, so a stage costs one global round trip.
     const int t = tid - epi_threads;
     if constexpr (streamed) {
-      // ---- A tile, k-contiguous, many row tiles (packed B): software-pipelined -- the global loads of stage i + 1 (possibly the next tile's first
-      //      stage) are in flight while stage i is converted and stored, so a stage no longer costs a full DRAM round trip
-      //      per loader thread (ncu: 74 % of the loader samples were long-scoreboard stalls)
-      int64_t tile = blockIdx.x, ntile = tile;
-      GemmTile tl, ntl;
-      int it = 0, nit = 0;
-      bool have = false, nhave = false;
-      auto fetch = [&](int64_t& tl_id, GemmTile& c, int& i_, bool& ok, int64_t from_tile, int from_it, const GemmTile& from, bool first) {
-        // position after (from_tile, from_it), or the first position if `first`
-        tl_id = from_tile; c = from; i_ = first ? 0 : from_it + 1;
-        if (first) c = tl_id < total_tiles ? gemm_tile<BN>(g, tl_id, mtiles, ntiles) : c;
-        while (tl_id < total_tiles && i_ >= c.nk) {
-          tl_id += gridDim.x; i_ = 0;
-          if (tl_id < total_tiles) c = gemm_tile<BN>(g, tl_id, mtiles, ntiles);
+      // ---- A tile, k-contiguous, many row tiles (packed B): software-pipelined with G_LOOK register buffers -- the global
+      //      loads of the next G_LOOK - 1 stages (across tile boundaries) are in flight while a stage is converted and
+      //      stored (ncu, one-stage version: loader samples 46 % long-scoreboard, a stage cost ~4 k cycles against 1.5 k of
+      //      UMMAs).  The buffers rotate by unrolling, never by register moves (a move of an in-flight load's destination
+      //      would wait for it).
+      constexpr int G_LOOK = MSACL_GEMM_LOOKAHEAD;
+      // fetch cursor: the position (tile, k stage) G_LOOK stages ahead of the one being stored
+      int64_t ctile = blockIdx.x;
+      GemmTile ctl;
+      int cit = 0;
+      bool cok = ctile < total_tiles;
+      auto settle = [&]() {                           // skip tiles without k stages, stop behind the last tile
+        while (cok && cit >= ctl.nk) {
+          ctile += gridDim.x; cit = 0;
+          cok = ctile < total_tiles;
+          if (cok) ctl = gemm_tile<BN>(g, ctile, mtiles, ntiles);
         }
-        ok = tl_id < total_tiles;
       };
-      fetch(tile, tl, it, have, (int64_t)blockIdx.x, 0, tl, true);
-      float4 cur[4], nxt[4];
-      auto load = [&](float4 (&v)[4], const GemmTile& c, int i_) {
-        g_kcontig_load<256, GM>(v, g.a, g.a_row_stride, c.m0, g.m, GM, c.kbeg + i_ * GK, c.kend, t);
-      };
-      if (have) load(cur, tl, it);
-      uint32_t gs = 0;
-      while (have) {
-        fetch(ntile, ntl, nit, nhave, tile, it, tl, false);
-        if (nhave) load(nxt, ntl, nit);
-        const int s = gs % G_STAGES;
-        if (gs >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((gs / G_STAGES - 1) & 1));
-        if (t == 0) {                                   // the stage's B tile: one bulk copy of the pre-packed images
-          constexpr uint32_t bytes = NIMG * GB_HALF;
-          tc::mbar_expect_tx(&sm.full[s], bytes);
-          tc::tma_bulk_g2s(sm.b[s], static_cast<const unsigned char*>(g.b_packed) + (size_t)((tl.kbeg + it * GK) / GK) * bytes, bytes, &sm.full[s]);
-        }
-        g_kcontig_store<GA_LBO, GA_HALF, NIMG, 256, GM>(sm.a[s], cur, GM, t);
-        tc::fence_async_smem();
-        tc::mbar_arrive(&sm.full[s]);
-        ++gs;
+      if (cok) ctl = gemm_tile<BN>(g, ctile, mtiles, ntiles);
+      settle();
+      float r[G_LOOK][2][8];
+      int kst[G_LOOK];
+      bool ok[G_LOOK];
+      auto refill = [&](int ph) {
+        ok[ph] = cok;
+        if (cok) {
+#ifdef MSACL_GEMM_DEBUG_NOLOAD      // (bottleneck triage: no global loads of the A operand)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
-        tile = ntile; tl = ntl; it = nit; have = nhave;
+          for (int q = 0; q < 16; ++q) r[ph][q >> 3][q & 7] = (float)(t + q);
+#else
+          g_k8_load(r[ph], g.a, g.a_row_stride, ctl.m0, g.m, ctl.kbeg + cit * GK, ctl.kend, t);
+#endif
+          kst[ph] = (ctl.kbeg + cit * GK) / GK;
+          ++cit;
+          settle();
+        }
+      };
+#pragma unroll
+      for (int ph = 0; ph < G_LOOK; ++ph) refill(ph);
+      uint32_t gs = 0;
+      bool more = true;
+      while (more) {
+#pragma unroll
+        for (int ph = 0; ph < G_LOOK; ++ph) {
+          if (!more) break;
+          if (!ok[ph]) { more = false; break; }
+          const int s = gs % G_STAGES;
+          if (gs >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((gs / G_STAGES - 1) & 1));
+          if (t == 0) {                                 // the stage's B tile: one bulk copy of the pre-packed images
+            constexpr uint32_t bytes = NIMG * GB_HALF;
+            tc::mbar_expect_tx(&sm.full[s], bytes);
+            tc::tma_bulk_g2s(sm.b[s], static_cast<const unsigned char*>(g.b_packed) + (size_t)kst[ph] * bytes, bytes, &sm.full[s]);
+          }
+          g_k8_store<A_LBO, A_HALF, NIMG>(sm.a[s], r[ph], t);
+          tc::fence_async_smem();
+          tc::mbar_arrive(&sm.full[s]);
+          ++gs;
+          refill(ph);
+        }
       }
     } else if (t < 128 || !packed_b || t == 128) {    // (packed B behind a strided A: thread 128 issues the bulk copies)
       const bool avec = g.a_k_stride == 1 && (g.a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0;
@@ -296,8 +365,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
           if (gs >= G_STAGES) tc::mbar_wait(&sm.empty[s], (uint32_t)((gs / G_STAGES - 1) & 1));
           const int k0 = tl.kbeg + it * GK;
           if (a_role) {
-            if (avec) g_load_tile_kcontig<GA_LBO, GA_HALF, NIMG, 128, GM>(sm.a[s], g.a, g.a_row_stride, tl.m0, g.m, GM, k0, tl.kend, t);
-            else g_load_row<GA_LBO, GA_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, tl.m0 + t, tl.m0 + t < g.m, k0, tl.kend, t, false);
+            if (avec) g_load_tile_kcontig<A_LBO, A_HALF, NIMG, 128, GM>(sm.a[s], g.a, g.a_row_stride, tl.m0, g.m, GM, k0, tl.kend, t);
+            else g_load_row<A_LBO, A_HALF, NIMG>(sm.a[s], g.a, g.a_row_stride, g.a_k_stride, tl.m0 + t, tl.m0 + t < g.m, k0, tl.kend, t, false);
           } else if (packed_b) {
             constexpr uint32_t bytes = NIMG * GB_HALF;
             tc::mbar_expect_tx(&sm.full[s], bytes);
@@ -334,7 +403,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
             uint64_t da[NIMG], db[NIMG];
 #pragma unroll
             for (int i = 0; i < NIMG; ++i) {
-              da[i] = tc::make_smem_desc(ab + i * GA_HALF + j * 2 * GA_LBO, GA_LBO, G_SBO);
+              da[i] = tc::make_smem_desc(ab + i * A_HALF + j * 2 * A_LBO, A_LBO, G_SBO);
               db[i] = tc::make_smem_desc(bb + i * GB_HALF + j * 2 * GB_LBO, GB_LBO, G_SBO);
             }
             tc::umma_bf16(tacc, da[0], db[0], idesc, (it > 0 || j > 0) ? 1u : 0u);
@@ -357,6 +426,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
     const bool two_halves = epi_warps == 8;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const bool cvec = (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(g.c) & 15) == 0 && (g.c_split_stride & 3) == 0;
+    const bool cvec8 = (g.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(g.c) & 31) == 0 && (g.c_split_stride & 7) == 0;
+    const bool mvec8 = g.mask_src && (g.mask_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(g.mask_src) & 31) == 0;
     const bool mvec = g.mask_src && (g.mask_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask_src) & 15) == 0;
     uint32_t li = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
@@ -402,46 +473,73 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
         }
         if (!row_ok) continue;
 #pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const int col = c + j4;                 // tile-local column
-          if (col >= tl.n_rem) break;
-          float x[4];
+        for (int j8 = 0; j8 < 32; j8 += 8) {
+          const int col8 = c + j8;                // tile-local column of this group of 8
+          if (col8 >= tl.n_rem) break;
+          float x[8];
+          float m8[8];
+          const bool m8ok = mrow && mvec8 && col8 + 7 < tl.n_rem;      // activation-derivative source: one 32-byte load
+          if (m8ok) g_ldg256(mrow + col8, m8);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = __uint_as_float(v[j4 + j]);
-          const bool full4 = col + 3 < tl.n_rem;
-          if (g.bias) {
-            const float4 bb = *reinterpret_cast<const float4*>(&sm.bias[col]);
-            x[0] += bb.x; x[1] += bb.y; x[2] += bb.z; x[3] += bb.w;
-          }
-          if (g.act == 1) {
+          for (int hq = 0; hq < 2; ++hq) {
+            const int col = col8 + 4 * hq;
+            float* xs = x + 4 * hq;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
-          } else if (g.act == 2) {
+            for (int j = 0; j < 4; ++j) xs[j] = __uint_as_float(v[j8 + 4 * hq + j]);
+            if (col >= tl.n_rem) continue;
+            const bool full4 = col + 3 < tl.n_rem;
+            if (g.bias) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sm.bias[col]);
+              xs[0] += bb.x; xs[1] += bb.y; xs[2] += bb.z; xs[3] += bb.w;
+            }
+            if (g.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
-          }
-          if (mrow) {
-            float hsrc[4];
-            if (mvec && full4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(mrow + col);
-              hsrc[0] = t4.x; hsrc[1] = t4.y; hsrc[2] = t4.z; hsrc[3] = t4.w;
-            } else {
+              for (int j = 0; j < 4; ++j) xs[j] = fmaxf(xs[j], 0.f);
+            } else if (g.act == 2) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) hsrc[j] = (col + j < tl.n_rem) ? mrow[col + j] : 0.f;
+              for (int j = 0; j < 4; ++j) xs[j] = tanhf(xs[j]);
+            }
+            if (mrow) {
+              float hsrc[4];
+              if (m8ok) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hsrc[j] = m8[4 * hq + j];
+              } else if (mvec && full4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(mrow + col);
+                hsrc[0] = t4.x; hsrc[1] = t4.y; hsrc[2] = t4.z; hsrc[3] = t4.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hsrc[j] = (col + j < tl.n_rem) ? mrow[col + j] : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (g.mask_act == 1) xs[j] = hsrc[j] > 0.f ? xs[j] : 0.f;                       // relu'(pre) = [post > 0]
+                else if (g.mask_act == 2) xs[j] = xs[j] * (1.0f - hsrc[j] * hsrc[j]);           // tanh'(pre) = 1 - post^2
+              }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (g.mask_act == 1) x[j] = hsrc[j] > 0.f ? x[j] : 0.f;                       // relu'(pre) = [post > 0]
-              else if (g.mask_act == 2) x[j] = x[j] * (1.0f - hsrc[j] * hsrc[j]);           // tanh'(pre) = 1 - post^2
-            }
+            for (int j = 0; j < 4; ++j) if (col + j < tl.n_rem) ss = __fmaf_rn(xs[j], xs[j], ss);
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (col + j < tl.n_rem) ss = __fmaf_rn(x[j], x[j], ss);
-          if (cvec && full4) {
-            *reinterpret_cast<float4*>(crow + col) = make_float4(x[0], x[1], x[2], x[3]);
+#ifdef MSACL_GEMM_DEBUG_NOSTORE     // (bottleneck triage: no global stores of the result, except a never-true sentinel)
+          if (x[0] == 123456.789f) crow[col8] = x[1];
+          continue;
+#endif
+          if (cvec8 && col8 + 7 < tl.n_rem) {
+            // one 32-byte store per lane (STG.256): a whole sector, half the store instructions / LSU wavefronts of two
+            // 16-byte stores (the thread-per-row epilogue touches 32 lines per instruction either way)
+            g_stg256(crow + col8, x);
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (col + j < tl.n_rem) crow[col + j] = x[j];
+            for (int hq = 0; hq < 2; ++hq) {
+              const int col = col8 + 4 * hq;
+              if (col >= tl.n_rem) break;
+              if (cvec && col + 3 < tl.n_rem) {
+                *reinterpret_cast<float4*>(crow + col) = make_float4(x[4 * hq], x[4 * hq + 1], x[4 * hq + 2], x[4 * hq + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (col + j < tl.n_rem) crow[col + j] = x[4 * hq + j];
+              }
+            }
           }
         }
       }
@@ -527,7 +625,7 @@ extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
   X(2, 64, 4, false) X(3, 64, 4, false)
   if (!attr_set) {
     bool ok = true;
-#define X(NI, BN_, ST, SM_) ok = ok && set_attr(gemm_tc_kernel<NI, BN_, ST, SM_>, sizeof(GemmSmem<NI, BN_, ST>) + 128);
+#define X(NI, BN_, ST, SM_) ok = ok && set_attr(gemm_tc_kernel<NI, BN_, ST, SM_>, sizeof(GemmSmem<NI, BN_, ST, SM_>) + 128);
     MSACL_GEMM_VARIANTS(X)
 #undef X
     if (!ok) { set_error("gemm_tc: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"); return MSACL_ERR_CUDA; }
@@ -536,9 +634,9 @@ extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nimg = g->precision == 3 ? 2 : 3;
   // streamed mode: pre-packed weights (BN = 256) behind a k-contiguous, 16-byte aligned A operand
-  const bool streamed = bn == 256 && g->b_packed && g->a_k_stride == 1 && (g->a_row_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g->a) & 15) == 0;
+  const bool streamed = bn == 256 && g->b_packed && g->a_k_stride == 1 && (g->a_row_stride & 7) == 0 && (reinterpret_cast<uintptr_t>(g->a) & 31) == 0;
 #define X(NI, BN_, ST, SM_) \
-  if (nimg == NI && bn == BN_ && streamed == SM_) gemm_tc_kernel<NI, BN_, ST, SM_><<<grid, G_THREADS, sizeof(GemmSmem<NI, BN_, ST>) + 128, st>>>(*g);
+  if (nimg == NI && bn == BN_ && streamed == SM_) gemm_tc_kernel<NI, BN_, ST, SM_><<<grid, G_THREADS, sizeof(GemmSmem<NI, BN_, ST, SM_>) + 128, st>>>(*g);
   MSACL_GEMM_VARIANTS(X)
 #undef X
 #undef MSACL_GEMM_VARIANTS
