@@ -349,7 +349,12 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           for (int j = 0; j < NS; ++j)
             if (s0 + j < nt) TC_WAIT(&sm.bars.logits[s0 + j], lcount & 1, 1, lcount);
         } else {
+#if defined(MSACL_TC_ENV_SLEEP) && !defined(MSACL_TC_WATCHDOG)
+          // (experiment) back off between probes: an env warp waits ~26 k cycles for its logits on average
+          while (!tc::mbar_test(&sm.bars.logits[s], lcount & 1)) __nanosleep(MSACL_TC_ENV_SLEEP);
+#else
           TC_WAIT(&sm.bars.logits[s], lcount & 1, 1, lcount);
+#endif
         }
         float lg[A2];
         if constexpr (PARK) {
