@@ -33,7 +33,8 @@ class nStepExperience(NamedTuple):
 
 
 class ActorWeights:
-    """Device copy of a StochaPolicy MLP (obs -> 256 -> 256 -> 2*act), packed for the kernel."""
+    """Device copy of a StochaPolicy MLP (obs -> h1 -> h2 -> 2*act, ReLU, h1, h2 <= 256: zero-padded to the kernels' 256-wide
+    layers), packed for the fused rollout kernels."""
 
     HIDDEN = 256
 
@@ -41,10 +42,24 @@ class ActorWeights:
         (w1, b1), (w2, b2), (w3, b3) = layers
         dev = torch.device(device)
         t = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a.detach(), dtype=torch.float32).to(dev).contiguous()
-        self.w1, self.b1, self.b2, self.w3, self.b3 = t(w1), t(b1), t(b2), t(w3), t(b3)
-        self.w2t = t(w2).t().contiguous()
-        if self.w1.shape[0] != self.HIDDEN or tuple(self.w2t.shape) != (self.HIDDEN, self.HIDDEN) or self.w3.shape[1] != self.HIDDEN:
-            raise ValueError("the fused rollout kernel is specialised for policy_hidden_sizes=[256, 256]")
+        w1, b1, w2, b2, w3, b3 = t(w1), t(b1), t(w2), t(b2), t(w3), t(b3)
+        H = self.HIDDEN
+        h1, h2 = w1.shape[0], w2.shape[0]
+        if w2.shape[1] != h1 or w3.shape[1] != h2:
+            raise ValueError("layer widths do not chain")
+        if h1 > H or h2 > H:
+            raise ValueError("the fused rollout kernels hold two hidden layers of at most 256 units (policy_hidden_sizes=[256, 256] "
+                             "is the reference default); wider policies run on the general engine")
+        if (h1, h2) != (H, H):
+            # narrower ReLU layers are embedded in the 256-wide kernel by zero padding: the extra units have zero weights and
+            # biases, relu(0) = 0, and adding exact zeros changes no partial sum -- the logits are those of the narrow network
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+            W1, B1, W2, B2, W3 = z(H, w1.shape[1]), z(H), z(H, H), z(H), z(w3.shape[0], H)
+            W1[:h1] = w1; B1[:h1] = b1; W2[:h2, :h1] = w2; B2[:h2] = b2; W3[:, :h2] = w3
+            w1, b1, w2, b2, w3 = W1, B1, W2, B2, W3
+        self.hidden_sizes = (h1, h2)
+        self.w1, self.b1, self.b2, self.w3, self.b3 = w1, b1, b2, w3, b3
+        self.w2t = w2.t().contiguous()
         self.obs_dim = self.w1.shape[1]
         self.act_dim = self.w3.shape[0] // 2
         self.desc = _lib.Actor(w1=self.w1.data_ptr(), b1=self.b1.data_ptr(), w2t=self.w2t.data_ptr(), b2=self.b2.data_ptr(),
@@ -89,7 +104,7 @@ class ActorWeights:
 
 class GeneralActor:
     """Any StochaPolicy MLP (RL/apprfunc/mlp.py:18-33,111-136): Linear / activation pairs of arbitrary depth, width and
-    activation -- the policies `ActorWeights` (the fused rollout kernels: two hidden layers of 256 ReLU units) cannot take.
+    activation -- the policies `ActorWeights` (the fused rollout kernels: two ReLU hidden layers of at most 256 units) cannot take.
     A forward pass is one `msacl_gemm_tc` per layer (split-bf16 tcgen05 GEMM at FP32-class precision; bias and ReLU / Tanh
     fused into the epilogue, any other activation module applied in place to the GEMM output); layer 1 reads the
     observations straight out of the structure-of-arrays env state (row stride 1, k stride = env pitch)."""
@@ -149,8 +164,9 @@ class GeneralActor:
 
 
 def actor_from_policy(policy, device="cuda", strict=False):
-    """The packed actor the rollout engines take: `ActorWeights` for the [256, 256] ReLU policy the fused kernels are
-    specialised for, else (unless `strict`) a `GeneralActor` driving per-layer GEMMs + msacl_rollout_step."""
+    """The packed actor the rollout engines take: `ActorWeights` for the policies the fused kernels hold (two ReLU hidden
+    layers of at most 256 units; reference default [256, 256]), else (unless `strict`) a `GeneralActor` driving per-layer
+    GEMMs + msacl_rollout_step."""
     try:
         return ActorWeights.from_policy(policy, device=device)
     except ValueError:

@@ -20,7 +20,20 @@ def test_default_policy_takes_the_fused_actor():
     assert tuple(a.w2t.shape) == (256, 256)
 
 
-@pytest.mark.parametrize("sizes,act", [([4, 64, 64, 4], torch.nn.ReLU), ([12, 256, 256, 8], torch.nn.Tanh),
+def test_narrow_relu_policy_is_zero_padded_into_the_fused_actor():
+    pol = _policy([7, 64, 96, 4], torch.nn.ReLU)
+    a = actor_from_policy(pol, device="cpu")
+    assert isinstance(a, ActorWeights) and a.hidden_sizes == (64, 96)
+    assert tuple(a.w1.shape) == (256, 7) and tuple(a.w2t.shape) == (256, 256) and tuple(a.w3.shape) == (4, 256)
+    x = torch.randn(33, 7)
+    with torch.no_grad():
+        want = pol(x)
+        got = torch.relu(torch.relu(x @ a.w1.t() + a.b1) @ a.w2t + a.b2) @ a.w3.t() + a.b3
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-6)
+    assert float(a.w1[64:].abs().max()) == 0.0 and float(a.w2t[64:].abs().max()) == 0.0 and float(a.w2t[:, 96:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("sizes,act", [([4, 300, 64, 4], torch.nn.ReLU), ([12, 256, 256, 8], torch.nn.Tanh),
                                        ([2, 256, 256, 256, 2], torch.nn.ReLU), ([7, 300, 4], torch.nn.GELU)])
 def test_other_policies_take_the_general_actor(sizes, act):
     pol = _policy(sizes, act)

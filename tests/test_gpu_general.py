@@ -90,6 +90,28 @@ def test_general_engine_matches_fused_engine_on_the_default_policy(name):
     np.testing.assert_allclose(a.stats[:5].cpu().numpy(), b.stats[:5].cpu().numpy(), rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("name,hidden,engine", [("Pendulum", (64, 64), "tc"), ("QuadTracking", (128, 32), "tc"), ("DuctedFan", (40, 200), "ffma")])
+def test_narrow_relu_policy_runs_on_the_fused_kernels_zero_padded(name, hidden, engine):
+    """Two ReLU hidden layers narrower than 256 are embedded in the fused kernels' 256-wide layers by zero padding: same logits
+    as the narrow network (oracle), at fused-kernel speed."""
+    from msacl_b200.sampler import ActorWeights, FusedRollout
+    n, K, seed = 640, 5, 7
+    spec = oenv.SPECS[name]
+    w = oactor.init_policy_weights(spec.obs_dim, spec.act_dim, hidden=hidden, seed=5)
+    aw = ActorWeights(w)
+    assert aw.hidden_sizes == hidden
+    ro = FusedRollout(name, n, K, n_step=3, seed=seed, engine=engine, record_logits=True)
+    ro.state.reset()
+    eps = np.random.default_rng(3).standard_normal((K, n, spec.act_dim)).astype(np.float32)
+    ro.run(aw, eps=torch.as_tensor(eps).cuda())
+    obs = ro.tr.obs[ro.tr.H:].cpu().numpy()
+    logits = ro.tr.logits.cpu().numpy()
+    tol = 5e-5 if engine == "tc" else 2e-5
+    for k in range(K):          # the kernel's own observation through the narrow network (NumPy)
+        want = oactor.mlp_forward(w, obs[k])
+        assert np.abs(logits[k] - want).max() <= tol * max(np.abs(want).max(), 1.0)
+
+
 def test_sampler_selects_the_general_engine_for_other_policies():
     """policy_hidden_sizes / activation other than the fused kernels' [256, 256] ReLU: the reference-compatible sampler
     falls back to the general engine (and refuses when a fused engine was requested by name)."""
