@@ -319,12 +319,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
       auto refill = [&](int ph) {
         ok[ph] = cok;
         if (cok) {
-#ifdef MSACL_GEMM_DEBUG_NOLOAD      // (bottleneck triage: no global loads of the A operand)
-#pragma unroll
-          for (int q = 0; q < 16; ++q) r[ph][q >> 3][q & 7] = (float)(t + q);
-#else
           g_k8_load(r[ph], g.a, g.a_row_stride, ctl.m0, g.m, ctl.kbeg + cit * GK, ctl.kend, t);
-#endif
           kst[ph] = (ctl.kbeg + cit * GK) / GK;
           ++cit;
           settle();
@@ -520,10 +515,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(msacl_gemm_t g) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (col + j < tl.n_rem) ss = __fmaf_rn(xs[j], xs[j], ss);
           }
-#ifdef MSACL_GEMM_DEBUG_NOSTORE     // (bottleneck triage: no global stores of the result, except a never-true sentinel)
-          if (x[0] == 123456.789f) crow[col8] = x[1];
-          continue;
-#endif
           if (cvec8 && col8 + 7 < tl.n_rem) {
             // one 32-byte store per lane (STG.256): a whole sector, half the store instructions / LSU wavefronts of two
             // 16-byte stores (the thread-per-row epilogue touches 32 lines per instruction either way)

@@ -217,11 +217,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   using CFG = TcCfg<NS>;
   constexpr int D = E::D, A = E::A, A2 = 2 * A;
   constexpr int NT = NS * TPW;                 // tiles in flight per CTA ("group"); tile slot s belongs to warpgroup s % NS
-#ifdef MSACL_TC_FORCE_PARK
-  constexpr bool PARK = true;                  // (experiment: TPW = 1 scheduling with the TPW = 2 hand-overs)
-#else
   constexpr bool PARK = TPW > 1;
-#endif
   // env state parked in global memory between steps, logits through global scratch
   static_assert(NT <= SCR_TILES && A2 <= 8, "scratch layout");
   constexpr int TC_THREADS = CFG::THREADS, NB = S::NB, XH = S::XH, W1H = S::W1H, W3S = tc_w3_stride<ID>();
@@ -276,15 +272,8 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   if (warp < W_EPI1) {
     // =========================== env warps ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CFG::ENV_REGS));
-#ifdef MSACL_TC_COLOC
-    // (experiment) NS == 4: the four warps of an env warpgroup share one SM sub-partition (warp % 4), so they run the
-    // same instruction stream through the same L0 instruction cache
-    const int w = NS == 4 ? (warp & 3) : (warp >> 2);
-    const int r = NS == 4 ? ((warp >> 2) * 32 + lane) : (tid & (TCM - 1));
-#else
     const int w = warp >> 2;                 // env warpgroup: tile slots w, w + NS, ...
     const int r = tid & (TCM - 1);
-#endif
     uint32_t xcount = 0;                     // X operands this warpgroup has written
     uint32_t lcount = 0;                     // logits deliveries each of its tile slots has consumed
     float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_term = 0.f, st_trunc = 0.f;
@@ -349,12 +338,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
           for (int j = 0; j < NS; ++j)
             if (s0 + j < nt) TC_WAIT(&sm.bars.logits[s0 + j], lcount & 1, 1, lcount);
         } else {
-#if defined(MSACL_TC_ENV_SLEEP) && !defined(MSACL_TC_WATCHDOG)
-          // (experiment) back off between probes: an env warp waits ~26 k cycles for its logits on average
-          while (!tc::mbar_test(&sm.bars.logits[s], lcount & 1)) __nanosleep(MSACL_TC_ENV_SLEEP);
-#else
           TC_WAIT(&sm.bars.logits[s], lcount & 1, 1, lcount);
-#endif
         }
         float lg[A2];
         if constexpr (PARK) {
