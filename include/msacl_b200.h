@@ -218,6 +218,18 @@ int msacl_window_index_store(const uint8_t* emit_new, int32_t K, int64_t n, int6
 int msacl_window_gather_indexed(const msacl_transitions_t* tr, int64_t n, const int64_t* win_pos, const int64_t* idx,
                                 int64_t B, const msacl_ring_t* batch, void* stream);
 
+/* NstepReplayBuffer.sample_batch (nstep_replay_buffer.py:138-146) of the index-based store in one launch, without a host
+ * read of the counters: window b of the batch is drawn uniformly (with replacement) from the `valid` most recent ring
+ * entries, valid = min(ptr_size[1], sum of launch_counts[0..n_counts)) -- the windows whose slices are still resident --
+ * with a Philox4x32-10 draw keyed by (seed, draw, b), and gathered like msacl_window_gather_indexed.
+ *   ptr_size       device int64[2] as maintained by msacl_window_index_store
+ *   launch_counts  device int64[n_counts]: windows emitted by each of the launches that are still resident
+ *   slots_out      optional device int64[B]: the ring slots that were drawn
+ * valid == 0 leaves the batch untouched. */
+int msacl_window_sample_indexed(const msacl_transitions_t* tr, int64_t n, const int64_t* win_pos, int64_t max_size,
+                                const int64_t* ptr_size, const int64_t* launch_counts, int32_t n_counts, uint64_t seed,
+                                uint64_t draw, int64_t B, const msacl_ring_t* batch, int64_t* slots_out, void* stream);
+
 /* MSACL soft-TD backup (RL/algorithm/msacl.py:249-252), elementwise over B*n. */
 int msacl_q_backup(int64_t count, const float* rew, const float* done, const float* next_q1, const float* next_q2,
                    const float* next_logp, float gamma, float alpha, float* backup, void* stream);

@@ -77,6 +77,8 @@ SIGNATURES = {
                                      vp, vp]),
     "msacl_window_index_store": (C.c_int, [vp, C.c_int32, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, vp, vp]),
     "msacl_window_gather_indexed": (C.c_int, [C.POINTER(Transitions), C.c_int64, vp, vp, C.c_int64, C.POINTER(Ring), vp]),
+    "msacl_window_sample_indexed": (C.c_int, [C.POINTER(Transitions), C.c_int64, vp, C.c_int64, vp, vp, C.c_int32, C.c_uint64, C.c_uint64,
+                                              C.c_int64, C.POINTER(Ring), vp, vp]),
     "msacl_ring_gather": (C.c_int, [C.POINTER(Ring), vp, C.c_int64, C.POINTER(Ring), vp]),
     "msacl_q_backup": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp]),
     "msacl_lyapunov_risk": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_float,

@@ -141,8 +141,8 @@ class B200IndexedReplayBuffer:
         self._tr = None                  # the sampler's TransitionBuffers, bound on the first add_batch
         self._launch_counts = None       # windows emitted by each of the last M - 2 launches (device, circular)
         self._adds = 0
-        self._gen = torch.Generator(device=self.device)
-        self._gen.manual_seed(int(kwargs.get("seed") or 0))
+        self._seed = int(kwargs.get("seed") or 0) & (2 ** 64 - 1)
+        self._draws = 0                  # sample_batch calls so far: keys the Philox index draws together with the seed
 
     @staticmethod
     def chunks_for(buffer_max_size, num_envs, horizon):
@@ -221,12 +221,22 @@ class B200IndexedReplayBuffer:
                                                           C.byref(dst), _lib.current_stream()))
         return out
 
-    def sample_batch(self, batch_size: int, out=None) -> dict:
-        """Uniform with replacement over the resident windows (nstep_replay_buffer.py:138), drawn on the device."""
+    def sample_batch(self, batch_size: int, out=None, return_slots=False) -> dict:
+        """Uniform with replacement over the resident windows (nstep_replay_buffer.py:138-146): index draw (Philox keyed by
+        the buffer seed and a call counter) and gather in ONE launch that reads ptr / size / residency from the device."""
         if self._tr is None:
             raise RuntimeError("sample_batch before any add_batch")
-        u = torch.rand(int(batch_size), device=self.device, generator=self._gen, dtype=torch.float64)
-        valid = self.valid_count()
-        back = torch.minimum((u * valid).to(torch.int64), torch.clamp(valid - 1, min=0))      # 0 = newest entry
-        slot = torch.remainder(self._ptr_size[0] - 1 - back, self.max_size)
-        return self.gather(slot, out=out)
+        B = int(batch_size)
+        n, D, A = self.n_step, self.obsv_dim, self.act_dim
+        z = lambda *s: torch.empty(B, n, *s, dtype=torch.float32, device=self.device)
+        if out is None:
+            out = {"obs": z(D), "act": z(A), "rew": z(), "cost": z(), "obs2": z(D), "done": z(), "logp": z()}
+        dst = _lib.Ring(max_size=B, n_step=n, obs_dim=D, act_dim=A, **{k: out[k].data_ptr() for k in FIELDS})
+        slots = torch.empty(B, dtype=torch.int64, device=self.device) if return_slots else None
+        desc = self._tr.full_desc()
+        self._draws += 1
+        _lib.check(_lib.load().msacl_window_sample_indexed(C.byref(desc), self._tr.n, self.win_pos.data_ptr(), self.max_size,
+                                                          self._ptr_size.data_ptr(), self._launch_counts.data_ptr(),
+                                                          self._launch_counts.numel(), self._seed, self._draws, B, C.byref(dst),
+                                                          None if slots is None else slots.data_ptr(), _lib.current_stream()))
+        return (out, slots) if return_slots else out

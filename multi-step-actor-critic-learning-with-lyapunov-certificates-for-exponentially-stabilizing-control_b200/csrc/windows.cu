@@ -9,6 +9,7 @@
 // Integer bookkeeping is bit-exact; payload is copied verbatim.  HBM-bound:
 // bytes per stored window = 2 * 4 * n_step * (2D + A + 4)  (read transitions + write ring).
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace msacl {
 
@@ -312,6 +313,37 @@ window_gather_indexed_kernel(msacl_transitions_t tr, int64_t n, const int64_t* _
     cp.copy(win_pos[idx[b]], b);
 }
 
+// sample_batch of the index-based replay in ONE launch (nstep_replay_buffer.py:138-146: uniform with replacement over the
+// stored windows): warp b draws u ~ U[0, 1) from Philox keyed by (seed, draw counter, b), walks `back = floor(u * valid)`
+// entries back from the newest ring slot -- valid = min(size, windows emitted by the launches whose slices are still
+// resident), all read from device counters, so the host never synchronises -- and gathers that window.
+template <int W>
+__global__ void __launch_bounds__(256)
+window_sample_indexed_kernel(msacl_transitions_t tr, int64_t n, const int64_t* __restrict__ win_pos, int64_t max_size,
+                             const int64_t* __restrict__ ptr_size, const int64_t* __restrict__ launch_counts, int n_counts,
+                             uint64_t seed, uint64_t draw, int64_t B, msacl_ring_t batch, int64_t* __restrict__ slots_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x / 32);
+  int64_t resident = 0;
+  for (int i = 0; i < n_counts; ++i) resident += launch_counts[i];
+  const int64_t ptr = ptr_size[0], size = ptr_size[1];
+  const int64_t valid = size < resident ? size : resident;
+  if (valid <= 0) return;                                  // nothing stored yet: the batch is left untouched
+  WindowCopier<W> cp(tr, n, batch, lane);
+  for (int64_t b = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); b < B; b += wstride) {
+    const U4 r = philox4x32_10((uint32_t)b, (uint32_t)((uint64_t)b >> 32), (uint32_t)draw, (uint32_t)(draw >> 32) ^ 0x5EED5A3Du,
+                               (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint64_t bits = ((uint64_t)(r.x >> 5) << 26) | (uint64_t)(r.y >> 6);          // 53 random bits
+    const double u = (double)bits * 1.1102230246251565e-16;                               // * 2^-53: [0, 1)
+    int64_t back = (int64_t)(u * (double)valid);
+    if (back > valid - 1) back = valid - 1;
+    int64_t slot = (ptr - 1 - back) % max_size;
+    if (slot < 0) slot += max_size;
+    if (slots_out && lane == 0) slots_out[b] = slot;
+    cp.copy(win_pos[slot], b);
+  }
+}
+
 // One warp per sampled window (grid-stride).  Every field of a window is a contiguous run of floats; with
 // n_step % 4 == 0 (reference default 20) all runs are whole, 16-byte aligned float4 vectors, and the window is copied as
 // ONE flat list of vectors (obs | obs2 | act | rew | cost | done | logp).  The vector -> (field, offset) map is the same
@@ -459,6 +491,33 @@ extern "C" int msacl_window_gather_indexed(const msacl_transitions_t* tr, int64_
   else if (W == 2) window_gather_indexed_kernel<2><<<grid, wpb * 32, 0, st>>>(*tr, n, win_pos, idx, B, *batch);
   else window_gather_indexed_kernel<1><<<grid, wpb * 32, 0, st>>>(*tr, n, win_pos, idx, B, *batch);
   return check_launch("window_gather_indexed");
+}
+
+extern "C" int msacl_window_sample_indexed(const msacl_transitions_t* tr, int64_t n, const int64_t* win_pos, int64_t max_size,
+                                           const int64_t* ptr_size, const int64_t* launch_counts, int32_t n_counts, uint64_t seed,
+                                           uint64_t draw, int64_t B, const msacl_ring_t* batch, int64_t* slots_out, void* stream) {
+  if (int rc = validate_ring(batch)) return rc;
+  if (!tr || !tr->obs || !tr->act || !tr->rew || !tr->cost || !tr->obs2 || !tr->done || !tr->logp || !win_pos || !ptr_size ||
+      !launch_counts || n_counts <= 0 || max_size <= 0 || B <= 0 || n <= 0) {
+    set_error("window_sample_indexed: bad argument");
+    return MSACL_ERR_BAD_ARG;
+  }
+  const int wpb = 8;
+  const int64_t want = (B + wpb - 1) / wpb, cap = (int64_t)kNumSMs * 8;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  const int D = batch->obs_dim;
+  auto misaligned = [&](const void* p, int w) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(4 * w - 1)) != 0; };
+  int W = (D % 4 == 0) ? 4 : ((D % 2 == 0) ? 2 : 1);
+  while (W > 1 && (misaligned(tr->obs, W) || misaligned(tr->obs2, W) || misaligned(batch->obs, W) || misaligned(batch->obs2, W))) W >>= 1;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MSACL_SAMPLE_LAUNCH(W_)                                                                                                  \
+  window_sample_indexed_kernel<W_><<<grid, wpb * 32, 0, st>>>(*tr, n, win_pos, max_size, ptr_size, launch_counts, n_counts, seed, draw, B, \
+                                                              *batch, slots_out)
+  if (W == 4) MSACL_SAMPLE_LAUNCH(4);
+  else if (W == 2) MSACL_SAMPLE_LAUNCH(2);
+  else MSACL_SAMPLE_LAUNCH(1);
+#undef MSACL_SAMPLE_LAUNCH
+  return check_launch("window_sample_indexed");
 }
 
 extern "C" int msacl_ring_gather(const msacl_ring_t* ring, const int64_t* idx, int64_t B, const msacl_ring_t* batch,

@@ -166,6 +166,19 @@ def test_indexed_replay_equals_reference_layout_ring(name, ring_size, chunks):
     assert ref.size > 0 and launch >= 2 * chunks
     s = ixb.sample_batch(64)
     assert set(s) == set(FIELDS) and s["obs"].shape == (64, n_step, spec.obs_dim) and s["done"].dtype == torch.float32
+    # the one-launch sample_batch: the drawn slots lie among the `resident` most recent entries, the batch is exactly the
+    # gather of those slots, the draws are uniform over them and differ from call to call
+    big, slots = ixb.sample_batch(20000, return_slots=True)
+    back = (ixb.ptr - 1 - slots.cpu().numpy()) % ring_size
+    assert back.min() >= 0 and back.max() < resident
+    want = ixb.gather(slots)
+    for k in FIELDS:
+        assert torch.equal(big[k], want[k]), k
+    hist = np.bincount(back, minlength=resident)
+    assert hist.min() > 0 or resident > 4000
+    assert abs(back.mean() - (resident - 1) / 2) < 4 * resident / np.sqrt(12 * 20000)
+    _, slots2 = ixb.sample_batch(20000, return_slots=True)
+    assert not torch.equal(slots, slots2)
     with pytest.raises(NotImplementedError):
         ixb.store(None)
 
