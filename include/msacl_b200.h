@@ -218,6 +218,12 @@ int msacl_window_index_store(const uint8_t* emit_new, int32_t K, int64_t n, int6
 int msacl_window_gather_indexed(const msacl_transitions_t* tr, int64_t n, const int64_t* win_pos, const int64_t* idx,
                                 int64_t B, const msacl_ring_t* batch, void* stream);
 
+/* NstepReplayBuffer.sample_batch (nstep_replay_buffer.py:138-146) of the reference-layout ring: idx[b] ~ U{0..size-1} drawn on
+ * the device (Philox keyed by (seed, draw, b); size = ptr_size[1] read on the device), then msacl_ring_gather.
+ *   idx  device int64[B], receives the drawn slots */
+int msacl_ring_sample(const msacl_ring_t* ring, const int64_t* ptr_size, uint64_t seed, uint64_t draw, int64_t B,
+                      const msacl_ring_t* batch, int64_t* idx, void* stream);
+
 /* NstepReplayBuffer.sample_batch (nstep_replay_buffer.py:138-146) of the index-based store in one launch, without a host
  * read of the counters: window b of the batch is drawn uniformly (with replacement) from the `valid` most recent ring
  * entries, valid = min(ptr_size[1], sum of launch_counts[0..n_counts)) -- the windows whose slices are still resident --

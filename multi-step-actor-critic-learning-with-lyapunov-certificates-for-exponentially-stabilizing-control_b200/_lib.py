@@ -77,6 +77,7 @@ SIGNATURES = {
                                      vp, vp]),
     "msacl_window_index_store": (C.c_int, [vp, C.c_int32, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, vp, vp]),
     "msacl_window_gather_indexed": (C.c_int, [C.POINTER(Transitions), C.c_int64, vp, vp, C.c_int64, C.POINTER(Ring), vp]),
+    "msacl_ring_sample": (C.c_int, [C.POINTER(Ring), vp, C.c_uint64, C.c_uint64, C.c_int64, C.POINTER(Ring), vp, vp]),
     "msacl_window_sample_indexed": (C.c_int, [C.POINTER(Transitions), C.c_int64, vp, C.c_int64, vp, vp, C.c_int32, C.c_uint64, C.c_uint64,
                                               C.c_int64, C.POINTER(Ring), vp, vp]),
     "msacl_ring_gather": (C.c_int, [C.POINTER(Ring), vp, C.c_int64, C.POINTER(Ring), vp]),

@@ -30,8 +30,9 @@ class B200NstepReplayBuffer:
         self._scratch = None
         self._host_ps = (0, 0)
         self._ring = self._make_ring(self.n_step_buf, self.max_size)
-        self._gen = torch.Generator(device=self.device)
-        self._gen.manual_seed(int(kwargs.get("seed") or 0))
+        self._seed = int(kwargs.get("seed") or 0) & (2 ** 64 - 1)
+        self._draws = 0                  # sample_batch calls so far: keys the Philox index draws together with the seed
+        self._idx = None
 
     def _make_ring(self, bufs, max_size):
         return _lib.Ring(max_size=max_size, n_step=self.n_step, obs_dim=self.obsv_dim, act_dim=self.act_dim,
@@ -104,11 +105,17 @@ class B200NstepReplayBuffer:
 
     def sample_batch(self, batch_size: int, out=None) -> dict:
         """Uniform sampling with replacement over the valid range (nstep_replay_buffer.py:138)."""
-        # idx ~ U{0..size-1} drawn on the device from the device-resident size (no host synchronisation)
-        u = torch.rand(int(batch_size), device=self.device, generator=self._gen, dtype=torch.float64)
-        size = self._ptr_size[1]
-        idx = torch.minimum((u * size).to(torch.int64), torch.clamp(size - 1, min=0))
-        return self.gather(idx, out=out)
+        # idx ~ U{0..size-1} drawn by the library from the device-resident size (no host synchronisation, two launches)
+        B = int(batch_size)
+        if out is None:
+            out = {k: torch.empty(B, *v.shape[1:], dtype=torch.float32, device=self.device) for k, v in self.n_step_buf.items()}
+        dst = self._make_ring(out, B)
+        if self._idx is None or self._idx.numel() < B:
+            self._idx = torch.empty(B, dtype=torch.int64, device=self.device)
+        self._draws += 1
+        _lib.check(_lib.load().msacl_ring_sample(C.byref(self._ring), self._ptr_size.data_ptr(), self._seed, self._draws, B, C.byref(dst),
+                                                self._idx.data_ptr(), _lib.current_stream()))
+        return out
 
 
 class B200IndexedReplayBuffer:

@@ -520,6 +520,32 @@ extern "C" int msacl_window_sample_indexed(const msacl_transitions_t* tr, int64_
   return check_launch("window_sample_indexed");
 }
 
+// idx[b] ~ U{0 .. size - 1} (nstep_replay_buffer.py:138 `np.random.randint(0, self.size, batch_size)`), Philox keyed by
+// (seed, draw, b); size is read from the device counters
+__global__ void __launch_bounds__(256) ring_draw_kernel(const int64_t* __restrict__ ptr_size, uint64_t seed, uint64_t draw, int64_t B,
+                                                        int64_t* __restrict__ idx) {
+  const int64_t size = ptr_size[1];
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const U4 r = philox4x32_10((uint32_t)b, (uint32_t)((uint64_t)b >> 32), (uint32_t)draw, (uint32_t)(draw >> 32) ^ 0x5EED5A3Du,
+                               (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint64_t bits = ((uint64_t)(r.x >> 5) << 26) | (uint64_t)(r.y >> 6);
+    int64_t i = (int64_t)((double)bits * 1.1102230246251565e-16 * (double)size);
+    if (i > size - 1) i = size - 1;
+    idx[b] = i < 0 ? 0 : i;
+  }
+}
+
+extern "C" int msacl_ring_gather(const msacl_ring_t* ring, const int64_t* idx, int64_t B, const msacl_ring_t* batch, void* stream);
+
+extern "C" int msacl_ring_sample(const msacl_ring_t* ring, const int64_t* ptr_size, uint64_t seed, uint64_t draw, int64_t B,
+                                 const msacl_ring_t* batch, int64_t* idx, void* stream) {
+  if (!ptr_size || !idx || B <= 0) { set_error("ring_sample: bad argument"); return MSACL_ERR_BAD_ARG; }
+  const int64_t want = (B + 255) / 256;
+  ring_draw_kernel<<<(unsigned)(want < 1184 ? want : 1184), 256, 0, (cudaStream_t)stream>>>(ptr_size, seed, draw, B, idx);
+  if (int rc = check_launch("ring_sample")) return rc;
+  return msacl_ring_gather(ring, idx, B, batch, stream);
+}
+
 extern "C" int msacl_ring_gather(const msacl_ring_t* ring, const int64_t* idx, int64_t B, const msacl_ring_t* batch,
                                  void* stream) {
   if (int rc = validate_ring(ring)) return rc;

@@ -56,6 +56,13 @@ def test_window_store_matches_oracle_ring(name, ring_size):
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
     b = buf.sample_batch(64)
     assert set(b) == set(FIELDS) and b["obs"].shape == (64, n_step, spec.obs_dim) and b["rew"].shape == (64, n_step)
+    # sample_batch = library-side index draw over [0, size) + gather: the batch is the ring at the drawn slots
+    big = buf.sample_batch(5000)
+    idx = buf._idx[:5000].cpu().numpy()
+    assert idx.min() >= 0 and idx.max() < ring.size and abs(idx.mean() - (ring.size - 1) / 2) < 4 * ring.size / np.sqrt(12 * 5000)
+    want = ring.gather(idx)
+    for k in FIELDS:
+        assert np.array_equal(big[k].cpu().numpy(), want[k]), k
 
 
 @pytest.mark.parametrize("chunks", [1, 2, None])
