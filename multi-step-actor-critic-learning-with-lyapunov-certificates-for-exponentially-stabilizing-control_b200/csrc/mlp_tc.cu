@@ -606,6 +606,10 @@ extern "C" int msacl_gemm_tc(const msacl_gemm_t* g, void* stream) {
       if (best_waves < 0 || waves < best_waves) { best_waves = waves; bn = cand; }
     }
   }
+  // a pre-packed weight operand is a 256-wide column tile: take the streamed-weights instantiation also for few row tiles
+  // (measured at 40 row tiles: the learner's model_update at replay batch 256 drops from 1.14 to 1.00 ms -- bulk-copied
+  // weights and the pipelined A loader beat the converting loaders' one memory round trip per K stage, even with 40 CTAs)
+  if (g->b_packed) bn = 256;
   const int64_t tiles = mt * ((g->n + bn - 1) / bn) * g->split_k;
   const dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));          // persistent: one CTA per SM
   static bool attr_set = false;

@@ -66,10 +66,11 @@ class MLPWorkspace:
         self.h1, self.h2, self.y = f(M, H1), f(M, H2), f(M, Dout)
         self.v = f(M) if sumsq else None
         self.x = None
-        # Many row tiles (>= one per SM): the weight operands of the forward / dgrad GEMMs are pre-converted once per call
-        # (msacl_gemm_pack_b) and streamed by bulk copies, instead of being re-converted from FP32 in each of the CTAs.
+        # The weight operands of the forward / dgrad GEMMs are pre-converted once per call (msacl_gemm_pack_b) and streamed by
+        # bulk copies instead of being re-converted from FP32 in each of the CTAs -- also for few row tiles, where the
+        # streamed-weights kernel's pipelined loader wins on latency (model_update at replay batch 256: 1.14 -> 1.00 ms).
         self.packed = {}
-        pack_ok = (M + 127) // 128 >= 148
+        pack_ok = True
 
         def packed(tag, k, n):
             if not pack_ok or n > 256:               # a pre-packed operand covers one 256-wide column tile
