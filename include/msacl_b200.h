@@ -297,8 +297,8 @@ typedef struct {
   int32_t precision;   /* bf16 products per algorithmic product: 6 (or 0 = default; 3-term operand split, FP32-class ~2^-23)
                           or 3 (2-term split, ~1.5e-5 relative per product, half the tensor work) */
   const void* b_packed; /* optional: the B operand pre-converted by msacl_gemm_pack_b (same b / strides / n / k / precision);
-                          used when the launch takes 256-wide column tiles (many row tiles): the B stages are then streamed
-                          by bulk copies instead of being re-converted from `b` in every CTA.  `b` must still be valid. */
+                          the launch then takes 256-wide column tiles and the B stages are streamed by bulk copies instead
+                          of being re-converted from `b` in every CTA.  `b` must still be valid. */
 } msacl_gemm_t;
 int msacl_gemm_tc(const msacl_gemm_t* g, void* stream);
 /* Pre-convert the B operand described by g (b, b_row_stride, b_k_stride, n <= 256, k, precision) into the kernel's
@@ -307,7 +307,7 @@ int msacl_gemm_tc(const msacl_gemm_t* g, void* stream);
 int64_t msacl_gemm_packed_b_bytes(int32_t k, int32_t precision);
 int msacl_gemm_pack_b(const msacl_gemm_t* g, void* packed, void* stream);
 
-/* out[z][c] = sum over the rows of split z (rows divided evenly over `splits`) of x[r*ld + c]; cols <= 256.  Bias gradients. */
+/* out[z][c] = sum over the rows of split z (rows divided evenly over `splits`) of x[r*ld + c].  Bias gradients. */
 int msacl_colsum(const float* x, int64_t rows, int32_t cols, int64_t ld, int32_t splits, float* out, void* stream);
 /* out[r] = [a[r] | b[r]]  (ActionValue input, mlp.py:50-52) */
 int msacl_concat2(const float* a, int32_t da, const float* b, int32_t db, int64_t rows, float* out, void* stream);

@@ -127,6 +127,7 @@ class GeneralActor:
         self.precision = int(precision)
         self.device = dev
         self._ws = {}
+        self._packed = None
 
     @classmethod
     def from_policy(cls, policy, device="cuda"):
@@ -144,17 +145,36 @@ class GeneralActor:
             self._ws[n] = [torch.empty(n, w.shape[0], dtype=torch.float32, device=self.device) for w, _ in self.layers]
         return self._ws[n]
 
+    def _packed_weights(self):
+        """Pre-converted bf16 operand images of the layers' weights (msacl_gemm_pack_b), built once: an actor is a snapshot
+        of the policy for one rollout (the sampler rebuilds it when a parameter changes), so every env step streams the same
+        images instead of re-converting the weights in every CTA.  Layers wider than one 256-column tile stay unpacked."""
+        if self._packed is None:
+            from .learner import _desc
+            lib = _lib.load()
+            self._packed = []
+            for w, _ in self.layers:
+                if w.shape[0] > 256:
+                    self._packed.append(None)
+                    continue
+                g = _desc(0, w.shape[1], 1, w, w.shape[1], 1, 128, w.shape[0], w.shape[1], 0, w.shape[0], precision=self.precision)
+                buf = torch.empty(int(lib.msacl_gemm_packed_b_bytes(w.shape[1], self.precision)), dtype=torch.uint8, device=self.device)
+                _lib.check(lib.msacl_gemm_pack_b(C.byref(g), buf.data_ptr(), _lib.current_stream()))
+                self._packed.append(buf)
+        return self._packed
+
     def forward_state(self, state):
         """logits [n, 2*act_dim] for the current observations of an `EnvStateBuffers`."""
         from .learner import _desc
         lib = _lib.load()
         n, spec = state.n, state.spec
         outs = self._workspace(n)
+        packed = self._packed_weights()
         a_ptr, a_rs, a_ks = state.sf.data_ptr() + 4 * spec.obs_off * n, 1, n       # SoA: obs[r][k] = sf[obs_off + k][r]
-        for (w, b), act, y in zip(self.layers, self.activations, outs):
+        for (w, b), act, y, pk in zip(self.layers, self.activations, outs, packed):
             code = self._FUSED_ACT.get(type(act))
             g = _desc(a_ptr, a_rs, a_ks, w, w.shape[1], 1, n, w.shape[0], w.shape[1], y, w.shape[0], bias=b,
-                      act=code or 0, precision=self.precision)
+                      act=code or 0, precision=self.precision, b_packed=pk)
             _lib.check(lib.msacl_gemm_tc(C.byref(g), _lib.current_stream()))
             if code is None:                    # gelu / elu / selu / sigmoid ...: the module itself, on the device
                 with torch.no_grad():
