@@ -78,8 +78,9 @@ __device__ __forceinline__ void wd_wait(void* bar, uint32_t parity, int site, ui
 // icc hit rate 78 %, gcc instruction requests 93 % of peak, 33 % of the env-phase samples `no_instruction`); with the
 // batch wait below the fetches are shared (icc 96 %, gcc 50 %) but the twelve env warps then contend for issue slots and
 // the FP64 pipe (math-pipe throttle 1.8 warps per issue): every arrangement tried -- (NS, TPW) = (3,1) (3,2) (2,2) (2,3)
-// (4,1) -- lands within 5 % of 14 k cycles per tile-step, the SM's instruction throughput for this mix (~7.5 k useful
-// warp-instructions per sub-partition per tile-step at ~0.55 IPC).  Kept as a build option (MSACL_TC_TPW=2); default 1.
+// (4,1) -- lands within 8 % of 14 k cycles per tile-step: the SM's instruction throughput for this mix of dependent
+// FP32 / FP64 / MUFU code at 5-6 resident warps per sub-partition (~0.5 IPC; profiles/r2_rollout_tc_tile_slot_experiments.md).
+// Kept as a build option (MSACL_TC_TPW=2); default 1.
 #ifndef MSACL_TC_TPW
 #define MSACL_TC_TPW(ID) 1
 #endif
