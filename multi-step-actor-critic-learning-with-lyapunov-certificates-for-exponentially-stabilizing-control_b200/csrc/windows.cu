@@ -187,6 +187,99 @@ struct WindowCopier {
   }
 };
 
+#ifndef MSACL_SCATTER_GROUP
+#define MSACL_SCATTER_GROUP 8
+#endif
+// G windows per warp, 32 / G lanes each (window_scatter_kernel; described for G = 4).  The windows a block stores are consecutive in (t, env)
+// order, so the four windows of a warp are -- almost always -- four ADJACENT envs at the same step: for a given row the four
+// 8-lane groups then read one contiguous piece of the transition store (TwoLink: 4 x 16 B = two full sectors) instead of 20
+// lanes touching 20 different lines for a single window; ncu had the one-window-per-warp copy at ~150 LSU wavefronts per
+// 1.1 KB window.  Nothing depends on the adjacency: every group addresses its own window.  Items are walked with additions
+// only (the lane's first item and the (row, offset) increment per 8 items are derived once per call).
+template <int W, int G>
+struct WindowCopier4 {
+  static constexpr int L = 32 / G;      // lanes per window
+  using VecT = typename ObsVec<W>::type;
+  static constexpr int CH = 3;          // items per lane whose loads are issued before the first store
+  const msacl_transitions_t& tr;
+  const msacl_ring_t& ring;
+  int64_t n, row_stride, arow_stride;
+  int j, ns, D, A, vpr, nv, na, r0, q0, dr, dq, ar0, aj0, adr, adj;
+
+  __device__ __forceinline__ WindowCopier4(const msacl_transitions_t& tr_, int64_t n_, const msacl_ring_t& ring_, int lane)
+      : tr(tr_), ring(ring_), n(n_), j(lane & (L - 1)) {
+    ns = ring.n_step; D = ring.obs_dim; A = ring.act_dim;
+    vpr = D / W; nv = ns * vpr; na = ns * A;
+    r0 = j / vpr; q0 = j - r0 * vpr; dr = L / vpr; dq = L - dr * vpr;
+    ar0 = j / A; aj0 = j - ar0 * A; adr = L / A; adj = L - adr * A;
+    row_stride = n * (int64_t)D; arow_stride = n * (int64_t)A;
+  }
+
+  // the 8-lane group of this lane copies the window whose newest transition is `newest` into ring entry `slot` (< 0: none)
+  __device__ __forceinline__ void copy(int64_t newest, int64_t slot) const {
+    if (slot < 0) return;
+    const int64_t first = newest - (int64_t)(ns - 1) * n;
+    const float* so = tr.obs + first * D;
+    const float* so2 = tr.obs2 + first * D;
+    const float* sa = tr.act + first * A;
+    float* dob = ring.obs + slot * ns * D;
+    float* dob2 = ring.obs2 + slot * ns * D;
+    float* da = ring.act + slot * ns * A;
+    {
+      int r = r0, q = q0;
+      for (int v0 = j; v0 < nv; v0 += L * CH) {
+        VecT a[CH], b[CH];
+        int rr = r, qq = q;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          if (v0 + L * c < nv) {
+            const int64_t src = rr * row_stride + qq * W;
+            a[c] = *reinterpret_cast<const VecT*>(so + src);
+            b[c] = *reinterpret_cast<const VecT*>(so2 + src);
+          }
+          rr += dr; qq += dq;
+          if (qq >= vpr) { qq -= vpr; ++rr; }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int v = v0 + L * c;
+          if (v < nv) {
+            *reinterpret_cast<VecT*>(dob + (int64_t)v * W) = a[c];
+            *reinterpret_cast<VecT*>(dob2 + (int64_t)v * W) = b[c];
+          }
+        }
+        r = rr; q = qq;
+      }
+    }
+    {
+      int r = ar0, jj = aj0;
+      for (int e0 = j; e0 < na; e0 += L * CH) {
+        float a[CH];
+        int rr = r, q = jj;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          if (e0 + L * c < na) a[c] = sa[rr * arow_stride + q];
+          rr += adr; q += adj;
+          if (q >= A) { q -= A; ++rr; }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          if (e0 + L * c < na) da[e0 + L * c] = a[c];
+        r = rr; jj = q;
+      }
+    }
+    for (int r = j; r < ns; r += L) {
+      const int64_t src = first + (int64_t)r * n;
+      const float vr = tr.rew[src], vc = tr.cost[src], vl = tr.logp[src];
+      const uint8_t vd = tr.done[src];
+      ring.rew[slot * ns + r] = vr;
+      ring.cost[slot * ns + r] = vc;
+      ring.done[slot * ns + r] = vd ? 1.0f : 0.0f;
+      ring.logp[slot * ns + r] = vl;
+    }
+  }
+};
+
 // W = obs vector width in floats (4 if obs_dim % 4 == 0, 2 if even, else 1)
 template <int W>
 __global__ void __launch_bounds__(WB)
@@ -222,12 +315,21 @@ window_scatter_kernel(msacl_transitions_t tr, int H, int64_t n, int64_t total_fl
   }
   __syncthreads();
   const int num = s_num;
+#ifdef MSACL_SCATTER_ONE_PER_WARP
   WindowCopier<W> cp(tr, n, ring, lane);
   for (int w = warp; w < num; w += WB / 32) {
     const int64_t slot = s_slot[w];
     if (slot < 0) continue;
     cp.copy(s_src[w], slot);
   }
+#else
+  constexpr int G = MSACL_SCATTER_GROUP;                 // windows per warp
+  WindowCopier4<W, G> cp(tr, n, ring, lane);
+  for (int w0 = warp * G; w0 < num; w0 += (WB / 32) * G) {
+    const int w = w0 + lane / (32 / G);
+    cp.copy(w < num ? s_src[w] : 0, w < num ? s_slot[w] : -1);
+  }
+#endif
 }
 
 // ---- index-based window store: a window is the flat position of its newest transition in the
