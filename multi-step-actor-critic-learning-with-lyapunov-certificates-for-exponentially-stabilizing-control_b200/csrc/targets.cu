@@ -267,6 +267,145 @@ lyapunov_risk_striped_kernel(int64_t B, int n, const float* __restrict__ obs, co
   }
 }
 
+// Streaming form of the all-lanes-live kernel for tiles of P > 1 passes (n = 20: P = 5).  The version above keeps every
+// pass's intermediates of a tile in registers until its last pass (128 registers at P = 5: 25 % occupancy, 0.59 of HBM against
+// 0.75 for the single-pass window lengths).  Here a pass is finished as soon as it is computed: the only state carried from
+// pass to pass is the running cumprod, the previous pass's (||o||^2, V) for window heads that lie one pass back, and ONE
+// pending window head per lane -- the head of a window that continues into the next pass waits for that pass's lane-0 suffix
+// sum before its gradient is written.  The loads of pass p + 1 are issued before pass p is computed.
+template <int DT>
+struct LyaRow {
+  float ln, lo, v1, v2, a[DT], c[DT];
+};
+
+template <int DT>
+__device__ __forceinline__ void lya_load(LyaRow<DT>& r, int64_t e, const float* __restrict__ obs, const float* __restrict__ obs2,
+                                         const float* __restrict__ logp_new, const float* __restrict__ logp_old,
+                                         const float* __restrict__ lya_obs, const float* __restrict__ lya_obs2) {
+  r.ln = logp_new[e]; r.lo = logp_old[e]; r.v1 = lya_obs[e]; r.v2 = lya_obs2[e];
+  const float* o = obs + e * DT;
+  const float* q = obs2 + e * DT;
+  if constexpr (DT % 4 == 0) {
+#pragma unroll
+    for (int d = 0; d < DT / 4; ++d) {
+      const float4 x = reinterpret_cast<const float4*>(o)[d], y = reinterpret_cast<const float4*>(q)[d];
+      r.a[4 * d] = x.x; r.a[4 * d + 1] = x.y; r.a[4 * d + 2] = x.z; r.a[4 * d + 3] = x.w;
+      r.c[4 * d] = y.x; r.c[4 * d + 1] = y.y; r.c[4 * d + 2] = y.z; r.c[4 * d + 3] = y.w;
+    }
+  } else if constexpr (DT % 2 == 0) {
+#pragma unroll
+    for (int d = 0; d < DT / 2; ++d) {
+      const float2 x = reinterpret_cast<const float2*>(o)[d], y = reinterpret_cast<const float2*>(q)[d];
+      r.a[2 * d] = x.x; r.a[2 * d + 1] = x.y; r.c[2 * d] = y.x; r.c[2 * d + 1] = y.y;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DT; ++d) { r.a[d] = o[d]; r.c[d] = q[d]; }
+  }
+}
+
+template <int WPB, int P, int DT>
+__global__ void __launch_bounds__(WPB * 32, 3)
+lyapunov_risk_stream_kernel(int64_t B, int n, const float* __restrict__ obs, const float* __restrict__ obs2,
+                            const float* __restrict__ logp_new, const float* __restrict__ logp_old,
+                            const float* __restrict__ lya_obs, const float* __restrict__ lya_obs2,
+                            const float* __restrict__ coef_son, const float* __restrict__ coef_diff,
+                            const float* __restrict__ coef_sl, float alpha1, float alpha2, float diff_scale, float pos_scale,
+                            double* __restrict__ loss_parts, float* __restrict__ g_obs, float* __restrict__ g_obs2,
+                            float* __restrict__ is_clip_out, float* __restrict__ esl_out) {
+  __shared__ float s_part[3][WPB];
+  __shared__ float s_coef[3][32];
+  if (threadIdx.x < 32) {
+    const bool in = (int)threadIdx.x < n;
+    s_coef[0][threadIdx.x] = in ? coef_son[threadIdx.x] : 0.f;
+    s_coef[1][threadIdx.x] = in ? coef_diff[threadIdx.x] : 0.f;
+    s_coef[2][threadIdx.x] = in ? coef_sl[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int T = 32 * P;
+  const int64_t total = B * (int64_t)n;
+  const float inv_bn = pos_scale / (float)((double)B * n);
+  const float w_scale = diff_scale / (float)B;
+  int kk[P];                                     // tile-relative step index of this lane's element in every pass
+#pragma unroll
+  for (int p = 0; p < P; ++p) kk[p] = (32 * p + lane) % n;
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+  const int64_t tiles = (total + T - 1) / T;
+  for (int64_t tile = (int64_t)blockIdx.x * WPB + warp; tile < tiles; tile += (int64_t)gridDim.x * WPB) {
+    const int64_t e0 = tile * T + lane;
+    float carry = 1.f, prev_op = 0.f, prev_v1 = 0.f;
+    float pend_g1 = 0.f, pend_sfx = 0.f;
+    int64_t pend_e = -1;
+    LyaRow<DT> cur, nxt;
+    lya_load<DT>(cur, min(e0, total - 1), obs, obs2, logp_new, logp_old, lya_obs, lya_obs2);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int64_t e = e0 + 32 * p;
+      const bool live = e < total;
+      if (p + 1 < P) lya_load<DT>(nxt, min(e + 32, total - 1), obs, obs2, logp_new, logp_old, lya_obs, lya_obs2);
+      const int k = kk[p];
+      const float son = s_coef[0][k], dif = s_coef[1][k], sl = s_coef[2][k];
+      float op = 0.f, op2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) { op = __fmaf_rn(cur.a[d], cur.a[d], op); op2 = __fmaf_rn(cur.c[d], cur.c[d], op2); }
+      float c = fminf(fmaxf(expf(cur.ln - cur.lo), 0.f), 1.f);     // clamp(ratio, 0, 1) :284-285
+      float v1 = cur.v1, v2 = cur.v2;
+      if (!live) { op = 0.f; op2 = 0.f; v1 = 0.f; v2 = 0.f; c = 1.f; }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {                           // segmented inclusive cumprod (:286)
+        const float y = __shfl_up_sync(0xffffffffu, c, o);
+        if (lane >= o && k >= o) c *= y;
+      }
+      if (k > lane) c *= carry;                                    // the window began in the previous pass
+      carry = __shfl_sync(0xffffffffu, c, 31);
+      const int src = (lane - k) & 31;                             // lane of the window head, in this pass or the previous one
+      float h_op = __shfl_sync(0xffffffffu, op, src), h_v1 = __shfl_sync(0xffffffffu, v1, src);
+      if (p > 0) {
+        const float q_op = __shfl_sync(0xffffffffu, prev_op, src), q_v1 = __shfl_sync(0xffffffffu, prev_v1, src);
+        if (k > lane) { h_op = q_op; h_v1 = q_v1; }
+      }
+      const float lo = alpha1 * op - v1, up = v1 - alpha2 * op;                       // boundedness hinge :291-301
+      const float start_norm = sqrtf(h_op);                                          // ||o_0|| :306-307
+      const float esl = (start_norm * son - sqrtf(op2)) >= 0.f ? 1.f : -1.f;         // :308-312
+      const float inner = esl * (v2 - h_v1 * sl);                                    // :318-323
+      const float term = c * fmaxf(inner, 0.f);
+      const float w = (live && inner > 0.f) ? dif * c * esl * w_scale : 0.f;
+      float sx = w * sl;                                           // suffix sum of w * sl inside the window, within this pass
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float y = __shfl_down_sync(0xffffffffu, sx, o);
+        if (lane + o < 32 && k + o < n) sx += y;
+      }
+      // the pending head of the previous pass takes its window's continuation (this pass's lane-0 suffix)
+      const float next0 = __shfl_sync(0xffffffffu, sx, 0);
+      if (pend_e >= 0) { g_obs[pend_e] = pend_g1 - (pend_sfx + next0); pend_e = -1; }
+      if (live) {
+        p0 += fmaxf(lo, 0.f);
+        p1 += fmaxf(up, 0.f);
+        p2 += dif * term;
+        float g1 = ((lo > 0.f) ? -inv_bn : 0.f) + ((up > 0.f) ? inv_bn : 0.f);
+        const bool cont = k == 0 && p + 1 < P && lane + n > 32;    // a window head whose window continues in the next pass
+        if (cont) { pend_g1 = g1; pend_sfx = sx; pend_e = e; }
+        else { if (k == 0) g1 -= sx + 0.f; g_obs[e] = g1; }
+        g_obs2[e] = w;
+        if (is_clip_out) is_clip_out[e] = c;
+        if (esl_out) esl_out[e] = esl;
+      }
+      prev_op = op; prev_v1 = v1;
+      if (p + 1 < P) cur = nxt;
+    }
+  }
+  p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
+  if (lane == 0) { s_part[0][warp] = p0; s_part[1][warp] = p1; s_part[2][warp] = p2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int w = 0; w < WPB; ++w) s += (double)s_part[threadIdx.x][w];
+    atomicAdd(&loss_parts[threadIdx.x], s);
+  }
+}
+
 // One THREAD per window (a window is only n floats: a warp per window spends an instruction per 80 bytes and is
 // issue-bound at a fifth of the HBM peak).  A warp covers 32 consecutive windows = 32*n contiguous floats; each lane
 // reads its own n floats as float4 vectors when n % 4 == 0 (every sector fetched is fully used by the warp).  The
@@ -530,13 +669,18 @@ extern "C" int msacl_lyapunov_risk(int64_t B, int32_t n, int32_t D, const float*
     const int64_t tiles = (B * (int64_t)n + 32 * P - 1) / (32 * P);
 #define MSACL_LYA_STRIPED(P_, DT)                                                                                            \
     if (P == P_ && D == DT) {                                                                                                \
-      lyapunov_risk_striped_kernel<WPB, P_, DT><<<grid_for(tiles, WPB), WPB * 32, 0, s>>>(                                    \
-          B, n, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale,   \
-          pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);                                                  \
+      if constexpr (P_ > 1)        /* multi-pass tiles: the streaming kernel (n = 20: 0.62 of HBM against 0.51) */             \
+        lyapunov_risk_stream_kernel<WPB, P_, DT><<<grid_for(tiles, WPB), WPB * 32, 0, s>>>(                                   \
+            B, n, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale, \
+            pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);                                                \
+      else                                                                                                                    \
+        lyapunov_risk_striped_kernel<WPB, P_, DT><<<grid_for(tiles, WPB), WPB * 32, 0, s>>>(                                  \
+            B, n, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale, \
+            pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);                                                \
       return check_launch("lyapunov_risk");                                                                                   \
     }
 #define MSACL_LYA_STRIPED_D(P_) MSACL_LYA_STRIPED(P_, 2) MSACL_LYA_STRIPED(P_, 4) MSACL_LYA_STRIPED(P_, 6) MSACL_LYA_STRIPED(P_, 7) MSACL_LYA_STRIPED(P_, 12)
-    if (n > 1 && !getenv("MSACL_LYA_WARP_PER_WINDOW")) { MSACL_LYA_STRIPED_D(1) MSACL_LYA_STRIPED_D(3) MSACL_LYA_STRIPED_D(5) }
+    if (n > 1) { MSACL_LYA_STRIPED_D(1) MSACL_LYA_STRIPED_D(3) MSACL_LYA_STRIPED_D(5) }
 #undef MSACL_LYA_STRIPED_D
 #undef MSACL_LYA_STRIPED
   }
