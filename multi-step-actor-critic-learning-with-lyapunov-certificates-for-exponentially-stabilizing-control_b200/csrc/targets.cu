@@ -673,7 +673,7 @@ extern "C" int msacl_lyapunov_risk(int64_t B, int32_t n, int32_t D, const float*
         lyapunov_risk_stream_kernel<WPB, P_, DT><<<grid_for(tiles, WPB), WPB * 32, 0, s>>>(                                   \
             B, n, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale, \
             pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);                                                \
-      else                                                                                                                    \
+      else     /* single-pass tiles (n = 32, 16, 8 ...): 0.86 of HBM as they are; the streaming kernel with 4-pass tiles measured 0.77 */ \
         lyapunov_risk_striped_kernel<WPB, P_, DT><<<grid_for(tiles, WPB), WPB * 32, 0, s>>>(                                  \
             B, n, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale, \
             pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);                                                \
