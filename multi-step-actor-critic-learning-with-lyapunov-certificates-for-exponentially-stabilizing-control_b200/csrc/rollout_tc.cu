@@ -23,6 +23,8 @@
 //   TMA warp          pre-split W2 k-step images (16 KB) global/L2 -> shared ring (cp.async.bulk).
 // All hand-offs are mbarriers (per-stage full/free for A and B, per-buffer full/free for H2, H1 full/free, X full,
 // logits); tcgen05.commit signals the ones the tensor pipe produces.
+#include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -84,6 +86,14 @@ __device__ __forceinline__ void wd_wait(void* bar, uint32_t parity, int site, ui
 #ifndef MSACL_TC_TPW
 #define MSACL_TC_TPW(ID) 1
 #endif
+// Warps of a DEDICATED epilogue-1 group (E1).  0: the 8 epilogue warps run both epilogues of every tile-step one after the
+// other (epilogue 1 of t+1, then epilogue 2 of t).  8 / 4: epilogue 1 gets its own 8 warps (column halves, as before) / 4 warps
+// (whole rows), and the 8 warps behind them run epilogue 2 only -- the two epilogues of different tile-steps then overlap
+// instead of queueing in the same warps (role timers: the shared warps are busy 3.9 k + 6.4 k of the 14.4 k cycles per
+// tile-step and every hand-off in the MMA -> epilogue 1 -> MMA -> epilogue 2 chain waits for them).
+#ifndef MSACL_TC_E1
+#define MSACL_TC_E1(ID) 0
+#endif
 constexpr int TCM = 128;            // envs per tile
 constexpr int TC_HID = 256;
 constexpr int KC2 = 32;             // K per A stage
@@ -100,7 +110,9 @@ constexpr int W1_HALF = TC_HID * 16 * 2;    // 8 KB
 // {MMA, TMA, 2 idle warps}.  Registers are rebalanced with setmaxnreg (65536 per SM in total).  Per warp:
 // launch regs * warps >= sum of the budgets below, or setmaxnreg.inc never returns; and all four warps of a
 // warpgroup must execute the same setmaxnreg (the {MMA, TMA, idle, idle} group shares MISC_REGS).
-template <int NS> struct TcCfg;
+template <int NS, int E1 = 0> struct TcCfg;
+template <> struct TcCfg<3, 8> { static constexpr int THREADS = 1024, ENV_REGS = 80, EPI_REGS = 56, MISC_REGS = 32, NB = 3; };  // launch 64*32 = 2048 >= 12*80 + 16*56 + 4*32
+template <> struct TcCfg<3, 4> { static constexpr int THREADS = 896, ENV_REGS = 96, EPI_REGS = 56, MISC_REGS = 32, NB = 3; };   // launch 72*28 = 2016 >= 12*96 + 12*56 + 4*32
 template <> struct TcCfg<2> { static constexpr int THREADS = 640, ENV_REGS = 152, EPI_REGS = 64, MISC_REGS = 40, NB = 3; };   // launch 96*20 = 1920 >= 8*152 + 8*64 + 4*40
 template <> struct TcCfg<3> { static constexpr int THREADS = 768, ENV_REGS = 112, EPI_REGS = 56, MISC_REGS = 32, NB = 3; };   // launch 80*24 = 1920 = 12*112 + 8*56 + 4*32
 template <> struct TcCfg<4> { static constexpr int THREADS = 896, ENV_REGS = 88, EPI_REGS = 56, MISC_REGS = 40, NB = 2; };    // launch 72*28 = 2016 = 16*88 + 8*56 + 4*40; the 4th slot's 8 KB come out of the W2 ring
@@ -207,15 +219,16 @@ __global__ void tc_pack_actor_kernel(msacl_actor_t actor, int D, unsigned char* 
   }
 }
 
-template <int ID, int NS, int TPW>
-__global__ void __launch_bounds__(TcCfg<NS>::THREADS, 1)
+template <int ID, int NS, int TPW, int E1>
+__global__ void __launch_bounds__(TcCfg<NS, E1>::THREADS, 1)
 rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char* __restrict__ w1p_g,
                   const unsigned char* __restrict__ w2p_g, float* __restrict__ scratch, int K, uint32_t step_base, int n_step,
                   float reward_scale, float cost_scale, const float* __restrict__ eps, int deterministic, msacl_transitions_t out,
                   double* stats) {
   using E = Env<ID>;
   using S = TcSmem<ID, NS>;
-  using CFG = TcCfg<NS>;
+  using CFG = TcCfg<NS, E1>;
+  static_assert(E1 == 0 || ((E1 == 4 || E1 == 8) && TPW == 1), "dedicated epilogue-1 group: 4 or 8 warps, one tile per env warpgroup");
   constexpr int D = E::D, A = E::A, A2 = 2 * A;
   constexpr int NT = NS * TPW;                 // tiles in flight per CTA ("group"); tile slot s belongs to warpgroup s % NS
   constexpr bool PARK = TPW > 1;
@@ -223,7 +236,8 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   static_assert(NT <= SCR_TILES && A2 <= 8, "scratch layout");
   constexpr int TC_THREADS = CFG::THREADS, NB = S::NB, XH = S::XH, W1H = S::W1H, W3S = tc_w3_stride<ID>();
   constexpr bool X2 = S::X2;
-  constexpr int W_EPI1 = 4 * NS, W_MMA = 4 * NS + 8, W_TMA = 4 * NS + 9;
+  constexpr int W_EPI1 = 4 * NS, W_EPI2 = W_EPI1 + E1, W_MMA = W_EPI2 + 8, W_TMA = W_MMA + 1;
+  constexpr int NC1 = E1 == 4 ? NCH : NCH / 2;      // A stages a warp of epilogue 1 fills per tile-step
   static_assert(D < 16, "layer-1 K block holds obs + bias column");
   static_assert(A2 * TCM * 4 <= XH && ((A2 + 1) / 2) * 2 * TCM * 4 <= XH, "logits and partial sums alias the two halves of the X-operand region (TPW == 1)");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -249,7 +263,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
     for (int s = 0; s < NS; ++s) { tc::mbar_init(&b.xfull[s], TCM); tc::mbar_init(&b.xfree[s], 1); }
     for (int s = 0; s < NT; ++s) tc::mbar_init(&b.logits[s], PARK ? 2 * TCM : TCM);   // PARK: both column halves deliver
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&b.h1full[i], 1); tc::mbar_init(&b.h1free[i], 2 * TCM);     // drained by all 8 epilogue warps
+      tc::mbar_init(&b.h1full[i], 1); tc::mbar_init(&b.h1free[i], E1 == 4 ? TCM : 2 * TCM);     // drained by all warps of epilogue 1
       tc::mbar_init(&b.h2full[i], 1); tc::mbar_init(&b.h2free[i], 2 * TCM);
     }
     for (int i = 0; i < NCH; ++i) { tc::mbar_init(&b.afull[i], TCM); tc::mbar_init(&b.afree[i], 1); }
@@ -264,8 +278,29 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   const uint32_t tmem = sm.bars.tmem_slot;     // buffer b of tile-step t (b = t & 1) = columns [256 b, 256 b + 256)
 
   const int64_t num_tiles = (st.n + TCM - 1) / TCM;
-  const int64_t num_pairs = (num_tiles + NT - 1) / NT;      // "pair" = group of NT tiles in flight
-  auto tiles_in_pair = [&](int64_t pair) { return (int)((num_tiles - NT * pair) < NT ? (num_tiles - NT * pair) : NT); };
+  // Groups ("pairs") of up to NT tiles in flight.  A CTA walks the group ids cta, cta + G, cta + 2 G, ... (G = gridDim.x).
+  // TPW == 1: the tiles are dealt to the CTAs in contiguous BALANCED shares -- CTA b owns T / G (+ 1) tiles and walks them in
+  // ceil(share / NT) rounds of share / rounds (+ 1) tiles, the larger rounds first (so a warpgroup that has no tile in a round
+  // has none in the later ones, and every earlier round of an active warpgroup was a full K steps: x_index below).  Cutting the
+  // tile list into fixed groups of NT instead leaves most SMs idle for half the launch when the tile count is a small
+  // multiple of the SM count: 65 536 envs = 512 tiles = 171 groups of 3 on 148 SMs are TWO rounds of 3 tiles for 23 CTAs and one
+  // for the rest; balanced, 68 CTAs run two rounds of 2 tiles and 80 one round of 3.  Results do not depend on the mapping
+  // (the RNG streams are keyed by the global env id).  TPW > 1 keeps fixed groups of NT tiles.
+  const int64_t G = gridDim.x, cta = blockIdx.x;
+  const int share = PARK ? 0 : (int)(num_tiles / G + (cta < num_tiles % G ? 1 : 0));
+  const int64_t share0 = PARK ? 0 : cta * (num_tiles / G) + (cta < num_tiles % G ? cta : num_tiles % G);
+  const int rounds = (share + NT - 1) / NT;
+  const int per = rounds ? share / rounds : 0, ex = rounds ? share % rounds : 0;
+  const int64_t num_pairs = PARK ? (num_tiles + NT - 1) / NT : cta + (int64_t)rounds * G;      // bound of `for (pair = cta; pair < num_pairs; pair += G)`
+  auto tiles_in_pair = [&](int64_t pair) -> int {
+    if (PARK) return (int)((num_tiles - NT * pair) < NT ? (num_tiles - NT * pair) : NT);
+    return per + ((int)(pair - cta) / (int)G < ex ? 1 : 0);      // (32-bit division: round index = tiles / G at most)
+  };
+  auto first_tile = [&](int64_t pair) -> int64_t {
+    if (PARK) return NT * pair;
+    const int j = (int)(pair - cta) / (int)G;
+    return share0 + (int64_t)j * per + (j < ex ? j : ex);
+  };
   // X operands are written per warpgroup: group pi (all but the last are full), step k, tile slot s -> running index
   auto tiles_of_wg = [&](int w, int nt) { return nt > w ? (nt - w - 1) / NS + 1 : 0; };
   auto x_index = [&](uint32_t pi, int k, int s, int nt) { return pi * (uint32_t)(TPW * K) + (uint32_t)(k * tiles_of_wg(s % NS, nt) + s / NS); };
@@ -301,11 +336,12 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
     for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
       const int nt = tiles_in_pair(pair);
       if (w >= nt) break;
+      const int64_t tile0 = first_tile(pair);
       EnvRegs<ID> e;
       // first observations of this group's tiles
 #pragma unroll 1
       for (int s = w; s < nt; s += NS) {
-        const int64_t gi = (NT * pair + s) * TCM + r;
+        const int64_t gi = (tile0 + s) * TCM + r;
         const bool owner = gi < st.n;
         if (owner) e.load(st, gi);
         write_xop(e.obs(), owner);
@@ -313,7 +349,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       for (int k = 0; k < K; ++k) {
 #pragma unroll 1
         for (int s = w; s < nt; s += NS) {
-        const int64_t gi = (NT * pair + s) * TCM + r;
+        const int64_t gi = (tile0 + s) * TCM + r;
         const bool owner = gi < st.n;
         if (PARK && owner) e.load(st, gi);     // issued in front of the logits wait: the L2 round trip hides behind it
         // the action noise of this step does not depend on the logits: draw it while the tile's MLP is still running
@@ -440,7 +476,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         ++lcount;
       }
       if constexpr (!PARK) {
-        const int64_t gi = (NT * pair + w) * TCM + r;
+        const int64_t gi = (tile0 + w) * TCM + r;
         if (gi < st.n) e.store(st, gi);
       }
     }
@@ -464,10 +500,13 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
     // epilogue 2 of t (while layer 2 of t+1 runs).  With a single slot the X operand of t+1 needs the logits of t, so
     // the order is swapped.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CFG::EPI_REGS));
-    const int q = warp & 3, h = (warp - W_EPI1) >> 2;
+    // E1 > 0: warps [W_EPI1, W_EPI2) run epilogue 1 only, [W_EPI2, W_MMA) epilogue 2 only
+    const bool first_group = E1 == 0 || warp < W_EPI2;
+    const int q = warp & 3;
+    const int h = first_group ? (E1 == 4 ? 0 : (warp - W_EPI1) >> 2) : (warp - W_EPI2) >> 2;      // column half
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const bool timer = (warp == W_EPI1 && lane == 0);
+    const bool timer = lane == 0 && (warp == W_EPI1 || (E1 > 0 && warp == W_EPI2));
     auto epi1 = [&](uint32_t t1) {
       const uint32_t buf = t1 & 1u, tmem_b = tmem + buf * 256u;
       TC_T0(t_a);
@@ -476,7 +515,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       if (timer) TC_ACC(8, t_a);                      // epi1: wait for H1
       TC_T0(t_b);
 #pragma unroll 1
-      for (int cc = 0; cc < NCH / 2; ++cc) {
+      for (int cc = 0; cc < NC1; ++cc) {
         const int c = h * (NCH / 2) + cc;
         TC_T0(t_c);
         if (t1 > 0) TC_WAIT(&sm.bars.afree[c], (t1 - 1) & 1, 3, t1);   // layer 2 of the previous tile-step is done with stage c
@@ -484,7 +523,7 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
         uint32_t v[32];
         tc::tmem_ld32(tmem_b + lane_addr + (uint32_t)(c * 32), v);
         tc::tmem_ld_wait();
-        if (cc == NCH / 2 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h1free[buf]); }   // layer 2 may overwrite the buffer
+        if (cc == NC1 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&sm.bars.h1free[buf]); }   // layer 2 may overwrite the buffer
         unsigned char* base = sm.astage[c] + r * 16;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
@@ -582,6 +621,17 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
       if (timer) TC_ACC(12, t_b);                     // epi2: compute
     };
     uint32_t ts = 0;
+    if constexpr (E1 > 0) {
+      // two independent groups: each walks the tile-steps in order; the hand-offs with the MMA thread are the only coupling
+      for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        const int nt = tiles_in_pair(pair);
+        for (int k = 0; k < K; ++k)
+          for (int s = 0; s < nt; ++s, ++ts) {
+            if (first_group) epi1(ts);
+            else epi2(ts, s);
+          }
+      }
+    } else
     for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
       const int nt = tiles_in_pair(pair);
       for (int k = 0; k < K; ++k)
@@ -762,19 +812,26 @@ extern "C" int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_a
     }
     constexpr int NS = MSACL_TC_NS(ID);      // env warpgroups
     constexpr int TPW = MSACL_TC_TPW(ID);    // tiles per warpgroup: NS * TPW tiles in flight per CTA
+    constexpr int E1_DEFAULT = MSACL_TC_E1(ID);      // warps of a dedicated epilogue-1 group (0: shared epilogue warps; needs NS == 3)
     static_assert(sizeof(TcSmem<ID, NS>) + 128 <= 232448, "shared-memory layout exceeds the 227 KB per-CTA limit");
-    const int64_t groups = (tiles + NS * TPW - 1) / (NS * TPW);
+    const int64_t groups = TPW == 1 ? tiles : (tiles + NS * TPW - 1) / (NS * TPW);      // TPW == 1: balanced shares, every CTA owns >= 1 tile
     const int64_t cap = g_tc_max_ctas > 0 ? g_tc_max_ctas : kNumSMs;
     const unsigned grid = (unsigned)(groups < cap ? groups : cap);
     const size_t smem = sizeof(TcSmem<ID, NS>) + 128;
-    auto kern = rollout_tc_kernel<ID, NS, TPW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("rollout_fused_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
     // the scratch area behind the W2 images is written by the kernel (the ABI hands the buffer over as const because the
     // images are; one launch at a time may use a given buffer)
     float* scratch = reinterpret_cast<float*>(const_cast<unsigned char*>((const unsigned char*)w2p) + W2P_BYTES);
-    kern<<<grid, TcCfg<NS>::THREADS, smem, (cudaStream_t)stream>>>(*st, *actor, (const unsigned char*)w1p, (const unsigned char*)w2p, scratch, K,
-                                                                  step_base, n_step, reward_scale, cost_scale, eps, deterministic, *out, stats);
+    auto launch = [&](auto e1_tag) -> int {
+      constexpr int E1 = decltype(e1_tag)::value;
+      auto kern = rollout_tc_kernel<ID, NS, TPW, E1>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("rollout_fused_tc: smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return MSACL_ERR_CUDA; }
+      kern<<<grid, TcCfg<NS, E1>::THREADS, smem, (cudaStream_t)stream>>>(*st, *actor, (const unsigned char*)w1p, (const unsigned char*)w2p, scratch, K,
+                                                                         step_base, n_step, reward_scale, cost_scale, eps, deterministic, *out, stats);
+      return MSACL_OK;
+    };
+    const int rc = launch(std::integral_constant<int, E1_DEFAULT>{});
+    if (rc != MSACL_OK) return rc;
   });
   return check_launch("rollout_fused_tc");
 }

@@ -69,9 +69,12 @@ def test_tc_rollout_matches_ffma_rollout_one_step(name):
     assert int(a.state.episode.sum().item()) > 0
 
 
-@pytest.mark.parametrize("name,n", [("Pendulum", 70000), ("QuadTracking", 40001)])
+# 70000 / 40001: shares of 3-4 / 2-3 tiles per CTA; 148 * 128 * 7 + 700: shares of 7 and 8 tiles = rounds of 3, 2, 2 / 3, 3, 2 tiles;
+# 1000: eight CTAs with one tile each; 65536: BASELINE config 2 (68 CTAs with two rounds of 2 tiles, 80 with one round of 3)
+@pytest.mark.parametrize("name,n", [("Pendulum", 70000), ("QuadTracking", 40001), ("TwoLink", 148 * 128 * 7 + 700), ("DuctedFan", 1000),
+                                    ("Pendulum", 65536)])
 def test_tc_rollout_multi_step_large(name, n):
-    """K=6 steps in one launch on a grid that wraps over tile pairs (persistent loop, tails)."""
+    """K=6 steps in one launch on a grid whose CTAs walk several rounds of tiles (persistent loop, balanced shares, tails)."""
     K = 6
     spec = oenv.SPECS[name]
     a, b, aw, _ = _pair(name, n, K)
