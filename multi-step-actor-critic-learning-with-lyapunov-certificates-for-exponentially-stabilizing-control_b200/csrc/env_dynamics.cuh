@@ -202,11 +202,21 @@ template <> struct Env<kTwoLink> {
       const double b1 = ((double)a[0] - Cq1) - (double)G1;
       const double b2 = ((double)a[1] - Cq2) - (double)G2;
       const double m11 = (double)M11, m12 = (double)M12;
+#ifdef MSACL_TWOLINK_LU
       const double l21 = m12 / m11;
       const double u22 = M22 - l21 * m12;
       const double y2 = b2 - l21 * b1;
       const double x2 = y2 / u22;
       const double x1 = (b1 - m12 * x2) / m11;
+#else
+      // The LU solve above written out: x2 = (m11 b2 - m12 b1) / det, x1 = (M22 b1 - m12 b2) / det with det = m11 M22 - m12^2
+      // (>= 0.19 for every theta2; condition number < 50), ONE float64 division per sub-step instead of three.  The
+      // result differs from LAPACK's by a few float64 ulps (as the LU form did: dgesv scales by the reciprocal pivot), far
+      // below the float32 state it is rounded to; the golden-step tolerance (4e-6) is unchanged.
+      const double rdet = 1.0 / (m11 * M22 - m12 * m12);
+      const double x2 = (m11 * b2 - m12 * b1) * rdet;
+      const double x1 = (M22 * b1 - m12 * b2) * rdet;
+#endif
       o[0] = (float)((double)th1 + q1 * kDtD);
       o[1] = (float)((double)th2 + q2 * kDtD);
       o[2] = (float)((double)d1 + x1 * kDtD);
