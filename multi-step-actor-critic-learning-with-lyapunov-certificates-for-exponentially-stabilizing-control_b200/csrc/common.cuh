@@ -4,6 +4,8 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 #include "../../include/msacl_b200.h"
 #include "env_dynamics.cuh"
@@ -14,6 +16,30 @@ constexpr int kNumSMs = 148;  // B200
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+
+// Grid of a grid-stride ("persistent") kernel: whole waves of RESIDENT blocks.  A fixed cap of 8 blocks per SM is 1.6 waves for
+// a kernel that fits 5 blocks per SM (48 registers x 256 threads) -- the last wave runs at 60 % occupancy; measured on
+// lyapunov_risk: 0.77 -> 0.80 of HBM from the grid alone.  `waves` resident sets are launched (2: blocks that fall behind
+// are balanced by the second set).  The occupancy query is a host-side table lookup (no stream operation: legal during
+// graph capture) and is cached per kernel.
+inline int cached_occupancy(const void* kern, int block_threads) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;      // per translation unit; a kernel is always launched with one block size
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(kern);
+  if (it != cache.end()) return it->second;
+  int o = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, block_threads, 0) != cudaSuccess || o < 1) { o = 4; (void)cudaGetLastError(); }
+  cache.emplace(kern, o);
+  return o;
+}
+
+template <typename Kernel>
+inline unsigned resident_grid(Kernel kern, int block_threads, int64_t work_items, int per_block, int waves = 2) {
+  const int64_t want = (work_items + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)kNumSMs * cached_occupancy(reinterpret_cast<const void*>(kern), block_threads) * waves;
+  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
 
 #define MSACL_DISPATCH_ENV(env_id, ...)                                        \
   switch (env_id) {                                                            \

@@ -671,12 +671,14 @@ extern "C" int msacl_lyapunov_risk(int64_t B, int32_t n, int32_t D, const float*
     if (P == P_ && D == DT) {                                                                                                \
       if constexpr (P_ > 1) {      /* multi-pass tiles: the streaming kernel (n = 20: 0.62 of HBM against 0.51) */             \
         /* 64 registers (4 blocks per SM) for the narrow observations: n = 20, obs_dim 4 0.77 -> 0.86 of HBM */               \
-        lyapunov_risk_stream_kernel<WPB, P_, DT, (DT <= 4 ? 4 : 3)><<<grid_for(tiles, WPB), WPB * 32, 0, s>>>(                \
+        lyapunov_risk_stream_kernel<WPB, P_, DT, (DT <= 4 ? 4 : 3)><<<resident_grid(lyapunov_risk_stream_kernel<WPB, P_, DT, (DT <= 4 ? 4 : 3)>, WPB * 32, tiles, WPB), WPB * 32, 0, s>>>( \
+                \
             B, n, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale, \
             pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);                                                \
       }                                                                                                                       \
       else     /* single-pass tiles (n = 32, 16, 8 ...): 0.86 of HBM as they are; the streaming kernel with 4-pass tiles measured 0.77 */ \
-        lyapunov_risk_striped_kernel<WPB, P_, DT><<<grid_for(tiles, WPB), WPB * 32, 0, s>>>(                                  \
+        lyapunov_risk_striped_kernel<WPB, P_, DT><<<resident_grid(lyapunov_risk_striped_kernel<WPB, P_, DT>, WPB * 32, tiles, WPB), WPB * 32, 0, s>>>( \
+                                  \
             B, n, obs, obs2, logp_new, logp_old, lya_obs, lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, diff_scale, \
             pos_scale, loss_parts, grad_lya_obs, grad_lya_obs2, is_clip, esl);                                                \
       return check_launch("lyapunov_risk");                                                                                   \
@@ -687,7 +689,7 @@ extern "C" int msacl_lyapunov_risk(int64_t B, int32_t n, int32_t D, const float*
 #undef MSACL_LYA_STRIPED
   }
 #define MSACL_LYA_LAUNCH(DT)                                                                                              \
-  lyapunov_risk_kernel<WPB, DT><<<grid_for(B, WPB), WPB * 32, 0, s>>>(B, n, D, obs, obs2, logp_new, logp_old, lya_obs,    \
+  lyapunov_risk_kernel<WPB, DT><<<resident_grid(lyapunov_risk_kernel<WPB, DT>, WPB * 32, B, WPB), WPB * 32, 0, s>>>(B, n, D, obs, obs2, logp_new, logp_old, lya_obs,    \
                                                                       lya_obs2, coef_son, coef_diff, coef_sl, alpha1, alpha2, \
                                                                       diff_scale, pos_scale, loss_parts, grad_lya_obs,       \
                                                                       grad_lya_obs2, is_clip, esl)
@@ -713,7 +715,8 @@ extern "C" int msacl_stability_advantage(int64_t B, int32_t n, const float* lya_
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(moments, 0, 2 * sizeof(double), s);
   constexpr int TPB = 128;
-  stability_adv_kernel<TPB><<<grid_for(B, TPB), TPB, 0, s>>>(B, n, lya_obs0, lya_obs2, coef_diff, coef_sl, adv_raw, moments);
+  stability_adv_kernel<TPB><<<grid_for(B, TPB), TPB, 0, s>>>(       /* (whole resident waves measured slower here: 24.9 vs 22.2 us) */
+      B, n, lya_obs0, lya_obs2, coef_diff, coef_sl, adv_raw, moments);
   return check_launch("stability_advantage");
 }
 

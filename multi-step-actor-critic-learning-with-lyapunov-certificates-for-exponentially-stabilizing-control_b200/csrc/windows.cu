@@ -654,20 +654,18 @@ extern "C" int msacl_ring_gather(const msacl_ring_t* ring, const int64_t* idx, i
   if (int rc = validate_ring(batch)) return rc;
   if (!idx || B <= 0) { set_error("ring_gather: bad argument"); return MSACL_ERR_BAD_ARG; }
   const int wpb = 8;
-  const int64_t want = (B + wpb - 1) / wpb, cap = (int64_t)kNumSMs * 8;
-  const unsigned grid = (unsigned)(want < cap ? want : cap);
   const int ns = ring->n_step;
   const int total = ns * (2 * ring->obs_dim + ring->act_dim + 4) / 4;      // float4 vectors per window
   const int nv = ((ns & 3) == 0 && total <= 32 * GATHER_MAX_VEC) ? (total + 31) / 32 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   switch (nv) {
-    case 1: ring_gather_kernel<1><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
-    case 2: ring_gather_kernel<2><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
-    case 3: ring_gather_kernel<3><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
-    case 4: ring_gather_kernel<4><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
-    case 5: ring_gather_kernel<5><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
-    case 6: ring_gather_kernel<6><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
-    default: ring_gather_kernel<0><<<grid, wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 1: ring_gather_kernel<1><<<resident_grid(ring_gather_kernel<1>, wpb * 32, B, wpb), wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 2: ring_gather_kernel<2><<<resident_grid(ring_gather_kernel<2>, wpb * 32, B, wpb), wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 3: ring_gather_kernel<3><<<resident_grid(ring_gather_kernel<3>, wpb * 32, B, wpb), wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 4: ring_gather_kernel<4><<<resident_grid(ring_gather_kernel<4>, wpb * 32, B, wpb), wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 5: ring_gather_kernel<5><<<resident_grid(ring_gather_kernel<5>, wpb * 32, B, wpb), wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    case 6: ring_gather_kernel<6><<<resident_grid(ring_gather_kernel<6>, wpb * 32, B, wpb), wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
+    default: ring_gather_kernel<0><<<resident_grid(ring_gather_kernel<0>, wpb * 32, B, wpb), wpb * 32, 0, st>>>(*ring, idx, B, *batch); break;
   }
   return check_launch("ring_gather");
 }
