@@ -148,6 +148,12 @@ int msacl_tc_pack_bytes(int64_t* w1p_bytes, int64_t* w2p_bytes);
  * sub-batches on a side stream, whose CTAs would otherwise displace rollout CTAs and stretch the launch by the collective's
  * cross-rank wait.  Host call, takes effect at the next launch. */
 int msacl_rollout_tc_set_max_ctas(int32_t max_ctas);
+
+/* How msacl_rollout_fused_tc deals its 128-env tiles to the persistent CTAs (host-side arithmetic, no launch; for tests and
+ * capacity planning): CTA `cta` of `grid` owns out[1] contiguous tiles starting at tile out[0] and walks them in out[2] rounds
+ * of out[3] tiles (+ 1 in the first out[4] rounds), at most 3 tiles (one per env warpgroup) per round.  out = int64[5].
+ * Replaces nothing in the reference (its sampler loops over the envs one by one, RL/trainer/sampler/base.py:141-220). */
+int msacl_tc_tile_share(int64_t n_envs, int32_t grid, int32_t cta, int64_t* out);
 int msacl_tc_pack_actor(const msacl_actor_t* actor, int32_t obs_dim, void* w1p, void* w2p, void* stream);
 int msacl_rollout_fused_tc(const msacl_env_state_t* st, const msacl_actor_t* actor, const void* w1p, const void* w2p,
                            int32_t K, uint32_t step_base, int32_t n_step, float reward_scale, float cost_scale,

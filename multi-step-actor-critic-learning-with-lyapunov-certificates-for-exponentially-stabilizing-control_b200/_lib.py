@@ -65,6 +65,7 @@ SIGNATURES = {
                                       C.c_float, C.c_float, vp, C.c_int32, C.POINTER(Transitions), vp, vp]),
     "msacl_tc_pack_bytes": (C.c_int, [c_i64p, c_i64p]),
     "msacl_rollout_tc_set_max_ctas": (C.c_int, [C.c_int32]),
+    "msacl_tc_tile_share": (C.c_int, [i64, C.c_int32, C.c_int32, vp]),
     "msacl_tc_pack_actor": (C.c_int, [C.POINTER(Actor), C.c_int32, vp, vp, vp]),
     "msacl_rollout_fused_tc": (C.c_int, [C.POINTER(EnvState), C.POINTER(Actor), vp, vp, C.c_int32, C.c_uint32, C.c_int32,
                                          C.c_float, C.c_float, vp, C.c_int32, C.POINTER(Transitions), vp, vp]),

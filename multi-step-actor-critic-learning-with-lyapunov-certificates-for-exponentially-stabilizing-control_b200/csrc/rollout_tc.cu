@@ -135,6 +135,23 @@ struct TcBars {
   uint32_t tmem_slot;
 };
 
+// The share of the tile list one CTA walks (TPW == 1; see the comment in the kernel): `share` contiguous tiles from `first`, in
+// `rounds` rounds of per (+ 1 for the first `ex`) tiles.  Host + device: msacl_tc_tile_share() exposes the same arithmetic to the
+// CPU tests (every tile exactly once, round sizes <= NS and non-increasing).
+struct TcShare {
+  int64_t first;
+  int share, rounds, per, ex;
+  __host__ __device__ TcShare(int64_t num_tiles, int64_t G, int64_t cta, int nt_max) {
+    share = (int)(num_tiles / G + (cta < num_tiles % G ? 1 : 0));
+    first = cta * (num_tiles / G) + (cta < num_tiles % G ? cta : num_tiles % G);
+    rounds = (share + nt_max - 1) / nt_max;
+    per = rounds ? share / rounds : 0;
+    ex = rounds ? share % rounds : 0;
+  }
+  __host__ __device__ int tiles_in_round(int j) const { return per + (j < ex ? 1 : 0); }
+  __host__ __device__ int64_t first_tile_of_round(int j) const { return first + (int64_t)j * per + (j < ex ? j : ex); }
+};
+
 // Layer-1 K block: obs (D) + bias column need 16 K columns only for the quadrotor (D + 1 = 13).  For the box envs
 // (D + 1 <= 8) the second 8-column K block of both layer-1 operands is all zero, so it is not stored per slot: the
 // operand descriptors' K-block stride (LBO) points at one shared zero block instead.  That and the narrower W3 (2A <= 4)
@@ -287,19 +304,15 @@ rollout_tc_kernel(msacl_env_state_t st, msacl_actor_t actor, const unsigned char
   // for the rest; balanced, 68 CTAs run two rounds of 2 tiles and 80 one round of 3.  Results do not depend on the mapping
   // (the RNG streams are keyed by the global env id).  TPW > 1 keeps fixed groups of NT tiles.
   const int64_t G = gridDim.x, cta = blockIdx.x;
-  const int share = PARK ? 0 : (int)(num_tiles / G + (cta < num_tiles % G ? 1 : 0));
-  const int64_t share0 = PARK ? 0 : cta * (num_tiles / G) + (cta < num_tiles % G ? cta : num_tiles % G);
-  const int rounds = (share + NT - 1) / NT;
-  const int per = rounds ? share / rounds : 0, ex = rounds ? share % rounds : 0;
-  const int64_t num_pairs = PARK ? (num_tiles + NT - 1) / NT : cta + (int64_t)rounds * G;      // bound of `for (pair = cta; pair < num_pairs; pair += G)`
+  const TcShare sh(num_tiles, G, cta, NT);
+  const int64_t num_pairs = PARK ? (num_tiles + NT - 1) / NT : cta + (int64_t)sh.rounds * G;      // bound of `for (pair = cta; pair < num_pairs; pair += G)`
   auto tiles_in_pair = [&](int64_t pair) -> int {
     if (PARK) return (int)((num_tiles - NT * pair) < NT ? (num_tiles - NT * pair) : NT);
-    return per + ((int)(pair - cta) / (int)G < ex ? 1 : 0);      // (32-bit division: round index = tiles / G at most)
+    return sh.tiles_in_round((int)(pair - cta) / (int)G);      // (32-bit division: round index = tiles / G at most)
   };
   auto first_tile = [&](int64_t pair) -> int64_t {
     if (PARK) return NT * pair;
-    const int j = (int)(pair - cta) / (int)G;
-    return share0 + (int64_t)j * per + (j < ex ? j : ex);
+    return sh.first_tile_of_round((int)(pair - cta) / (int)G);
   };
   // X operands are written per warpgroup: group pi (all but the last are full), step k, tile slot s -> running index
   auto tiles_of_wg = [&](int w, int nt) { return nt > w ? (nt - w - 1) / NS + 1 : 0; };
@@ -782,6 +795,13 @@ static int g_tc_max_ctas = 0;      // 0 = one persistent CTA per SM
 extern "C" int msacl_rollout_tc_set_max_ctas(int32_t max_ctas) {
   if (max_ctas < 0 || max_ctas > kNumSMs) { set_error("rollout_tc_set_max_ctas: expected 0 (all SMs) .. %d", kNumSMs); return MSACL_ERR_BAD_ARG; }
   g_tc_max_ctas = max_ctas;
+  return MSACL_OK;
+}
+
+extern "C" int msacl_tc_tile_share(int64_t n_envs, int32_t grid, int32_t cta, int64_t* out) {
+  if (n_envs <= 0 || grid <= 0 || cta < 0 || cta >= grid || !out) { set_error("tc_tile_share: bad argument"); return MSACL_ERR_BAD_ARG; }
+  const TcShare sh((n_envs + TCM - 1) / TCM, grid, cta, 3);
+  out[0] = sh.first; out[1] = sh.share; out[2] = sh.rounds; out[3] = sh.per; out[4] = sh.ex;
   return MSACL_OK;
 }
 

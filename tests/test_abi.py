@@ -75,3 +75,32 @@ def test_error_codes_without_gpu_work():
     assert lib.msacl_action_noise(0, 0, 8, 5, 0, None, None) == -2
     n1, n2 = C.c_int64(0), C.c_int64(0)
     assert lib.msacl_tc_pack_bytes(C.byref(n1), C.byref(n2)) == 0 and n1.value == 16384 and n2.value in (262144, 262144 + 148 * 65536)   # + scratch in MSACL_TC_TPW=2 builds
+
+
+@pytest.mark.parametrize("n_envs,grid", [(65536, 148), (1 << 21, 148), (1 << 22, 148), (1000, 8), (128, 1), (129, 2), (70000, 148),
+                                         (148 * 128 * 7 + 700, 148), (1 << 20, 140), (40001, 148), (5, 1)])
+def test_tc_tile_shares_partition_the_tile_list(n_envs, grid):
+    """msacl_rollout_fused_tc deals its 128-env tiles to the persistent CTAs in balanced contiguous shares, walked in rounds of at
+    most 3 tiles (host-side arithmetic shared with the kernel: TcShare in csrc/rollout_tc.cu).  Every tile is owned exactly once,
+    shares differ by at most one tile, round sizes are non-increasing (a warpgroup idle in one round stays idle: the kernel's
+    X-operand counters rely on it) and the number of rounds is the minimum."""
+    import ctypes as C
+    lib = msacl_b200.load_library()
+    tiles = (n_envs + 127) // 128
+    nxt, shares = 0, []
+    for cta in range(grid):
+        out = (C.c_int64 * 5)()
+        assert lib.msacl_tc_tile_share(n_envs, grid, cta, out) == 0
+        first, share, rounds, per, ex = list(out)
+        assert first == nxt, "shares are contiguous and in CTA order"
+        sizes = [per + (1 if j < ex else 0) for j in range(rounds)]
+        assert sum(sizes) == share and all(1 <= s <= 3 for s in sizes)
+        assert sizes == sorted(sizes, reverse=True)
+        assert rounds == -(-share // 3)
+        nxt += share
+        shares.append(share)
+    assert nxt == tiles
+    assert max(shares) - min(shares) <= 1
+    out = (C.c_int64 * 5)()
+    assert lib.msacl_tc_tile_share(n_envs, grid, grid, out) != 0          # cta out of range
+    assert b"tc_tile_share" in lib.msacl_last_error()
